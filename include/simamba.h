@@ -1,0 +1,125 @@
+/* simamba.h - C ABI of libsimamba_b200.so (sm_100a): the B200-native hot path of SI-Mamba's
+ * spectrally-ordered token encoder.
+ *
+ * The reference (denix56/SI-Mamba) is 100% Python; its native boundary sits inside third-party
+ * wheels (mamba-ssm, causal-conv1d, pytorch3d) and ATen/cuSOLVER.  Each entry point below names
+ * the reference call site it replaces (file:line relative to the upstream repo).  The host side
+ * that binds these (si_mamba_b200/_lib.py, ctypes) mirrors the reference's nn.Module API.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative sim_status on failure; the message of the
+ *    last failure on the calling thread is available from sim_last_error_string(); nothing throws.
+ *  - all buffers are caller-allocated DEVICE memory passed as raw pointers with explicit sizes
+ *    and row strides (in elements); no hidden allocation, no host synchronisation; work is
+ *    enqueued on `stream` (a cudaStream_t) of the current device.
+ *  - dtype codes: SIM_F32 = 0, SIM_BF16 = 1.  Index buffers are int32.
+ *  - activation tensors of the Mamba mixer are TOKEN-major: (batch*L, D) row-major with a row
+ *    stride, so the x / z halves of the in_proj output and the B / C column blocks of the x_proj
+ *    output are consumed in place.  mamba-ssm's channel-major (B, D, L) view of the same data is
+ *    a transpose; the Python wrapper accepts both.
+ *  - the library is re-entrant: no global mutable state besides the thread-local error string.
+ */
+#ifndef SIMAMBA_H_
+#define SIMAMBA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sim_stream_t; /* cudaStream_t */
+
+enum sim_status {
+  SIM_STATUS_OK = 0,
+  SIM_STATUS_INVALID = -1,   /* bad argument / unsupported shape */
+  SIM_STATUS_ALIGN = -2,     /* pointer or stride not aligned for vector / TMA access */
+  SIM_STATUS_CUDA = -3,      /* CUDA runtime error (message holds cudaGetErrorString) */
+  SIM_STATUS_WORKSPACE = -4  /* workspace missing or too small */
+};
+
+enum sim_dtype { SIM_F32 = 0, SIM_BF16 = 1 };
+
+/* flags of sim_spectral_eig */
+enum sim_spectral_flags {
+  SIM_GRAPH_SYMMETRIC = 1 << 0,  /* config key `symmetric` */
+  SIM_GRAPH_SELF_LOOP = 1 << 1,  /* config key `self_loop` */
+  SIM_GRAPH_BINARY = 1 << 2,     /* config key `binary` */
+  SIM_EIG_SMALLEST = 1 << 3,     /* config key `smallest` */
+  SIM_LAP_SYMMETRIC = 1 << 4,    /* config key `matrix` != "laplacian": I - D^-1/2 A D^-1/2, first pair dropped */
+  SIM_LAP_EPS_CLAMP = 1 << 5,    /* deg.clamp(min=1e-12) (batched MAE variant) instead of deg + 1e-6 */
+  SIM_EIG_CANONICAL_SIGN = 1 << 6 /* work_order.py:360-365 sign rule (first entry >= 0) */
+};
+
+int sim_version(void);
+const char* sim_last_error_string(void);
+
+/* a-1  Farthest point sampling.  Replaces pytorch3d sample_farthest_points at
+ * models/point_mamba.py:93 (seg: part_segmentation/models/pt_mamba.py:175).
+ * xyz (B,N,3) f32 -> idx (B,G) i32, center (B,G,3) f32.  Start index 0, ties -> lowest index. */
+int sim_fps(const float* xyz, int B, int N, int G, int32_t* idx, float* center, sim_stream_t stream);
+
+/* a-1  kNN grouping + gather + centre subtraction.  Replaces pytorch3d knn_points and the index
+ * gather at models/point_mamba.py:96-110.  idx (B,G,M) i32 ascending point index; nbr (centred)
+ * and nbr_org (B,G,M,3) f32; either of nbr / nbr_org may be NULL. */
+int sim_knn_group(const float* xyz, const float* center, int B, int N, int G, int M, int32_t* idx, float* nbr,
+                  float* nbr_org, sim_stream_t stream);
+
+/* a-3 + a-4 + a-5  centres -> kNN graph -> Laplacian -> k extremal eigenpairs -> argsort.
+ * Replaces create_graph_from_* (models/point_mamba.py:620-715), calc_top_k_eigenvalues_eigenvectors
+ * (:717-761, :3001-3050, symmetric :764-814) and the torch.sort of sort_points_by_fiedler (:817-826).
+ * eigvals (B,k) f32, eigvecs (B,G,k) f32, perm (B,k,G) i32 with perm[b,s,r] = index of the r-th
+ * smallest entry of eigenvector s (ties -> lower index), inv_perm (B,k,G) i32 or NULL,
+ * adjacency (B,G,G) f32 or NULL (the scattered adjacency before symmetrisation). */
+size_t sim_spectral_eig_workspace_bytes(int B, int G, int k);
+int sim_spectral_eig(const float* center, int B, int G, int k_nn, float alpha, int flags, int k, float* eigvals,
+                     float* eigvecs, int32_t* perm, int32_t* inv_perm, float* adjacency, void* workspace,
+                     size_t workspace_bytes, sim_stream_t stream);
+
+/* a-5  stable ascending argsort of fp32 keys along rows (the torch.sort inside
+ * sort_points_by_fiedler, models/point_mamba.py:820).  keys (rows, n) with row stride ld and element
+ * stride es (so a column of (B,G,k) eigenvectors can be sorted in place): perm (rows, n) i32. */
+int sim_argsort_rows(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,
+                     sim_stream_t stream);
+
+/* a-6  SAST order assembly: out[b, s*G+r] = x[b, perm[b,s,r]] and, when reverse, the mirrored copy
+ * (cat + flip + cat at models/point_mamba.py:889-898, 982-989).  x, x2 (B,G,C); o1, o2 (B,T,C) with
+ * T = (reverse ? 2 : 1) * k * G.  x2/o2 may be NULL; x2 != NULL with o2 == NULL writes o1 = x[..] + x2[..]
+ * (tokens + pos of MixerModel.forward, models/point_mamba.py:250, folded into the gather). */
+int sim_order_gather_fwd(const void* x, const void* x2, const int32_t* perm, void* o1, void* o2, int B, int G,
+                         int k, int C, int reverse, int dtype, sim_stream_t stream);
+/* backward of sim_order_gather_fwd w.r.t. x: dx[b,g] = sum over the (reverse ? 2 : 1)*k rows that read g. */
+int sim_order_gather_bwd(const void* dout, const int32_t* inv_perm, void* dx, int B, int G, int k, int C,
+                         int reverse, int dtype, sim_stream_t stream);
+
+/* a-8 / a-16 / a-17  general row gather: out[b,t] = src_idx[b,t] >= 0 ? x[b, src_idx[b,t]] : fill
+ * (fill == NULL -> zeros).  HLT layout (part_segmentation/models/pt_mamba.py:670-723), MAE visible-token
+ * compaction (models/point_mamba.py:2734-2772) and token restore (:3147-3197). */
+int sim_gather_rows(const void* x, const int32_t* src_idx, const void* fill, void* out, int B, int R_in, int R_out,
+                    int C, int dtype, sim_stream_t stream);
+
+/* a-9 / a-13  res_out = x (+ x2) (+ res_in); y = LayerNorm(res_out) * gamma + beta
+ * (models/block.py:56-58; models/point_mamba.py:250, 256-258).  res_* are f32; x2, res_in, res_out may be NULL. */
+int sim_add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                      float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
+                      sim_stream_t stream);
+
+/* a-12  causal depthwise conv1d (+ SiLU).  Replaces causal_conv1d_fn inside Mamba.forward
+ * (models/block.py:72).  x, y (batch*L, D) token-major with row strides; w (D, width) f32; bias (D) f32 or NULL. */
+int sim_causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y,
+                          int batch, int L, int D, int width, int silu, int dtype, sim_stream_t stream);
+
+/* a-11  selective scan forward.  Replaces mamba-ssm selective_scan_fn inside Mamba.forward
+ * (models/block.py:72); semantics of selective_scan_ref.  u, delta, z, out (batch*L, D) token-major;
+ * Bm, Cm (batch*L, N) token-major; A (D,N) f32; Dvec, delta_bias (D) f32 or NULL; z may be NULL.
+ * N must be 16.  variant: 0 = auto, else states per thread (2, 4, 8, 16). */
+int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                           const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
+                           long ld_z, const float* delta_bias, void* out, long ld_out, int batch, int L, int D,
+                           int N, int delta_softplus, int dtype, int variant, sim_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMAMBA_H_ */

@@ -1,0 +1,56 @@
+"""Oracle: MAE mask / masked spectral sort / token restore.
+
+Test infrastructure (see oracle/__init__.py).  Follows models/point_mamba.py:
+  * _mask_center_rand           :2232-2255  (m = int(mask_ratio * G) ones, shuffled per cloud)
+  * masked sort (MaskMamba_3)   :2734-2796  (per order: sort tokens+mask, keep ~mask rows in order;
+                                             cat k orders; cat(seq, flip(seq)))
+  * token restore               :3147-3197  (x_full[mask] = mask_token, x_full[~mask] = x_vis rows in order)
+"""
+
+from __future__ import annotations
+
+import torch
+
+
+def mask_full(mask: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """mask (B,G) bool, perm (B,k,G) -> mask_full (B,2kG): cat_s mask[perm[s]] then cat(m, flip(m)) (:2795-2796)."""
+    B, k, G = perm.shape
+    m = torch.gather(mask, 1, perm.reshape(B, k * G))
+    return torch.cat((m, m.flip(1)), dim=1)
+
+
+def compact_visible(x: torch.Tensor, perm: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """x (B,G,C) -> x_vis (B, 2k*n_vis, C): visible rows of each sorted copy, order preserved, then flip+cat."""
+    B, k, G = perm.shape
+    C = x.shape[-1]
+    seq = torch.gather(x, 1, perm.reshape(B, k * G)[..., None].expand(-1, -1, C))
+    m = torch.gather(mask, 1, perm.reshape(B, k * G))
+    vis = seq[~m].reshape(B, -1, C)
+    return torch.cat((vis, vis.flip(1)), dim=1)
+
+
+def restore(x_vis: torch.Tensor, mfull: torch.Tensor, mask_token: torch.Tensor) -> torch.Tensor:
+    """Token restore (:3147-3197): x_full[b,t] = mask_token if mfull[b,t] else x_vis[b, rank_vis(b,t)]."""
+    B, T = mfull.shape
+    C = x_vis.shape[-1]
+    rank = torch.cumsum((~mfull).to(torch.int64), dim=1) - 1
+    rank = rank.clamp(min=0)
+    gathered = torch.gather(x_vis, 1, rank[..., None].expand(-1, -1, C))
+    return torch.where(mfull[..., None], mask_token.reshape(1, 1, C).to(x_vis.dtype), gathered)
+
+
+def gather_masked(x_full: torch.Tensor, mfull: torch.Tensor) -> torch.Tensor:
+    """x_rec = x_full[mask_full] reshaped (B, 2k*m, C) (:3194-3197)."""
+    B = x_full.shape[0]
+    return x_full[mfull].reshape(B, -1, x_full.shape[-1])
+
+
+def rand_mask(B: int, G: int, mask_ratio: float, seed: int) -> torch.Tensor:
+    """_mask_center_rand (:2232-2255) with a torch generator instead of numpy's global RNG."""
+    g = torch.Generator().manual_seed(seed)
+    m = int(mask_ratio * G)
+    out = torch.zeros(B, G, dtype=torch.bool)
+    for b in range(B):
+        p = torch.randperm(G, generator=g)
+        out[b, p[:m]] = True
+    return out

@@ -1,0 +1,91 @@
+"""ctypes binding of libsimamba_b200.so (the C ABI in include/simamba.h).
+
+There is NO fallback: if the shared library is missing, or a call returns a
+non-zero status, a RuntimeError is raised.  The library is built in-tree by
+``python -m si_mamba_b200.build`` (``__graft_entry__.build()``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libsimamba_b200.so"
+
+SIM_F32, SIM_BF16 = 0, 1
+
+# sim_spectral_flags
+GRAPH_SYMMETRIC = 1 << 0
+GRAPH_SELF_LOOP = 1 << 1
+GRAPH_BINARY = 1 << 2
+EIG_SMALLEST = 1 << 3
+LAP_SYMMETRIC = 1 << 4
+LAP_EPS_CLAMP = 1 << 5
+EIG_CANONICAL_SIGN = 1 << 6
+
+_p, _i, _l, _f, _sz = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/simamba.h declares
+SIGNATURES = {
+    "sim_version": (_i, []),
+    "sim_last_error_string": (C.c_char_p, []),
+    "sim_fps": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "sim_knn_group": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "sim_spectral_eig_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sim_spectral_eig": (_i, [_p, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sim_argsort_rows": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
+    "sim_order_gather_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_order_gather_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_gather_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "sim_add_layernorm": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _f, _i, _i, _p]),
+    "sim_causal_conv1d_fwd": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_selective_scan_fwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l,
+                                    _i, _i, _i, _i, _i, _i, _i, _p]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and bind every entry point.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m si_mamba_b200.build` "
+            "(there is no CPU or PyTorch fallback for the si-mamba hot path)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class SimError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().sim_last_error_string().decode(errors="replace")
+        raise SimError(f"{what} failed with status {status}: {msg}")
+
+
+def launches() -> int:
+    """Number of kernels this process has launched through the C ABI (bench.py's gpu_launches claim)."""
+    return _launch_count[0]
+
+
+_launch_count = [0]
+
+
+def call(name: str, *args) -> None:
+    _launch_count[0] += 1
+    check(getattr(load(), name)(*args), name)

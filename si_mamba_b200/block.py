@@ -1,0 +1,68 @@
+"""``Block``: Add -> LayerNorm -> mixer, the reference's models/block.py:17-76 interface
+(ctor arguments, forward(hidden_states, residual, inference_params) -> (hidden_states, residual),
+attributes .mixer / .norm / .drop_path / .layer_idx).
+
+B200 path: the residual add and the LayerNorm run as ONE kernel (sim_add_layernorm) that reads
+hidden + residual once and writes the fp32 residual stream and the normalised activations; the
+reference issues them as separate ATen kernels (its Triton fused_add_norm is never enabled).
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from .autograd import _amp_dtype
+
+
+class DropPath(nn.Module):
+    """timm 0.4.5 DropPath semantics (per-sample Bernoulli, scale 1/keep), train mode only."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+        mask = (keep + torch.rand(shape, dtype=x.dtype, device=x.device)).floor_()
+        return x.div(keep) * mask
+
+
+def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor], want_residual: bool = True):
+    """(LayerNorm(hidden + residual), hidden + residual) through the CUDA kernel when no autograd graph is
+    needed; plain torch ops (so autograd works) when training."""
+    needs_grad = torch.is_grad_enabled() and (hidden.requires_grad or (residual is not None and residual.requires_grad)
+                                              or norm.weight.requires_grad)
+    if needs_grad or not isinstance(norm, nn.LayerNorm):
+        res = hidden + residual if residual is not None else hidden
+        res = res.float() if res.dtype != torch.float32 else res
+        return norm(res.to(dtype=norm.weight.dtype)), res
+    return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=_amp_dtype(hidden),
+                             want_residual=want_residual)
+
+
+class Block(nn.Module):
+    def __init__(self, dim, mixer_cls, norm_cls=nn.LayerNorm, fused_add_norm=False, residual_in_fp32=False,
+                 drop_path=0.):
+        super().__init__()
+        self.residual_in_fp32 = residual_in_fp32
+        self.fused_add_norm = fused_add_norm  # kept for signature parity; the CUDA add+LN is always used in eval
+        self.mixer = mixer_cls(dim)
+        self.norm = norm_cls(dim)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+
+    def forward(self, hidden_states: Tensor, residual: Optional[Tensor] = None, inference_params=None):
+        """residual = drop_path(hidden) + residual; hidden = mixer(LN(residual)).  block.py:47-73."""
+        hidden_states, residual = fused_add_norm(self.norm, self.drop_path(hidden_states), residual)
+        hidden_states = self.mixer(hidden_states, inference_params=inference_params)
+        return hidden_states, residual
+
+    def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
+        return self.mixer.allocate_inference_cache(batch_size, max_seqlen, dtype=dtype, **kwargs)

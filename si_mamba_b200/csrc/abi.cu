@@ -1,0 +1,123 @@
+// extern "C" surface of libsimamba_b200.so - see include/simamba.h for the contract and the
+// reference call site each entry point replaces.  No torch types, no exceptions across the ABI.
+
+#include <stdarg.h>
+
+#include "../../include/simamba.h"
+#include "kernels.cuh"
+
+namespace sim {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the sticky-less error so the next call starts clean
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SIM_ERR_CUDA;
+  }
+  return SIM_OK;
+}
+
+}  // namespace sim
+
+using sim::SIM_ERR_INVALID;
+
+extern "C" {
+
+int sim_version(void) { return 100; }
+
+const char* sim_last_error_string(void) { return sim::g_err; }
+
+int sim_fps(const float* xyz, int B, int N, int G, int32_t* idx, float* center, sim_stream_t stream) {
+  return sim::fps(xyz, B, N, G, idx, center, static_cast<cudaStream_t>(stream));
+}
+
+int sim_knn_group(const float* xyz, const float* center, int B, int N, int G, int M, int32_t* idx, float* nbr,
+                  float* nbr_org, sim_stream_t stream) {
+  return sim::knn_group(xyz, center, B, N, G, M, idx, nbr, nbr_org, static_cast<cudaStream_t>(stream));
+}
+
+size_t sim_spectral_eig_workspace_bytes(int B, int G, int k) { return sim::spectral_workspace_bytes(B, G, k); }
+
+int sim_spectral_eig(const float* center, int B, int G, int k_nn, float alpha, int flags, int k, float* eigvals,
+                     float* eigvecs, int32_t* perm, int32_t* inv_perm, float* adjacency, void* workspace,
+                     size_t workspace_bytes, sim_stream_t stream) {
+  sim::SpectralParams P;
+  memset(&P, 0, sizeof(P));
+  P.center = center;
+  P.eigvals = eigvals;
+  P.eigvecs = eigvecs;
+  P.perm = perm;
+  P.inv_perm = inv_perm;
+  P.adjacency = adjacency;
+  P.B = B, P.G = G, P.k_nn = k_nn, P.k = k;
+  P.alpha = alpha;
+  P.symmetric = (flags & SIM_GRAPH_SYMMETRIC) != 0;
+  P.self_loop = (flags & SIM_GRAPH_SELF_LOOP) != 0;
+  P.binary = (flags & SIM_GRAPH_BINARY) != 0;
+  P.smallest = (flags & SIM_EIG_SMALLEST) != 0;
+  P.matrix_sym = (flags & SIM_LAP_SYMMETRIC) != 0;
+  P.eps_clamp = (flags & SIM_LAP_EPS_CLAMP) != 0;
+  P.sign_rule = (flags & SIM_EIG_CANONICAL_SIGN) != 0;
+  return sim::spectral_eig(P, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sim_argsort_rows(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,
+                     sim_stream_t stream) {
+  return sim::argsort_rows(keys, ld, es, rows, n, perm, inv_perm, static_cast<cudaStream_t>(stream));
+}
+
+int sim_order_gather_fwd(const void* x, const void* x2, const int32_t* perm, void* o1, void* o2, int B, int G,
+                         int k, int C, int reverse, int dtype, sim_stream_t stream) {
+  return sim::order_gather_fwd(x, x2, perm, o1, o2, B, G, k, C, reverse, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_order_gather_bwd(const void* dout, const int32_t* inv_perm, void* dx, int B, int G, int k, int C,
+                         int reverse, int dtype, sim_stream_t stream) {
+  return sim::order_gather_bwd(dout, inv_perm, dx, B, G, k, C, reverse, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_gather_rows(const void* x, const int32_t* src_idx, const void* fill, void* out, int B, int R_in, int R_out,
+                    int C, int dtype, sim_stream_t stream) {
+  return sim::gather_rows(x, src_idx, fill, out, B, R_in, R_out, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                      float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
+                      sim_stream_t stream) {
+  return sim::add_layernorm(x, x2, res_in, gamma, beta, res_out, y, rows, C, eps, dtype_x, dtype_y,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int sim_causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y,
+                          int batch, int L, int D, int width, int silu, int dtype, sim_stream_t stream) {
+  return sim::causal_conv1d_fwd(x, ld_x, w, bias, y, ld_y, batch, L, D, width, silu, dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                           const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
+                           long ld_z, const float* delta_bias, void* out, long ld_out, int batch, int L, int D,
+                           int N, int delta_softplus, int dtype, int variant, sim_stream_t stream) {
+  if (N != 16) {
+    sim::set_error("sim_selective_scan_fwd: d_state must be 16 (got %d)", N);
+    return SIM_ERR_INVALID;
+  }
+  sim::ScanParams p;
+  p.u = u, p.delta = delta, p.z = z, p.Bm = Bm, p.Cm = Cm, p.out = out;
+  p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
+  p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_out = ld_out;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  return sim::selective_scan_fwd(p, dtype, variant, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

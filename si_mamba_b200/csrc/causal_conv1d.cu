@@ -1,0 +1,121 @@
+// Causal depthwise conv1d (+ SiLU), forward and backward.
+//
+// Replaces causal-conv1d's causal_conv1d_fn as SI-Mamba reaches it through
+// Mamba.forward (models/block.py:72).  Semantics (oracle/mamba.py causal_conv1d_ref):
+//   y[b,t,d] = act(bias[d] + sum_{j<W} w[d,j] * x[b, t-(W-1)+j, d]),  x = 0 for t < 0.
+//
+// Layout: token-major (batch*L, D) with explicit row strides, so x is consumed
+// in place as the first D columns of the in_proj output.  Each thread owns 4
+// adjacent channels (one 16-byte / 8-byte vector) and slides a W-tap register
+// window down a chunk of TC time steps: every load is a fully coalesced row
+// segment, the only re-read is the (W-1)-row halo per chunk.
+// Roofline: HBM, algorithmic bytes 2*B*L*D*s forward, 3*B*L*D*s backward.
+
+#include "kernels.cuh"
+
+namespace sim {
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using type = float4;
+  __device__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  __device__ static float4 load(const __nv_bfloat16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  __device__ static void store(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+constexpr int kConvW = 4;
+
+template <typename T, int TC>
+__global__ void __launch_bounds__(256) causal_conv1d_fwd_kernel(const T* __restrict__ x, long ld_x,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ bias, T* __restrict__ y,
+                                                                long ld_y, int batch, int L, int D, int silu) {
+  const int nv = D / 4;
+  const int nchunk = (L + TC - 1) / TC;
+  const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long)batch * nchunk * nv) return;
+  const int v = item % nv;
+  const int ch = (item / nv) % nchunk;
+  const int b = item / ((long)nv * nchunk);
+  const int d0 = v * 4;
+  const int t0 = ch * TC;
+  const int t1 = min(L, t0 + TC);
+
+  float wr[4][kConvW];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long)(d0 + c) * kConvW);
+    wr[c][0] = wv.x, wr[c][1] = wv.y, wr[c][2] = wv.z, wr[c][3] = wv.w;
+  }
+  float4 bv = bias ? *reinterpret_cast<const float4*>(bias + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const T* xb = x + ((long)b * L) * ld_x + d0;
+  T* yb = y + ((long)b * L) * ld_y + d0;
+  float4 win[kConvW];  // win[j] = x[t - (W-1) + j]
+#pragma unroll
+  for (int j = 0; j < kConvW - 1; ++j) {
+    const int t = t0 - (kConvW - 1) + j;
+    win[j + 1] = t >= 0 ? Vec4<T>::load(xb + (long)t * ld_x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int j = 0; j < kConvW - 1; ++j) win[j] = win[j + 1];
+    win[kConvW - 1] = Vec4<T>::load(xb + (long)t * ld_x);
+    float4 acc = bv;
+#pragma unroll
+    for (int j = 0; j < kConvW; ++j) {
+      acc.x = fmaf(wr[0][j], win[j].x, acc.x);
+      acc.y = fmaf(wr[1][j], win[j].y, acc.y);
+      acc.z = fmaf(wr[2][j], win[j].z, acc.z);
+      acc.w = fmaf(wr[3][j], win[j].w, acc.w);
+    }
+    if (silu) {
+      acc.x = silu_f(acc.x), acc.y = silu_f(acc.y), acc.z = silu_f(acc.z), acc.w = silu_f(acc.w);
+    }
+    Vec4<T>::store(yb + (long)t * ld_y, acc);
+  }
+}
+
+int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y, int batch,
+                      int L, int D, int width, int silu, int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(width == kConvW, SIM_ERR_INVALID, "causal_conv1d_fwd: only width 4 is built (got %d)", width);
+  SIM_REQUIRE(D % 4 == 0 && batch > 0 && L > 0, SIM_ERR_INVALID, "causal_conv1d_fwd: D must be a multiple of 4");
+  SIM_REQUIRE(dtype == 0 || dtype == 1, SIM_ERR_INVALID, "causal_conv1d_fwd: dtype must be 0 (fp32) or 1 (bf16)");
+  const int es = dtype == 0 ? 4 : 2;
+  const uintptr_t vmask = 4 * es - 1;
+  SIM_REQUIRE(((uintptr_t)x & vmask) == 0 && ((uintptr_t)y & vmask) == 0 && aligned16(w) && ld_x % 4 == 0 &&
+                  ld_y % 4 == 0 && (!bias || aligned16(bias)),
+              SIM_ERR_ALIGN, "causal_conv1d_fwd: x/y/w/bias need 16-byte bases and vector-aligned row strides");
+  constexpr int TC = 32;
+  const long items = (long)batch * ((L + TC - 1) / TC) * (D / 4);
+  const int grid = (int)((items + 255) / 256);
+  if (dtype == 0)
+    causal_conv1d_fwd_kernel<float, TC><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld_x, w, bias,
+                                                                  static_cast<float*>(y), ld_y, batch, L, D, silu);
+  else
+    causal_conv1d_fwd_kernel<__nv_bfloat16, TC><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<__nv_bfloat16*>(y), ld_y, batch, L, D, silu);
+  return check_launch("causal_conv1d_fwd");
+}
+
+}  // namespace sim

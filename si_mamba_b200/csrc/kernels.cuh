@@ -1,0 +1,57 @@
+// Internal (C++) interface between abi.cu and the kernel translation units.
+#pragma once
+
+#include "common.cuh"
+
+namespace sim {
+
+// implemented in the kernel translation units
+int fps(const float*, int, int, int, int*, float*, cudaStream_t);
+int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t);
+int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
+                  int, int, cudaStream_t);
+int order_gather_fwd(const void*, const void*, const int*, void*, void*, int, int, int, int, int, int, cudaStream_t);
+int order_gather_bwd(const void*, const int*, void*, int, int, int, int, int, int, cudaStream_t);
+int gather_rows(const void*, const int*, const void*, void*, int, int, int, int, int, cudaStream_t);
+int argsort_rows(const float*, long, long, int, int, int*, int*, cudaStream_t);
+int causal_conv1d_fwd(const void*, long, const float*, const float*, void*, long, int, int, int, int, int, int,
+                      cudaStream_t);
+
+struct ScanParams {
+  const void* u;
+  const void* delta;
+  const void* z;
+  const void* Bm;
+  const void* Cm;
+  void* out;
+  const float* A;
+  const float* Dv;
+  const float* dbias;
+  long ld_u, ld_delta, ld_z, ld_B, ld_C, ld_out;
+  int batch, L, D;
+  int softplus;
+};
+int selective_scan_fwd(const ScanParams&, int, int, cudaStream_t);
+
+struct SpectralParams {
+  const float* center;
+  float* eigvals;
+  float* eigvecs;
+  int* perm;
+  int* inv_perm;
+  float* adjacency;
+  double* ws_mat;
+  float* ws_adj;
+  int B, G, k_nn, k;
+  float alpha;
+  int symmetric, self_loop, binary;
+  int matrix_sym;
+  int eps_clamp;
+  int smallest;
+  int sign_rule;
+  int lu_alias;
+};
+size_t spectral_workspace_bytes(int, int, int);
+int spectral_eig(SpectralParams, void*, size_t, cudaStream_t);
+
+}  // namespace sim

@@ -1,0 +1,343 @@
+// Row-granular HBM-bound kernels: residual add + LayerNorm, spectral order
+// gather (+ reverse), general row gather (HLT / MAE restore), token mean.
+//
+// Reference rows:
+//   a-9   Block.forward add + LayerNorm           models/block.py:56-58
+//   a-13  MixerModel.forward tokens + pos, norm_f models/point_mamba.py:250,256-258
+//   a-5/6 sort_points_by_fiedler gather + cat + flip  models/point_mamba.py:817-826, 889-898, 982-989
+//   a-8   HLT layout                              part_segmentation/models/pt_mamba.py:670-723
+//   a-17  MAE token restore                       models/point_mamba.py:3147-3197
+// One warp moves one row with 16-byte vector accesses; rows are C <= 1024*... floats.
+
+#include "kernels.cuh"
+
+namespace sim {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// ----------------------------------------------------------------------------- add + LayerNorm
+// res_out = x (+ res_in) [(+ x2)];  y = LN(res_out) * gamma + beta.  Statistics in fp32, two-pass in registers.
+// MAXV = float4 vectors per lane (C <= 128 * MAXV).
+template <typename TX, typename TY, int MAXV>
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict__ x, const TX* __restrict__ x2,
+                                                            const float* __restrict__ res_in,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            float* __restrict__ res_out, TY* __restrict__ y,
+                                                            long rows, int C, float eps) {
+  const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C / 4;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nv) {
+      float4 a = ld4<TX>(x + row * C + 4 * q);
+      if (x2) {
+        const float4 c = ld4<TX>(x2 + row * C + 4 * q);
+        a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+      }
+      if (res_in) {
+        const float4 r = *reinterpret_cast<const float4*>(res_in + row * C + 4 * q);
+        a.x += r.x, a.y += r.y, a.z += r.z, a.w += r.w;
+      }
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+      if (res_out) *reinterpret_cast<float4*>(res_out + row * C + 4 * q) = a;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nv) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * q);
+      const float4 bb = *reinterpret_cast<const float4*>(beta + 4 * q);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+      st4<TY>(y + row * C + 4 * q, o);
+    }
+  }
+}
+
+int add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                  float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
+                  cudaStream_t stream) {
+  SIM_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
+              "add_layernorm: C must be a multiple of 4 and <= 1024 (got %d)", C);
+  SIM_REQUIRE(x && gamma && beta && y, SIM_ERR_INVALID, "add_layernorm: null tensor");
+  SIM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!x2 || aligned16(x2)) &&
+                  (!res_in || aligned16(res_in)) && (!res_out || aligned16(res_out)),
+              SIM_ERR_ALIGN, "add_layernorm: tensors must be 16-byte aligned");
+  const int grid = (int)((rows + 7) / 8);
+#define SIM_LN_LAUNCH(TX, TY, MAXV)                                                                          \
+  add_layernorm_kernel<TX, TY, MAXV><<<grid, 256, 0, stream>>>(static_cast<const TX*>(x),                    \
+                                                               static_cast<const TX*>(x2), res_in, gamma,    \
+                                                               beta, res_out, static_cast<TY*>(y), rows, C, eps)
+#define SIM_LN_MAXV(TX, TY)                     \
+  if (C <= 384) {                               \
+    SIM_LN_LAUNCH(TX, TY, 3);                   \
+  } else if (C <= 512) {                        \
+    SIM_LN_LAUNCH(TX, TY, 4);                   \
+  } else {                                      \
+    SIM_LN_LAUNCH(TX, TY, 8);                   \
+  }
+  if (dtype_x == 0 && dtype_y == 0) {
+    SIM_LN_MAXV(float, float)
+  } else if (dtype_x == 0 && dtype_y == 1) {
+    SIM_LN_MAXV(float, __nv_bfloat16)
+  } else if (dtype_x == 1 && dtype_y == 1) {
+    SIM_LN_MAXV(__nv_bfloat16, __nv_bfloat16)
+  } else if (dtype_x == 1 && dtype_y == 0) {
+    SIM_LN_MAXV(__nv_bfloat16, float)
+  } else {
+    set_error("add_layernorm: bad dtype codes %d/%d", dtype_x, dtype_y);
+    return SIM_ERR_INVALID;
+  }
+#undef SIM_LN_MAXV
+#undef SIM_LN_LAUNCH
+  return check_launch("add_layernorm");
+}
+
+// ----------------------------------------------------------------------------- SAST order gather
+// out[b, s*G + r, :] = x[b, perm[b,s,r], :] (+ x2[...]) and, if reverse, the mirrored row
+// out[b, 2kG-1-(s*G+r), :] gets the same data: each source row is read once and written twice.
+template <typename T>
+__global__ void __launch_bounds__(256) order_gather_kernel(const T* __restrict__ x, const T* __restrict__ x2,
+                                                           const int* __restrict__ perm, T* __restrict__ o1,
+                                                           T* __restrict__ o2, int B, int G, int k, int C,
+                                                           int reverse) {
+  const long w = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  const long total = (long)B * k * G;
+  if (w >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / ((long)k * G);
+  const int t = w % ((long)k * G);
+  const int src = perm[w];
+  const long T_out = (long)(reverse ? 2 : 1) * k * G;
+  const T* xr = x + ((long)b * G + src) * C;
+  const T* x2r = x2 ? x2 + ((long)b * G + src) * C : nullptr;
+  T* d1 = o1 + ((long)b * T_out + t) * C;
+  T* d1m = o1 + ((long)b * T_out + (T_out - 1 - t)) * C;
+  T* d2 = o2 ? o2 + ((long)b * T_out + t) * C : nullptr;
+  T* d2m = o2 ? o2 + ((long)b * T_out + (T_out - 1 - t)) * C : nullptr;
+  for (int q = lane; q < C / 4; q += 32) {
+    float4 a = ld4<T>(xr + 4 * q);
+    if (x2r) {
+      const float4 c = ld4<T>(x2r + 4 * q);
+      if (d2) {
+        st4<T>(d2 + 4 * q, c);
+        if (reverse) st4<T>(d2m + 4 * q, c);
+      } else {
+        a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+      }
+    }
+    st4<T>(d1 + 4 * q, a);
+    if (reverse) st4<T>(d1m + 4 * q, a);
+  }
+}
+
+int order_gather_fwd(const void* x, const void* x2, const int* perm, void* o1, void* o2, int B, int G, int k, int C,
+                     int reverse, int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(B > 0 && G > 0 && k > 0 && C > 0 && C % 4 == 0, SIM_ERR_INVALID,
+              "order_gather_fwd: C must be a multiple of 4");
+  SIM_REQUIRE(x && perm && o1 && (!o2 || x2), SIM_ERR_INVALID, "order_gather_fwd: null tensor / o2 without x2");
+  SIM_REQUIRE(aligned16(x) && aligned16(o1) && (!x2 || aligned16(x2)) && (!o2 || aligned16(o2)), SIM_ERR_ALIGN,
+              "order_gather_fwd: tensors must be 16-byte aligned");
+  const long rows = (long)B * k * G;
+  const int grid = (int)((rows + 7) / 8);
+  if (dtype == 0)
+    order_gather_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<const float*>(x2),
+                                                         perm, static_cast<float*>(o1), static_cast<float*>(o2), B,
+                                                         G, k, C, reverse);
+  else if (dtype == 1)
+    order_gather_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), perm,
+        static_cast<__nv_bfloat16*>(o1), static_cast<__nv_bfloat16*>(o2), B, G, k, C, reverse);
+  else {
+    set_error("order_gather_fwd: bad dtype %d", dtype);
+    return SIM_ERR_INVALID;
+  }
+  return check_launch("order_gather_fwd");
+}
+
+// ----------------------------------------------------------------------------- general row gather
+// out[b, t, :] = src_idx[b,t] >= 0 ? x[b, src_idx[b,t], :] : fill (zeros when fill == nullptr).
+// Serves the HLT layout (zero tokens), MAE restore (fill = mask_token) and MAE compaction.
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ x, const int* __restrict__ src_idx,
+                                                          const T* __restrict__ fill, T* __restrict__ out, int B,
+                                                          int R_in, int R_out, int C) {
+  const long w = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  if (w >= (long)B * R_out) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / R_out;
+  const int src = src_idx[w];
+  T* d = out + w * C;
+  if (src >= 0) {
+    const T* xr = x + ((long)b * R_in + src) * C;
+    for (int q = lane; q < C / 4; q += 32) st4<T>(d + 4 * q, ld4<T>(xr + 4 * q));
+  } else if (fill) {
+    for (int q = lane; q < C / 4; q += 32) st4<T>(d + 4 * q, ld4<T>(fill + 4 * q));
+  } else {
+    for (int q = lane; q < C / 4; q += 32) st4<T>(d + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+int gather_rows(const void* x, const int* src_idx, const void* fill, void* out, int B, int R_in, int R_out, int C,
+                int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(B > 0 && R_in > 0 && R_out > 0 && C > 0 && C % 4 == 0, SIM_ERR_INVALID,
+              "gather_rows: C must be a multiple of 4");
+  SIM_REQUIRE(x && src_idx && out, SIM_ERR_INVALID, "gather_rows: null tensor");
+  SIM_REQUIRE(aligned16(x) && aligned16(out) && (!fill || aligned16(fill)), SIM_ERR_ALIGN,
+              "gather_rows: tensors must be 16-byte aligned");
+  const long rows = (long)B * R_out;
+  const int grid = (int)((rows + 7) / 8);
+  if (dtype == 0)
+    gather_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), src_idx,
+                                                        static_cast<const float*>(fill), static_cast<float*>(out), B,
+                                                        R_in, R_out, C);
+  else if (dtype == 1)
+    gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), src_idx, static_cast<const __nv_bfloat16*>(fill),
+        static_cast<__nv_bfloat16*>(out), B, R_in, R_out, C);
+  else {
+    set_error("gather_rows: bad dtype %d", dtype);
+    return SIM_ERR_INVALID;
+  }
+  return check_launch("gather_rows");
+}
+
+// ----------------------------------------------------------------------------- order gather backward
+// dx[b,g,:] = sum_s dout[b, s*G + inv[b,s,g], :] (+ the mirrored row when reverse): a gather over the
+// inverse permutations - deterministic, no atomics (every source row is read by exactly (1|2)*k output rows).
+template <typename T>
+__global__ void __launch_bounds__(256) order_gather_bwd_kernel(const T* __restrict__ dout,
+                                                               const int* __restrict__ inv_perm, T* __restrict__ dx,
+                                                               int B, int G, int k, int C, int reverse) {
+  const long w = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  if (w >= (long)B * G) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / G, g = w % G;
+  const long T_out = (long)(reverse ? 2 : 1) * k * G;
+  for (int q = lane; q < C / 4; q += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < k; ++s) {
+      const long t = (long)s * G + inv_perm[((long)b * k + s) * G + g];
+      float4 a = ld4<T>(dout + ((long)b * T_out + t) * C + 4 * q);
+      acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+      if (reverse) {
+        a = ld4<T>(dout + ((long)b * T_out + (T_out - 1 - t)) * C + 4 * q);
+        acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+      }
+    }
+    st4<T>(dx + w * C + 4 * q, acc);
+  }
+}
+
+int order_gather_bwd(const void* dout, const int* inv_perm, void* dx, int B, int G, int k, int C, int reverse,
+                     int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(B > 0 && G > 0 && k > 0 && C > 0 && C % 4 == 0, SIM_ERR_INVALID,
+              "order_gather_bwd: C must be a multiple of 4");
+  SIM_REQUIRE(dout && inv_perm && dx, SIM_ERR_INVALID, "order_gather_bwd: null tensor");
+  SIM_REQUIRE(aligned16(dout) && aligned16(dx), SIM_ERR_ALIGN, "order_gather_bwd: tensors must be 16-byte aligned");
+  const long rows = (long)B * G;
+  const int grid = (int)((rows + 7) / 8);
+  if (dtype == 0)
+    order_gather_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(dout), inv_perm,
+                                                             static_cast<float*>(dx), B, G, k, C, reverse);
+  else if (dtype == 1)
+    order_gather_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                                     inv_perm, static_cast<__nv_bfloat16*>(dx), B, G,
+                                                                     k, C, reverse);
+  else {
+    set_error("order_gather_bwd: bad dtype %d", dtype);
+    return SIM_ERR_INVALID;
+  }
+  return check_launch("order_gather_bwd");
+}
+
+// ----------------------------------------------------------------------------- stable argsort of rows
+// One warp per row, keys staged in shared memory, rank counting on (key, index).
+__global__ void __launch_bounds__(256) argsort_rows_kernel(const float* __restrict__ keys, long ld, long es, int rows,
+                                                           int n, int* __restrict__ perm,
+                                                           int* __restrict__ inv_perm) {
+  extern __shared__ float s_keys[];  // 8 * n
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  float* kbuf = s_keys + (size_t)warp * n;
+  for (int i = lane; i < n; i += 32) kbuf[i] = keys[row * ld + (long)i * es];
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float ki = kbuf[i];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) {
+      const float kq = kbuf[q];
+      rank += (kq < ki) || (kq == ki && q < i);
+    }
+    perm[row * n + rank] = i;
+    if (inv_perm) inv_perm[row * n + i] = rank;
+  }
+}
+
+int argsort_rows(const float* keys, long ld, long es, int rows, int n, int* perm, int* inv_perm,
+                 cudaStream_t stream) {
+  SIM_REQUIRE(rows > 0 && n > 0 && n <= 4096, SIM_ERR_INVALID, "argsort_rows: n must be in [1, 4096] (got %d)", n);
+  SIM_REQUIRE(keys && perm, SIM_ERR_INVALID, "argsort_rows: null tensor");
+  const size_t smem = (size_t)8 * n * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(argsort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  argsort_rows_kernel<<<(rows + 7) / 8, 256, smem, stream>>>(keys, ld, es, rows, n, perm, inv_perm);
+  return check_launch("argsort_rows");
+}
+
+}  // namespace sim

@@ -1,0 +1,197 @@
+// Farthest-point sampling and kNN patch grouping.
+//
+// Replaces pytorch3d sample_farthest_points / knn_points as called by
+// Group.forward (models/point_mamba.py:93-110; seg twin pt_mamba.py:175-191).
+// Contract (oracle/tokenizer.py): squared distance ((dx*dx)+(dy*dy))+(dz*dz)
+// with separately rounded fp32 products and sums (no FMA contraction), ties
+// towards the lower point index; FPS starts at index 0; the kNN result is the
+// SET of the M smallest (distance, index) pairs, emitted in ascending index order.
+//
+// Both kernels are latency / SM-issue bound (HBM traffic is a few hundred KB):
+// FPS is a chain of G serial arg-max steps, one CTA per cloud, points and
+// running minima in registers, REDUX-based warp arg-max on the float bit
+// pattern and one __syncthreads per step; kNN runs one warp per centre with
+// the cloud staged in shared memory and selects the M-th smallest distance by
+// a 31-step MSB-first radix descent on the bit pattern.
+
+#include "kernels.cuh"
+
+namespace sim {
+
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ----------------------------------------------------------------------------- FPS
+template <int NT, int PPT>
+__global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, int N, int G, int* __restrict__ idx,
+                                                 float* __restrict__ center) {
+  extern __shared__ float s_xyz[];  // N*3
+  constexpr int NW = NT / 32;
+  __shared__ unsigned s_bits[2][NW];
+  __shared__ unsigned s_idx[2][NW];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* src = xyz + (long)b * N * 3;
+  for (int i = tid; i < N * 3; i += NT) s_xyz[i] = src[i];
+  __syncthreads();
+
+  float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = tid + j * NT;
+    if (i < N) {
+      px[j] = s_xyz[3 * i], py[j] = s_xyz[3 * i + 1], pz[j] = s_xyz[3 * i + 2];
+      md[j] = __int_as_float(0x7f800000);  // +inf
+    } else {
+      px[j] = py[j] = pz[j] = 0.f;
+      md[j] = 0.f;  // padding can never beat a real point (index tie-break)
+    }
+  }
+  unsigned last = 0;
+  for (int g = 0; g < G; ++g) {
+    if (tid == 0) {
+      idx[(long)b * G + g] = (int)last;
+      center[((long)b * G + g) * 3 + 0] = s_xyz[3 * last];
+      center[((long)b * G + g) * 3 + 1] = s_xyz[3 * last + 1];
+      center[((long)b * G + g) * 3 + 2] = s_xyz[3 * last + 2];
+    }
+    if (g == G - 1) break;
+    const float wx = s_xyz[3 * last], wy = s_xyz[3 * last + 1], wz = s_xyz[3 * last + 2];
+    unsigned best_bits = 0, best_idx = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int i = tid + j * NT;
+      const float d = sqdist3(px[j], py[j], pz[j], wx, wy, wz);
+      md[j] = fminf(md[j], d);
+      const unsigned bits = __float_as_uint(md[j]);
+      if (i < N && (best_idx == 0xffffffffu || bits > best_bits)) {  // strict >: keeps the lowest own index
+        best_bits = bits;
+        best_idx = (unsigned)i;
+      }
+    }
+    // warp arg-max on (bits desc, idx asc)
+    unsigned m = __reduce_max_sync(0xffffffffu, best_bits);
+    unsigned cand = (best_bits == m) ? best_idx : 0xffffffffu;
+    unsigned mi = __reduce_min_sync(0xffffffffu, cand);
+    const int buf = g & 1;
+    if (lane == 0) {
+      s_bits[buf][warp] = m;
+      s_idx[buf][warp] = mi;
+    }
+    __syncthreads();
+    unsigned wb = lane < NW ? s_bits[buf][lane] : 0u;
+    unsigned wi = lane < NW ? s_idx[buf][lane] : 0xffffffffu;
+    m = __reduce_max_sync(0xffffffffu, wb);
+    cand = (wb == m) ? wi : 0xffffffffu;
+    last = __reduce_min_sync(0xffffffffu, cand);
+  }
+}
+
+int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStream_t stream) {
+  SIM_REQUIRE(B > 0 && N > 0 && G > 0 && G <= N, SIM_ERR_INVALID, "fps: need 0 < G <= N (G=%d N=%d)", G, N);
+  SIM_REQUIRE(xyz && idx && center, SIM_ERR_INVALID, "fps: null tensor");
+  const size_t smem = (size_t)N * 3 * sizeof(float);
+#define SIM_FPS_LAUNCH(NT, PPT)                                                                         \
+  do {                                                                                                  \
+    auto kern = fps_kernel<NT, PPT>;                                                                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center);                                              \
+  } while (0)
+  if (N <= 512)
+    SIM_FPS_LAUNCH(128, 4);
+  else if (N <= 1024)
+    SIM_FPS_LAUNCH(256, 4);
+  else if (N <= 2048)
+    SIM_FPS_LAUNCH(256, 8);
+  else if (N <= 4096)
+    SIM_FPS_LAUNCH(512, 8);
+  else if (N <= 16384)
+    SIM_FPS_LAUNCH(1024, 16);
+  else {
+    set_error("fps: N=%d exceeds the built maximum of 16384", N);
+    return SIM_ERR_INVALID;
+  }
+#undef SIM_FPS_LAUNCH
+  return check_launch("fps");
+}
+
+// ----------------------------------------------------------------------------- kNN group
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) knn_group_kernel(const float* __restrict__ xyz,
+                                                               const float* __restrict__ center, int N, int G,
+                                                               int M, int* __restrict__ idx_out,
+                                                               float* __restrict__ nbr, float* __restrict__ nbr_org) {
+  extern __shared__ float sm[];
+  float* s_xyz = sm;                                              // N*3
+  unsigned* s_d = reinterpret_cast<unsigned*>(sm + (size_t)N * 3);  // WARPS * N distance bit patterns
+  int* s_sel = reinterpret_cast<int*>(s_d + (size_t)WARPS * N);   // WARPS * M
+  const int groups_per_cloud = (G + WARPS - 1) / WARPS;
+  const int b = blockIdx.x / groups_per_cloud;
+  const int g = (blockIdx.x % groups_per_cloud) * WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = xyz + (long)b * N * 3;
+  for (int i = threadIdx.x; i < N * 3; i += WARPS * 32) s_xyz[i] = src[i];
+  __syncthreads();
+  if (g >= G) return;
+  const float cx = center[((long)b * G + g) * 3], cy = center[((long)b * G + g) * 3 + 1],
+              cz = center[((long)b * G + g) * 3 + 2];
+  unsigned* d = s_d + (size_t)warp * N;
+  for (int i = lane; i < N; i += 32)
+    d[i] = __float_as_uint(sqdist3(cx, cy, cz, s_xyz[3 * i], s_xyz[3 * i + 1], s_xyz[3 * i + 2]));
+  __syncwarp();
+  // T = M-th smallest bit pattern: the largest v with #{d < v} < M (distances are >= 0, so bit 31 is clear)
+  unsigned T = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    const unsigned cand = T | (1u << bit);
+    unsigned cnt = 0;
+    for (int i = lane; i < N; i += 32) cnt += d[i] < cand;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((int)cnt < M) T = cand;
+  }
+  unsigned cnt_lt = 0;
+  for (int i = lane; i < N; i += 32) cnt_lt += d[i] < T;
+  cnt_lt = __reduce_add_sync(0xffffffffu, cnt_lt);
+  const int need_eq = M - (int)cnt_lt;  // ties at T taken in ascending index order
+  int* sel = s_sel + warp * M;
+  int out_base = 0, eq_seen = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned v = i < N ? d[i] : 0xffffffffu;
+    const bool is_eq = v == T;
+    const unsigned bal_eq = __ballot_sync(0xffffffffu, is_eq);
+    const bool take = (v < T) || (is_eq && (eq_seen + __popc(bal_eq & lt_mask)) < need_eq);
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (take) sel[out_base + __popc(bal & lt_mask)] = i;
+    out_base += __popc(bal);
+    eq_seen += __popc(bal_eq);
+  }
+  __syncwarp();
+  const long row = (long)b * G + g;
+  for (int e = lane; e < M; e += 32) idx_out[row * M + e] = sel[e];
+  const float cc[3] = {cx, cy, cz};
+  for (int e = lane; e < M * 3; e += 32) {
+    const int comp = e % 3;
+    const float v = s_xyz[3 * sel[e / 3] + comp];
+    if (nbr_org) nbr_org[row * M * 3 + e] = v;
+    if (nbr) nbr[row * M * 3 + e] = __fsub_rn(v, cc[comp]);
+  }
+}
+
+int knn_group(const float* xyz, const float* center, int B, int N, int G, int M, int* idx, float* nbr,
+              float* nbr_org, cudaStream_t stream) {
+  SIM_REQUIRE(B > 0 && N > 0 && G > 0 && M > 0 && M <= N, SIM_ERR_INVALID, "knn_group: need 0 < M <= N");
+  SIM_REQUIRE(xyz && center && idx, SIM_ERR_INVALID, "knn_group: null tensor");
+  constexpr int WARPS = 8;
+  const size_t smem = ((size_t)N * 3 + (size_t)WARPS * N + (size_t)WARPS * M) * 4;
+  SIM_REQUIRE(smem <= 227 * 1024, SIM_ERR_INVALID, "knn_group: N=%d does not fit the shared-memory staging", N);
+  auto kern = knn_group_kernel<WARPS>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = B * ((G + WARPS - 1) / WARPS);
+  kern<<<grid, WARPS * 32, smem, stream>>>(xyz, center, N, G, M, idx, nbr, nbr_org);
+  return check_launch("knn_group");
+}
+
+}  // namespace sim

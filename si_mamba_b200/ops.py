@@ -1,0 +1,298 @@
+"""Torch-tensor front end of the C ABI (include/simamba.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every op below
+enqueues hand-written sm_100a kernels from libsimamba_b200.so on the current
+CUDA stream.  No CPU path, no eager-PyTorch fallback: a CPU tensor or a missing
+library raises.
+
+Function names follow the packages they replace on the reference's hot path:
+``selective_scan_fn`` (mamba-ssm), ``causal_conv1d_fn`` (causal-conv1d),
+``sample_farthest_points`` / ``knn_points`` (pytorch3d).
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import SIM_BF16, SIM_F32
+
+
+# ----------------------------------------------------------------------------- helpers
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return SIM_F32
+    if t.dtype == torch.bfloat16:
+        return SIM_BF16
+    raise TypeError(f"si-mamba kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("si-mamba ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _tm(t: torch.Tensor) -> int:
+    """Row stride (elements) of a token-major (B, L, D) tensor whose rows are uniformly strided."""
+    assert t.dim() == 3 and t.stride(2) == 1, "token-major tensors need unit channel stride"
+    assert t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1), "batch stride must equal L * row stride"
+    return t.stride(1)
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.detach().float().contiguous()
+
+
+# ----------------------------------------------------------------------------- tokenizer (a-1)
+def sample_farthest_points(points: torch.Tensor, K: int):
+    """pytorch3d-compatible subset: (B,N,3) fp32 -> (centres (B,K,3), idx (B,K) int64)."""
+    center, idx = fps(points, K)
+    return center, idx.long()
+
+
+def fps(xyz: torch.Tensor, num_group: int):
+    """-> (center (B,G,3) fp32, idx (B,G) int32).  models/point_mamba.py:93."""
+    _cuda(xyz)
+    xyz = xyz.float().contiguous()
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, num_group, dtype=torch.int32, device=xyz.device)
+    center = torch.empty(B, num_group, 3, dtype=torch.float32, device=xyz.device)
+    _lib.call("sim_fps", _p(xyz), B, N, num_group, _p(idx), _p(center), _stream())
+    return center, idx
+
+
+def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, want_org: bool = True):
+    """-> (idx (B,G,M) int32 ascending, neighborhood centred, neighborhood_org).  point_mamba.py:96-110."""
+    _cuda(xyz, center)
+    xyz = xyz.float().contiguous()
+    center = center.float().contiguous()
+    B, N, _ = xyz.shape
+    G = center.shape[1]
+    idx = torch.empty(B, G, group_size, dtype=torch.int32, device=xyz.device)
+    nbr = torch.empty(B, G, group_size, 3, dtype=torch.float32, device=xyz.device)
+    org = torch.empty_like(nbr) if want_org else None
+    _lib.call("sim_knn_group", _p(xyz), _p(center), B, N, G, group_size, _p(idx), _p(nbr), _p(org), _stream())
+    return idx, nbr, org
+
+
+# ----------------------------------------------------------------------------- spectral (a-3..a-5)
+def spectral_flags(symmetric, self_loop, binary, smallest, matrix="laplacian", eps_mode="add1e-6",
+                   canonical_sign=True) -> int:
+    f = 0
+    f |= _lib.GRAPH_SYMMETRIC if symmetric else 0
+    f |= _lib.GRAPH_SELF_LOOP if self_loop else 0
+    f |= _lib.GRAPH_BINARY if binary else 0
+    f |= _lib.EIG_SMALLEST if smallest else 0
+    f |= _lib.LAP_SYMMETRIC if matrix != "laplacian" else 0
+    f |= _lib.LAP_EPS_CLAMP if eps_mode == "clamp1e-12" else 0
+    f |= _lib.EIG_CANONICAL_SIGN if canonical_sign else 0
+    return f
+
+
+def spectral_eig(center: torch.Tensor, k_nn: int, alpha: float, symmetric: bool, self_loop: bool, binary: bool,
+                 k: int, smallest: bool, matrix: str = "laplacian", eps_mode: str = "add1e-6",
+                 canonical_sign: bool = True, want_adjacency: bool = False):
+    """centres (B,G,3) -> dict(vals (B,k), vecs (B,G,k), perm (B,k,G) i32, inv_perm, [adjacency (B,G,G)])."""
+    _cuda(center)
+    center = center.detach().float().contiguous()
+    B, G, _ = center.shape
+    dev = center.device
+    vals = torch.empty(B, k, dtype=torch.float32, device=dev)
+    vecs = torch.empty(B, G, k, dtype=torch.float32, device=dev)
+    perm = torch.empty(B, k, G, dtype=torch.int32, device=dev)
+    inv = torch.empty(B, k, G, dtype=torch.int32, device=dev)
+    adj = torch.empty(B, G, G, dtype=torch.float32, device=dev) if want_adjacency else None
+    ws_bytes = _lib.load().sim_spectral_eig_workspace_bytes(B, G, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    flags = spectral_flags(symmetric, self_loop, binary, smallest, matrix, eps_mode, canonical_sign)
+    _lib.call("sim_spectral_eig", _p(center), B, G, int(k_nn), float(alpha), flags, int(k), _p(vals), _p(vecs),
+              _p(perm), _p(inv), _p(adj), _p(ws), ws_bytes, _stream())
+    out = dict(vals=vals, vecs=vecs, perm=perm, inv_perm=inv)
+    if want_adjacency:
+        out["adjacency"] = adj
+    return out
+
+
+def argsort_rows(keys: torch.Tensor):
+    """Stable ascending argsort along the last dim of a 2-D fp32 tensor (any strides) -> (perm, inv_perm) int32."""
+    _cuda(keys)
+    assert keys.dim() == 2 and keys.dtype == torch.float32
+    rows, n = keys.shape
+    perm = torch.empty(rows, n, dtype=torch.int32, device=keys.device)
+    inv = torch.empty_like(perm)
+    _lib.call("sim_argsort_rows", _p(keys), keys.stride(0), keys.stride(1), rows, n, _p(perm), _p(inv), _stream())
+    return perm, inv
+
+
+# ----------------------------------------------------------------------------- order gather (a-6)
+class _OrderGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, perm, inv_perm, reverse):
+        B, G, Cc = x.shape
+        k = perm.shape[1]
+        T = (2 if reverse else 1) * k * G
+        out = torch.empty(B, T, Cc, dtype=x.dtype, device=x.device)
+        _lib.call("sim_order_gather_fwd", _p(x), None, _p(perm), _p(out), None, B, G, k, Cc, int(reverse), _dt(x),
+                  _stream())
+        ctx.save_for_backward(inv_perm)
+        ctx.meta = (B, G, k, Cc, reverse)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (inv_perm,) = ctx.saved_tensors
+        B, G, k, Cc, reverse = ctx.meta
+        dout = dout.contiguous()
+        dx = torch.empty(B, G, Cc, dtype=dout.dtype, device=dout.device)
+        _lib.call("sim_order_gather_bwd", _p(dout), _p(inv_perm), _p(dx), B, G, k, Cc, int(reverse), _dt(dout),
+                  _stream())
+        return dx, None, None, None
+
+
+def order_gather(x: torch.Tensor, perm: torch.Tensor, reverse: bool = True,
+                 inv_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (B,G,C), perm (B,k,G) int32 -> (B, (2|1)*k*G, C): cat of the k sorted copies (+ flipped copy)."""
+    _cuda(x, perm)
+    x = x.contiguous()
+    perm = perm.contiguous()
+    if inv_perm is None:
+        if x.requires_grad and torch.is_grad_enabled():
+            inv_perm = torch.empty_like(perm)
+            ar = torch.arange(perm.shape[-1], dtype=torch.int32, device=perm.device).expand_as(perm)
+            inv_perm.scatter_(2, perm.long(), ar)
+        else:
+            inv_perm = perm  # unused without grad
+    return _OrderGather.apply(x, perm, inv_perm.contiguous(), bool(reverse))
+
+
+def order_gather_add(x: torch.Tensor, x2: torch.Tensor, perm: torch.Tensor, reverse: bool = True) -> torch.Tensor:
+    """Inference fast path: gather(x)+gather(x2) in one pass (tokens + pos, point_mamba.py:250)."""
+    _cuda(x, x2, perm)
+    x, x2, perm = x.contiguous(), x2.contiguous(), perm.contiguous()
+    B, G, Cc = x.shape
+    k = perm.shape[1]
+    T = (2 if reverse else 1) * k * G
+    out = torch.empty(B, T, Cc, dtype=x.dtype, device=x.device)
+    _lib.call("sim_order_gather_fwd", _p(x), _p(x2), _p(perm), _p(out), None, B, G, k, Cc, int(reverse), _dt(x),
+              _stream())
+    return out
+
+
+def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b,t] = x[b, src_idx[b,t]] if src_idx >= 0 else fill (zeros when fill is None).  Forward only."""
+    _cuda(x, src_idx, fill)
+    x = x.contiguous()
+    src_idx = src_idx.to(torch.int32).contiguous()
+    B, R_in, Cc = x.shape
+    R_out = src_idx.shape[1]
+    out = torch.empty(B, R_out, Cc, dtype=x.dtype, device=x.device)
+    f = None if fill is None else fill.to(x.dtype).contiguous()
+    _lib.call("sim_gather_rows", _p(x), _p(src_idx), _p(f), _p(out), B, R_in, R_out, Cc, _dt(x), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- add + LayerNorm (a-9)
+def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
+                  eps: float = 1e-5, x2: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                  want_residual: bool = True):
+    """res = x (+ x2) (+ residual) in fp32;  y = LayerNorm(res).  -> (y, res or None).  Forward only."""
+    _cuda(x, residual, weight, bias, x2)
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    res_out = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_residual else None
+    if residual is not None:
+        residual = residual.float().contiguous()
+    if x2 is not None:
+        x2 = x2.to(x.dtype).contiguous()
+    _lib.call("sim_add_layernorm", _p(x), _p(x2), _p(residual), _p(_f32c(weight)), _p(_f32c(bias)), _p(res_out),
+              _p(y), rows, Cc, float(eps), _dt(x), _dt(y), _stream())
+    return y, res_out
+
+
+# ----------------------------------------------------------------------------- causal conv1d (a-12)
+def causal_conv1d_tm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool = True,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-major causal depthwise conv: x (B,L,D) (any uniform row stride), weight (D,W) -> (B,L,D)."""
+    _cuda(x, weight, bias)
+    B, L, D = x.shape
+    ld_x = _tm(x)
+    if out is None:
+        out = torch.empty(B, L, D, dtype=x.dtype, device=x.device)
+    w = _f32c(weight.reshape(D, -1))
+    _lib.call("sim_causal_conv1d_fwd", _p(x), ld_x, _p(w), _p(_f32c(bias)), _p(out), _tm(out), B, L, D,
+              w.shape[1], int(silu), _dt(x), _stream())
+    return out
+
+
+def causal_conv1d_fn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                     activation: Optional[str] = None) -> torch.Tensor:
+    """causal-conv1d compatible signature: x (B,D,L) channel-major -> (B,D,L)."""
+    assert activation in (None, "silu", "swish")
+    xt = x.transpose(1, 2)
+    if xt.stride(2) != 1 or (xt.shape[0] > 1 and xt.stride(0) != xt.shape[1] * xt.stride(1)):
+        xt = xt.contiguous()
+    y = causal_conv1d_tm(xt, weight, bias, silu=activation is not None)
+    return y.transpose(1, 2)
+
+
+# ----------------------------------------------------------------------------- selective scan (a-11)
+def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """Token-major selective scan.  u, delta, z (B,L,D); Bm, Cm (B,L,N) - all may be column slices of wider
+    row-major buffers; A (D,N) fp32.  Returns out (B,L,D) in u's dtype."""
+    _cuda(u, delta, A, Bm, Cm, D, z, delta_bias)
+    B, L, Dm = u.shape
+    N = A.shape[1]
+    if out is None:
+        out = torch.empty(B, L, Dm, dtype=u.dtype, device=u.device)
+    u, delta, Bm, Cm, z = (_bulk_ok(t) for t in (u, delta, Bm, Cm, z))
+    assert delta.dtype == u.dtype and Bm.dtype == u.dtype and Cm.dtype == u.dtype and (z is None or z.dtype == u.dtype)
+    _lib.call("sim_selective_scan_fwd", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm), _tm(Bm), _p(Cm),
+              _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(out), _tm(out),
+              B, L, Dm, N, int(delta_softplus), _dt(u), int(variant), _stream())
+    return out
+
+
+def _bulk_ok(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """TMA bulk copies need 16-byte aligned row starts; copy the (rare) slices that are not."""
+    if t is None:
+        return None
+    ok = t.stride(2) == 1 and (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1)) \
+        and (t.stride(1) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+def _to_tm(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    tt = t.transpose(1, 2)
+    ok = tt.stride(2) == 1 and (tt.shape[0] == 1 or tt.stride(0) == tt.shape[1] * tt.stride(1)) \
+        and (tt.stride(1) * tt.element_size()) % 16 == 0 and tt.data_ptr() % 16 == 0
+    return tt if ok else tt.contiguous()
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """mamba-ssm compatible signature (channel-major): u, delta, z (B,D,L); B, C (B,N,L); A (D,N).
+
+    Channel-major arguments that are transposed views of token-major memory are used in place;
+    anything else is transposed once."""
+    if return_last_state:
+        raise NotImplementedError("return_last_state is not on SI-Mamba's path (inference_params is always None)")
+    out = selective_scan_tm(_to_tm(u), _to_tm(delta), A, _to_tm(B), _to_tm(C), D, _to_tm(z), delta_bias,
+                            delta_softplus)
+    return out.transpose(1, 2)

@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's module API for the spectrally-ordered token encoder path
+(models/point_mamba.py): ``Encoder``, ``Group``, ``create_block``, ``MixerModel``, ``PointMamba`` with the
+same constructor arguments, config keys, forward signatures and state-dict keys,
+running on the sm_100a kernels of libsimamba_b200.so.
+
+Out of scope: the wavelet / learned-ordering research code and the fork-only
+heads (eigen_embed, logit_*, permuter, sgwt) that only exist as state-dict keys on the default path;
+``load_model_from_ckpt`` loads with strict=False exactly like the reference, so such keys are ignored.
+"""
+
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .block import Block, DropPath, fused_add_norm
+from .mamba import Mamba
+
+
+class RMSNorm(nn.Module):
+    """Plain RMSNorm for the ``rms_norm: True`` config key (the shipped configs all use LayerNorm)."""
+
+    def __init__(self, hidden_size, eps=1e-5, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+        self.register_parameter("bias", None)
+
+    def forward(self, x):
+        xf = x.float()
+        return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight.float()).to(x.dtype)
+
+
+class Encoder(nn.Module):
+    """Per-patch mini-PointNet (models/point_mamba.py:42-73); dense contractions stay on cuDNN / cuBLAS."""
+
+    def __init__(self, encoder_channel):
+        super().__init__()
+        self.encoder_channel = encoder_channel
+        self.first_conv = nn.Sequential(nn.Conv1d(3, 128, 1), nn.BatchNorm1d(128), nn.ReLU(inplace=True),
+                                        nn.Conv1d(128, 256, 1))
+        self.second_conv = nn.Sequential(nn.Conv1d(512, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
+                                         nn.Conv1d(512, self.encoder_channel, 1))
+
+    def forward(self, point_groups):
+        """point_groups (B, G, M, 3) -> (B, G, C)."""
+        bs, g, n, _ = point_groups.shape
+        point_groups = point_groups.reshape(bs * g, n, 3)
+        feature = self.first_conv(point_groups.transpose(2, 1))
+        feature_global = torch.max(feature, dim=2, keepdim=True)[0]
+        feature = torch.cat([feature_global.expand(-1, -1, n), feature], dim=1)
+        feature = self.second_conv(feature)
+        feature_global = torch.max(feature, dim=2, keepdim=False)[0]
+        return feature_global.reshape(bs, g, self.encoder_channel)
+
+
+class Group(nn.Module):
+    """FPS centres + kNN patches (models/point_mamba.py:76-111) on the sim_fps / sim_knn_group kernels."""
+
+    def __init__(self, num_group, group_size):
+        super().__init__()
+        self.num_group = num_group
+        self.group_size = group_size
+
+    def forward(self, xyz):
+        """xyz (B, N, 3) -> (neighborhood (B,G,M,3) centred, center (B,G,3), neighborhood_org (B,G,M,3))."""
+        center, _ = ops.fps(xyz, self.num_group)
+        idx, neighborhood, neighborhood_org = ops.knn_group(xyz, center, self.group_size)
+        assert idx.size(1) == self.num_group
+        assert idx.size(2) == self.group_size
+        return neighborhood, center, neighborhood_org
+
+
+def _init_weights(module, n_layer, initializer_range=0.02, rescale_prenorm_residual=True, n_residuals_per_layer=1):
+    """models/point_mamba.py:115-144."""
+    if isinstance(module, nn.Linear):
+        if module.bias is not None and not getattr(module.bias, "_no_reinit", False):
+            nn.init.zeros_(module.bias)
+    elif isinstance(module, nn.Embedding):
+        nn.init.normal_(module.weight, std=initializer_range)
+    if rescale_prenorm_residual:
+        for name, p in module.named_parameters():
+            if name in ["out_proj.weight", "fc2.weight"]:
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+                with torch.no_grad():
+                    p /= math.sqrt(n_residuals_per_layer * n_layer)
+
+
+def create_block(d_model, ssm_cfg=None, norm_epsilon=1e-5, rms_norm=False, residual_in_fp32=False,
+                 fused_add_norm=False, layer_idx=None, drop_path=0., device=None, dtype=None):
+    """models/point_mamba.py:147-175."""
+    ssm_cfg = {} if ssm_cfg is None else ssm_cfg
+    factory_kwargs = {"device": device, "dtype": dtype}
+    mixer_cls = partial(Mamba, layer_idx=layer_idx, **ssm_cfg, **factory_kwargs)
+    norm_cls = partial(nn.LayerNorm if not rms_norm else RMSNorm, eps=norm_epsilon, **factory_kwargs)
+    block = Block(d_model, mixer_cls, norm_cls=norm_cls, fused_add_norm=fused_add_norm,
+                  residual_in_fp32=residual_in_fp32, drop_path=drop_path)
+    block.layer_idx = layer_idx
+    return block
+
+
+class MixerModel(nn.Module):
+    """Stack of Blocks + final add + norm_f (models/point_mamba.py:178-272)."""
+
+    def __init__(self, d_model: int, n_layer: int, ssm_cfg=None, norm_epsilon: float = 1e-5, rms_norm: bool = False,
+                 initializer_cfg=None, fused_add_norm=False, residual_in_fp32=False, drop_out_in_block: int = 0.,
+                 drop_path: int = 0.1, device=None, dtype=None) -> None:
+        factory_kwargs = {"device": device, "dtype": dtype}
+        super().__init__()
+        self.residual_in_fp32 = residual_in_fp32
+        self.fused_add_norm = fused_add_norm
+        self.layers = nn.ModuleList([
+            create_block(d_model, ssm_cfg=ssm_cfg, norm_epsilon=norm_epsilon, rms_norm=rms_norm,
+                         residual_in_fp32=residual_in_fp32, fused_add_norm=fused_add_norm, layer_idx=i,
+                         drop_path=drop_path, **factory_kwargs) for i in range(n_layer)])
+        self.norm_f = (nn.LayerNorm if not rms_norm else RMSNorm)(d_model, eps=norm_epsilon, **factory_kwargs)
+        self.apply(partial(_init_weights, n_layer=n_layer, **(initializer_cfg if initializer_cfg is not None else {})))
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.drop_out_in_block = nn.Dropout(drop_out_in_block) if drop_out_in_block > 0. else nn.Identity()
+
+    def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
+        return {i: layer.allocate_inference_cache(batch_size, max_seqlen, dtype=dtype, **kwargs)
+                for i, layer in enumerate(self.layers)}
+
+    def forward(self, input_ids, pos, inference_params=None):
+        """h = tokens + pos; 12 x Block; norm_f(h + residual).  models/point_mamba.py:247-258."""
+        hidden_states = input_ids + pos if pos is not None else input_ids
+        residual = None
+        for layer in self.layers:
+            hidden_states, residual = layer(hidden_states, residual, inference_params=inference_params)
+            hidden_states = self.drop_out_in_block(hidden_states)
+        hidden_states, _ = fused_add_norm(self.norm_f, hidden_states, residual, want_residual=False)
+        return hidden_states
+
+
+def _cfg_get(config, key, default):
+    return getattr(config, key) if hasattr(config, key) else default
+
+
+class PointMamba(nn.Module):
+    """Classification model (models/point_mamba.py:430-1130), default-argument forward, SAST / MAMBA orderings."""
+
+    def __init__(self, config, **kwargs):
+        super().__init__()
+        self.config = config
+        self.trans_dim = config.trans_dim
+        self.depth = config.depth
+        self.cls_dim = config.cls_dim
+        self.group_size = config.group_size
+        self.num_group = config.num_group
+        self.encoder_dims = config.encoder_dims
+
+        self.group_divider = Group(num_group=self.num_group, group_size=self.group_size)
+        self.encoder = Encoder(encoder_channel=self.encoder_dims)
+
+        self.use_cls_token = _cfg_get(config, "use_cls_token", False)
+        self.drop_path = _cfg_get(config, "drop_path", 0.)
+        self.rms_norm = _cfg_get(config, "rms_norm", False)
+        self.drop_out_in_block = _cfg_get(config, "drop_out_in_block", 0.)
+        if self.use_cls_token:
+            raise NotImplementedError("use_cls_token is unused by the reference forward (point_mamba.py:843-1130)")
+
+        self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, self.trans_dim))
+        self.add_after_layer = config.add_after_layer
+        if self.add_after_layer:
+            raise NotImplementedError("add_after_layer=True (MixerModel_add) is outside the hot-path scope")
+        self.blocks = MixerModel(d_model=self.trans_dim, n_layer=self.depth, rms_norm=self.rms_norm,
+                                 drop_out_in_block=self.drop_out_in_block, drop_path=self.drop_path)
+        self.norm = nn.LayerNorm(self.trans_dim)
+        self.HEAD_CHANEL = 1
+        self.cls_head_finetune = nn.Sequential(
+            nn.Linear(self.trans_dim * self.HEAD_CHANEL, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
+            nn.Dropout(0.5), nn.Linear(256, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(0.5),
+            nn.Linear(256, self.cls_dim))
+        self.build_loss_func()
+        self.drop_out = nn.Dropout(config.drop_out) if "drop_out" in config else nn.Dropout(0)
+
+        self.method = config.method
+        self.reverse = config.reverse
+        self.reverse_2 = config.reverse_2
+        self.reverse_3 = config.reverse_3
+        self.k_top_eigenvectors = config.k_top_eigenvectors
+        self.smallest = config.smallest
+        self.knn_graph = config.knn_graph
+        self.symmetric = config.symmetric
+        self.self_loop = config.self_loop
+        self.alpha = config.alpha
+        self.binary = config.binary
+        self.matrix = config.matrix
+        assert self.trans_dim >= self.k_top_eigenvectors
+        if self.reverse_2 or self.reverse_3:
+            raise NotImplementedError("reverse_2 / reverse_3 are 'always False' (cfgs/finetune_modelnet.yaml:38-39)")
+
+    # ------------------------------------------------------------------ reference helper API
+    def build_loss_func(self):
+        self.loss_ce = nn.CrossEntropyLoss(reduction='none')
+
+    def get_loss_acc(self, ret, gt):
+        loss = self.loss_ce(ret, gt.long())
+        pred = ret.argmax(-1)
+        acc = (pred == gt).sum() / float(gt.size(0))
+        return loss, acc * 100
+
+    def load_model_from_ckpt(self, bert_ckpt_path):
+        """models/point_mamba.py:574-605: strip ``module.``, remap ``MAE_encoder.`` / ``base_model.``, strict=False."""
+        if bert_ckpt_path is None:
+            self.apply(self._init_weights)
+            return None
+        ckpt = torch.load(bert_ckpt_path, map_location='cpu', weights_only=False)
+        base_ckpt = {k.replace("module.", ""): v for k, v in ckpt['base_model'].items()}
+        for k in list(base_ckpt.keys()):
+            if k.startswith('MAE_encoder'):
+                base_ckpt[k[len('MAE_encoder.'):]] = base_ckpt.pop(k)
+            elif k.startswith('base_model'):
+                base_ckpt[k[len('base_model.'):]] = base_ckpt.pop(k)
+        return self.load_state_dict(base_ckpt, strict=False)
+
+    def _init_weights(self, m):
+        """models/point_mamba.py:607-618 (trunc_normal std .02 on Linear / Conv1d, LayerNorm to identity)."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+        elif isinstance(m, nn.Conv1d):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def spectral_order(self, center):
+        """centres -> dict(vals, vecs, perm, inv_perm): graph + Laplacian + eigensolver + argsort in one kernel
+        (replaces create_graph_* + calc_top_k_eigenvalues_eigenvectors* + the sorts, point_mamba.py:872-898)."""
+        return ops.spectral_eig(center, self.knn_graph, self.alpha, self.symmetric, self.self_loop, self.binary,
+                                self.k_top_eigenvectors, self.smallest, self.matrix)
+
+    def create_graph_from_feature_space_gpu_weighted_adjacency(self, points, k=5, alpha=1, symmetric=False,
+                                                               self_loop=False, binary=False):
+        """point_mamba.py:664-715 -> adjacency (B,G,G)."""
+        return ops.spectral_eig(points, k, alpha, symmetric, self_loop, binary, 1, True,
+                                want_adjacency=True)["adjacency"]
+
+    create_graph_from_centers = create_graph_from_feature_space_gpu_weighted_adjacency
+
+    def sort_points_by_fiedler(self, points, fiedler_vector):
+        """point_mamba.py:817-826: rows of ``points`` (B,G,C) in ascending order of ``fiedler_vector`` (B,G)."""
+        perm, inv = ops.argsort_rows(fiedler_vector.float())
+        return ops.order_gather(points, perm[:, None, :], reverse=False, inv_perm=inv[:, None, :])
+
+    def multilevel_travers(self, eigen_vectors, level):
+        """point_mamba.py:829-841."""
+        means = eigen_vectors.mean(dim=1, keepdim=True)
+        binaries = (eigen_vectors >= means)[:, :, :level]
+        powers_of_2 = 2 ** torch.arange(start=level - 1, end=-1, step=-1, device=eigen_vectors.device)
+        return torch.sum(binaries * powers_of_2[None, None, :], dim=-1, keepdim=True).squeeze()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, pts, gt: torch.Tensor = None, tau: float = None, use_wavelets: bool = False,
+                save_pts_dir: str = None, epoch: int = None):
+        """pts (B, N, 3) -> logits (B, cls_dim)   [(logits, policy) when ``gt`` is given, as the reference]."""
+        if use_wavelets:
+            raise NotImplementedError("use_wavelets is broken at the reference HEAD (point_mamba.py:879) and out of scope")
+        batch_size = pts.size(0)
+        neighborhood, center, neighborhood_org = self.group_divider(pts)
+        group_input_tokens = self.encoder(neighborhood)
+        pos = self.pos_embed(center)
+
+        if self.method == "MAMBA":
+            # xyz-argsort baseline ordering (point_mamba.py:850-866) served by the same gather kernel
+            keys = center.transpose(1, 2).reshape(batch_size * 3, self.num_group).contiguous()
+            perm, inv = ops.argsort_rows(keys)
+            perm, inv = perm.view(batch_size, 3, -1), inv.view(batch_size, 3, -1)
+            reverse = False
+        elif self.method == "SAST":
+            spec = self.spectral_order(center)
+            perm, inv = spec["perm"], spec["inv_perm"]
+            reverse = bool(self.reverse)
+        else:
+            raise NotImplementedError(f"method {self.method!r} (HLT lives in the part-segmentation model)")
+
+        training_graph = torch.is_grad_enabled() and (group_input_tokens.requires_grad or pos.requires_grad)
+        p_drop = self.drop_out.p if self.training else 0.0
+        if not training_graph and p_drop == 0.0:
+            # tokens + pos folded into the gather: gather(tok) + gather(pos) == gather(tok + pos) bit for bit
+            x = ops.order_gather_add(group_input_tokens, pos, perm, reverse)
+            x = self.blocks(x, None)
+        else:
+            x = ops.order_gather(group_input_tokens, perm, reverse, inv)
+            pos = ops.order_gather(pos, perm, reverse, inv)
+            x = self.drop_out(x)
+            x = self.blocks(x, pos)
+        x = self.norm(x)
+        concat_f = x[:, :].mean(1)
+        ret = self.cls_head_finetune(concat_f)
+        if gt is not None:
+            policy = torch.zeros((batch_size,), device=center.device, dtype=center.dtype)
+            return ret, policy
+        return ret

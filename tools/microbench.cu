@@ -1,0 +1,99 @@
+// Pipe-throughput microbenchmark for B200 (sm_100a): how many FFMA / FFMA2 / MUFU.EX2 / mixed
+// instructions per clock per SM?  The selective scan is balanced between HBM, MUFU and FMA issue,
+// so these numbers decide its inner-loop design ("scan cost model").
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/microbench tools/microbench.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#define ITERS 4096
+#define UNR 8
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(float* out, float seed) {
+  float a[UNR], b[UNR];
+  float2 p[UNR];
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) {
+    a[i] = seed + i + threadIdx.x;
+    b[i] = seed * 0.5f + i;
+    p[i] = make_float2(a[i], b[i]);
+  }
+  const float c1 = seed * 1.0001f, c2 = seed * 0.37f;
+  const float2 q1 = make_float2(c1, c2), q2 = make_float2(c2, c1);
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      if (MODE == 0) {  // FFMA
+        a[i] = fmaf(a[i], c1, c2);
+        b[i] = fmaf(b[i], c2, c1);
+      } else if (MODE == 1) {  // FFMA2
+        p[i] = __ffma2_rn(p[i], q1, q2);
+      } else if (MODE == 2) {  // MUFU.EX2
+        a[i] = ex2(a[i]);
+        b[i] = ex2(b[i]);
+      } else if (MODE == 3) {  // scan-like mix, scalar: FMUL, EX2, FMUL, FFMA, FFMA per update
+        float x = a[i] * c1;
+        float e = ex2(x);
+        float bu = c2 * b[i];
+        a[i] = fmaf(e, a[i], bu);
+        b[i] = fmaf(a[i], c1, b[i]);
+      } else if (MODE == 4) {  // scan-like mix, packed: FMUL2, 2xEX2, FMUL2, FFMA2, FFMA2 per two updates
+        float2 x = __fmul2_rn(p[i], q1);
+        float2 e = make_float2(ex2(x.x), ex2(x.y));
+        float2 bu = __fmul2_rn(q2, p[i]);
+        p[i] = __ffma2_rn(e, p[i], bu);
+        p[i] = __ffma2_rn(p[i], q1, q2);
+      } else if (MODE == 5) {  // FMUL2 only
+        p[i] = __fmul2_rn(p[i], q1);
+      } else if (MODE == 6) {  // FFMA + EX2 1:1 (do the pipes overlap?)
+        a[i] = fmaf(a[i], c1, c2);
+        b[i] = ex2(b[i]);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) s += a[i] + b[i] + p[i].x + p[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int MODE>
+void run(const char* name, double ops_per_iter_per_thread, float* out) {
+  const int grid = 148 * 8, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k<MODE><<<grid, block>>>(out, 0.001f);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  k<MODE><<<grid, block>>>(out, 0.001f);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  int clk_khz;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  const double total = (double)grid * block * ITERS * UNR * ops_per_iter_per_thread;
+  printf("%-28s %8.3f ms  %9.1f Gop/s  (%6.1f ops/clk/SM at max clock %d MHz)\n", name, ms, total / ms * 1e-6,
+         total / (ms * 1e-3) / 148.0 / (clk_khz * 1e3), clk_khz / 1000);
+}
+
+int main() {
+  float* out;
+  cudaMalloc(&out, 148 * 8 * 256 * sizeof(float));
+  run<0>("FFMA (scalar)", 2, out);
+  run<1>("FFMA2 (packed, FMAs)", 2, out);
+  run<5>("FMUL2 (packed, muls)", 2, out);
+  run<2>("MUFU.EX2", 2, out);
+  run<6>("FFMA+EX2 1:1 (pairs)", 1, out);
+  run<3>("scan mix scalar (updates)", 1, out);
+  run<4>("scan mix packed (updates)", 2, out);
+  printf("cuda error: %s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
