@@ -48,7 +48,8 @@ def cls_head(sd, prefix, x):
     return F.linear(h, sd[prefix + "8.weight"], sd[prefix + "8.bias"])
 
 
-def point_mamba_forward(sd: dict, cfg: dict, pts: torch.Tensor, return_intermediates: bool = False):
+def point_mamba_forward(sd: dict, cfg: dict, pts: torch.Tensor, return_intermediates: bool = False,
+                        perm_override: torch.Tensor = None):
     """PointMamba.forward(pts) -> logits (B, cls_dim), SAST path.
 
     ``cfg`` uses the reference's config keys (cfgs/finetune_modelnet.yaml:23-50).
@@ -62,6 +63,11 @@ def point_mamba_forward(sd: dict, cfg: dict, pts: torch.Tensor, return_intermedi
         center, cfg["knn_graph"], cfg["alpha"], cfg["symmetric"], cfg["self_loop"], cfg["binary"],
         cfg["k_top_eigenvectors"], cfg["smallest"], cfg.get("matrix", "laplacian"))
     perm = spectral.sast_perm(vecs)
+    perm_oracle = perm
+    if perm_override is not None:
+        # near-tied eigenvector entries admit several valid orderings; a caller that has verified
+        # its permutation against `vecs` can ask for the downstream result under that ordering
+        perm = perm_override
     x = spectral.order_gather(tok, perm, cfg["reverse"])
     p = spectral.order_gather(pos, perm, cfg["reverse"])
     h = mamba.mixer_model(sd, "blocks.", x, p, cfg["depth"])
@@ -70,5 +76,5 @@ def point_mamba_forward(sd: dict, cfg: dict, pts: torch.Tensor, return_intermedi
     logits = cls_head(sd, "cls_head_finetune.", feat)
     if return_intermediates:
         return logits, dict(fps_idx=fidx, knn_idx=kidx, center=center, tokens=tok, pos=pos,
-                            eigvals=vals, eigvecs=vecs, perm=perm, hidden=h, feat=feat)
+                            eigvals=vals, eigvecs=vecs, perm=perm_oracle, hidden=h, feat=feat)
     return logits

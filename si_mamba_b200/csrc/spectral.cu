@@ -530,9 +530,12 @@ int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cuda
 #define SIM_SPEC_LAUNCH(NT_, INS)                                                                   \
   do {                                                                                              \
     auto kern = spectral_kernel<NT_, INS>;                                                          \
-    if (smem > 48 * 1024)                                                                           \
+    static size_t attr_smem = 0; /* grow-only, set outside stream capture by the first (warm-up) call */ \
+    if (smem > 48 * 1024 && smem > attr_smem) {                                                     \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
         return check_launch("spectral_eig attr");                                                   \
+      attr_smem = smem;                                                                             \
+    }                                                                                               \
     kern<<<P.B, NT_, smem, stream>>>(P);                                                            \
   } while (0)
   if (NT == 256) {

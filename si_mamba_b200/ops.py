@@ -45,8 +45,11 @@ def _stream() -> int:
 
 def _tm(t: torch.Tensor) -> int:
     """Row stride (elements) of a token-major (B, L, D) tensor whose rows are uniformly strided."""
-    assert t.dim() == 3 and t.stride(2) == 1, "token-major tensors need unit channel stride"
-    assert t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1), "batch stride must equal L * row stride"
+    assert t.dim() == 3 and (t.stride(2) == 1 or t.shape[2] == 1), "token-major tensors need unit channel stride"
+    B, L, D = t.shape
+    if L == 1:  # size-1 dims carry arbitrary strides: rows are then indexed by the batch stride alone
+        return t.stride(0) if B > 1 else D
+    assert B == 1 or t.stride(0) == L * t.stride(1), "batch stride must equal L * row stride"
     return t.stride(1)
 
 

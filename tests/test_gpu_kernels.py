@@ -66,18 +66,20 @@ def check_spectral(out, vals, vecs, S, perm_ref=None):
     allv = torch.linalg.eigvalsh(S.double())
     for b in range(B):
         for s in range(k):
-            other = (allv[b] - vals[b, s]).abs()
-            other = other[other > 0]
             # documented exemption: (near-)degenerate eigengaps below 1e-6 have no unique eigenvector
-            near = (other < 1e-6).sum() > 0 or ((allv[b] - vals[b, s]).abs() < 1e-12).sum() > 1
-            gaps_ok[b, s] = not near
+            diffs = (allv[b] - vals[b, s]).abs().sort().values  # diffs[0] is the eigenvalue itself
+            gaps_ok[b, s] = diffs[1] >= 1e-6
     err = (v_k - vecs).abs().amax(dim=1)
     assert err[gaps_ok].max() < 1e-4                             # eigenvectors: 1e-4 up to (canonical) sign
-    # permutation: bit-exact wherever the oracle's sorted neighbours are separated by more than 1e-9 ...
+    # permutation: bit-exact at every position whose oracle value is separated from both sorted neighbours by
+    # more than 1e-9 (binary kNN graphs contain "twin" patches with identical neighbourhoods, whose eigenvector
+    # entries coincide in exact arithmetic - those positions have no defined order) ...
     perm_o = spectral.sast_perm(vecs)
     srt = torch.gather(vecs.transpose(1, 2), 2, perm_o)
-    min_gap = (srt[..., 1:] - srt[..., :-1]).amin(-1)
-    strict = gaps_ok & (min_gap > 1e-9)
+    d = srt[..., 1:] - srt[..., :-1]
+    big = torch.full_like(d[..., :1], 1.0)
+    sep = torch.minimum(torch.cat([big, d], -1), torch.cat([d, big], -1)) > 1e-9
+    strict = sep & gaps_ok[..., None]
     assert torch.equal(perm_k[strict], perm_o[strict])
     # ... and always a valid ascending order of the ORACLE's eigenvector up to 1e-9
     srt_k = torch.gather(vecs.transpose(1, 2), 2, perm_k)
@@ -89,12 +91,22 @@ def check_spectral(out, vals, vecs, S, perm_ref=None):
     return strict.float().mean().item()
 
 
+def check_adjacency(a, ref, binary):
+    """Edge selection (an index result) is bit-exact; binary weights are exact; exp() weights agree to a few ulp
+    (CUDA expf is within 2 ulp, the CPU libm within 1 ulp of the true value)."""
+    assert torch.equal(a != 0, ref != 0)
+    if binary:
+        assert torch.equal(a, ref)
+    else:
+        assert torch.allclose(a, ref, rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("case", ["cls_binary", "seg_weighted", "mae_clamp", "largest", "symnorm"])
 def test_spectral_golden(ops, golden, case):
     g = golden("spectral")[case]
     out = ops.spectral_eig(dev(g["center"]), g["k_nn"], g["alpha"], g["symmetric"], g["self_loop"], g["binary"],
                            g["k"], g["smallest"], g["matrix"], g["eps_mode"], want_adjacency=True)
-    assert torch.equal(out["adjacency"].cpu(), g["adjacency"])  # graph build is bit-exact
+    check_adjacency(out["adjacency"].cpu(), g["adjacency"], g["binary"])
     check_spectral(out, g["vals"], g["vecs"], g["operator"])
 
 
@@ -110,10 +122,10 @@ def test_spectral_vs_oracle(ops, B, N, G, k_nn, alpha, self_loop, binary):
     center = tokenizer.group(xyz, G, 4)[1]
     vals, vecs, allv, S = spectral.spectral_eig(center, k_nn, alpha, True, self_loop, binary, 4, True)
     out = ops.spectral_eig(dev(center), k_nn, alpha, True, self_loop, binary, 4, True, want_adjacency=True)
-    assert torch.equal(out["adjacency"].cpu(), spectral.knn_adjacency(center, k_nn, alpha, True, self_loop, binary))
+    check_adjacency(out["adjacency"].cpu(), spectral.knn_adjacency(center, k_nn, alpha, True, self_loop, binary), binary)
     frac = check_spectral(out, vals, vecs, S)
     if binary:
-        assert frac > 0.9  # the bit-exact comparison must actually cover (almost) all eigenvectors
+        assert frac > 0.5  # the bit-exact comparison must actually cover most positions (twins are exempt)
 
 
 def test_argsort_rows(ops):
@@ -237,6 +249,7 @@ def test_scan_optional_args_and_slices(ops):
     """No z / D / bias / softplus, and B / C / z consumed as column slices of wider buffers (the mixer layout)."""
     B, D, L = 2, 128, 50
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 77)
+    delta = delta.abs() * 0.1  # without softplus the step size must already be positive
     ref = mamba.selective_scan_ref(u, delta, A, Bm, Cm, None, None, None, False)
     tm = lambda t: t.transpose(1, 2).contiguous()
     out = ops.selective_scan_tm(dev(tm(u)), dev(tm(delta)), dev(A), dev(tm(Bm)), dev(tm(Cm)))

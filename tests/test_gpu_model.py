@@ -71,7 +71,18 @@ def test_point_mamba_forward_vs_oracle(lib, name, B, N):
         tok = m.encoder(nbr)
         assert torch.allclose(tok.cpu(), inter["tokens"], rtol=1e-4, atol=1e-4)
         spec = m.spectral_order(center)
-        assert torch.equal(spec["perm"].cpu().long(), inter["perm"])           # spectral ordering bit-exact
+        perm = spec["perm"].cpu().long()
+        # spectral ordering: bit-exact except at near-tied entries (< 1e-9 apart in the fp64 oracle vector),
+        # where it must still be a valid ascending order of the oracle's eigenvector
+        vt = inter["eigvecs"].transpose(1, 2)
+        srt = torch.gather(vt, 2, perm)
+        assert (srt[..., 1:] - srt[..., :-1]).min() > -1e-9
+        srt_o = torch.gather(vt, 2, inter["perm"])
+        well_separated = (srt_o[..., 1:] - srt_o[..., :-1]).amin(-1) > 1e-9
+        assert torch.equal(perm[well_separated], inter["perm"][well_separated])
+        assert well_separated.float().mean() > 0.5
+        if not torch.equal(perm, inter["perm"]):
+            ref = omodel.point_mamba_forward(sd, dict(cfg), pts, perm_override=perm)
         logits = m(pts.cuda())
     assert logits.shape == (B, cfg.cls_dim)
     err = (logits.cpu() - ref).abs().max() / ref.abs().max()

@@ -29,13 +29,21 @@ def time_fn(fns, iters=20, warmup=5):
     for i in range(warmup):
         fns[i % len(fns)]()
     torch.cuda.synchronize()
+    # capture the launch sequence in a CUDA graph so host-side launch overhead (ctypes, allocator) is not timed
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(iters):
+            fns[i % len(fns)]()
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
     e0.record()
-    for i in range(iters):
-        fns[i % len(fns)]()
+    for _ in range(reps):
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3
+    return e0.elapsed_time(e1) / (iters * reps) * 1e-3
 
 
 def report(name, secs, bytes_, **extra):
@@ -67,12 +75,15 @@ def scan_case(B, L, D, dtype, variant, nsets):
 
 def main():
     quick = "--quick" in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    want = lambda name: only is None or only == name
     torch.cuda.set_device(0)
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), hbm_peak_gbs=HBM)), flush=True)
     shapes = [(32, 512, 768), (32, 1024, 768), (256, 512, 768)] if not quick else [(32, 512, 768)]
-    for (B, L, D) in shapes:
+    for (B, L, D) in (shapes if want("scan") else []):
         for dtype in (torch.float32, torch.bfloat16):
-            for variant in (2, 4, 8, 16):
+            variants = (2, 4, 8, 16, 102, 104, 108, 204, 208, 304) if "--variants" in sys.argv else (0, 4, 8)
+            for variant in variants:
                 nsets = max(2, int(300e6 // (4 * B * L * D * (4 if dtype == torch.float32 else 2))) + 1)
                 fns, alg = scan_case(B, L, D, dtype, variant, min(nsets, 4))
                 t = time_fn(fns)
@@ -80,7 +91,7 @@ def main():
                 del fns
                 torch.cuda.empty_cache()
     # conv
-    for (B, L, D) in shapes[:2]:
+    for (B, L, D) in (shapes[:2] if want("conv") else []):
         for dtype in (torch.float32, torch.bfloat16):
             xs = [torch.randn(B, L, 2 * D, device="cuda").to(dtype) for _ in range(4)]
             outs = [torch.empty(B, L, D, device="cuda", dtype=dtype) for _ in range(4)]
@@ -88,6 +99,8 @@ def main():
             fns = [(lambda x=x, o=o: ops.causal_conv1d_tm(x[..., :D], w, b, True, out=o)) for x, o in zip(xs, outs)]
             es = 4 if dtype == torch.float32 else 2
             report("causal_conv1d_fwd", time_fn(fns), 2 * B * L * D * es, B=B, L=L, D=D, dtype=str(dtype).split(".")[-1])
+    if not want("rows") and not want("tok"):
+        return
     # add + layernorm
     B, L, C = 32, 512, 384
     xs = [(torch.randn(B, L, C, device="cuda"), torch.randn(B, L, C, device="cuda")) for _ in range(6)]
