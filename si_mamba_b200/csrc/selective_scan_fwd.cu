@@ -39,45 +39,87 @@ struct ScanTmaps {
   CUtensorMap u, delta, z, B, C, out;
 };
 
-template <typename T, int S_, int CH_, int TT_, int NS_>
+// S states x CPT channels per thread: every step a thread needs 2*S words of B/C and 2*CPT words of dt/u from
+// shared memory for S*CPT state updates, i.e. 2/CPT + 2/S shared-memory wavefronts per warp-update.  ncu on the
+// first version (S=4, CPT=1: 2.5 + epilogue) showed the LSU shared pipe at 73% with MUFU at 46%, so B/C reuse
+// across channels (CPT > 1) is what moves the kernel towards its MUFU bound.
+template <typename T, int S_, int CPT_, int CH_, int TT_, int NS_>
 struct ScanCfg {
-  static constexpr int S = S_;              // states per thread
-  static constexpr int LPC = kNState / S_;  // lanes per channel
-  static constexpr int CH = CH_;            // channels per CTA
-  static constexpr int TT = TT_;            // time steps per tile
-  static constexpr int NS = NS_;            // raw stages in flight
-  static constexpr int NT = CH_ * LPC;      // threads per CTA
+  static constexpr int S = S_;                  // states per thread
+  static constexpr int LPC = kNState / S_;      // lanes per channel group
+  static constexpr int CPT = CPT_;              // adjacent channels per thread
+  static constexpr int CH = CH_;                // channels per CTA
+  static constexpr int TT = TT_;                // time steps per tile
+  static constexpr int NS = NS_;                // raw stages in flight
+  static constexpr int NT = (CH_ / CPT_) * LPC; // threads per CTA
+  static constexpr int CHP = CH_ + 8;           // padded row stride (floats) of the work arrays
   static constexpr int RAW_MAIN = TT_ * CH_ * (int)sizeof(T);
   static constexpr int RAW_BC = TT_ * kNState * (int)sizeof(T);
-  static constexpr int RAW_STAGE = 3 * RAW_MAIN + 2 * RAW_BC;  // multiple of 128 for every built config
-  static constexpr int WORK = 3 * TT_ * CH_ * 4 + 2 * TT_ * kNState * 4;
+  static constexpr int RAW_STAGE = 3 * RAW_MAIN + 2 * RAW_BC;
   static constexpr int OBUF = TT_ * CH_ * (int)sizeof(T);
-  static constexpr int SMEM = NS_ * RAW_STAGE + WORK + OBUF + NS_ * 8 + 128;
-  static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0, "TMA tiles must stay 128-B aligned");
+  static constexpr int WORK = 3 * TT_ * CHP * 4 + 2 * TT_ * kNState * 4 + CH_ * 4;
+  static constexpr int SMEM = NS_ * RAW_STAGE + OBUF + WORK + NS_ * 8 + 16;
+  static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && OBUF % 128 == 0,
+                "TMA tiles must stay 128-B aligned");
+  static_assert(NT % 32 == 0 && (CH_ & (CH_ - 1)) == 0, "whole warps, power-of-two channel tile");
 };
+
+// four consecutive elements of T from shared memory as fp32
+template <typename T>
+__device__ __forceinline__ float4 lds4(const T* p);
+template <>
+__device__ __forceinline__ float4 lds4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  // bf16 -> fp32 is a 16-bit shift
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+
+template <int N>
+__device__ __forceinline__ void lds_vec(const float* p, float (&v)[N]) {
+  if constexpr (N == 1) {
+    v[0] = p[0];
+  } else if constexpr (N == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x, v[1] = t.y;
+  } else {
+    static_assert(N % 4 == 0, "vector width");
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      const float4 t = reinterpret_cast<const float4*>(p)[i];
+      v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+  }
+}
 
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __grid_constant__ ScanTmaps tm,
                                                                      const ScanParams p) {
-  constexpr int S = Cfg::S, LPC = Cfg::LPC, CH = Cfg::CH, TT = Cfg::TT, NS = Cfg::NS, NT = Cfg::NT;
+  constexpr int S = Cfg::S, LPC = Cfg::LPC, CPT = Cfg::CPT, CH = Cfg::CH, CHP = Cfg::CHP, TT = Cfg::TT,
+                NS = Cfg::NS, NT = Cfg::NT;
   // NOTE: derive every pointer from the extern array itself (no integer round-trips), otherwise the
   // compiler loses the shared address space and emits generic LD/ST instead of LDS/STS.
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* raw = smem;
-  T* obuf = reinterpret_cast<T*>(smem + NS * Cfg::RAW_STAGE);
-  float* w_dt = reinterpret_cast<float*>(smem + NS * Cfg::RAW_STAGE + Cfg::OBUF);
-  float* w_u = w_dt + TT * CH;
-  float* w_g = w_u + TT * CH;
-  float* w_B = w_g + TT * CH;
-  float* w_C = w_B + TT * kNState;
-  uint64_t* full = reinterpret_cast<uint64_t*>(w_C + TT * kNState);
+  T* __restrict__ obuf = reinterpret_cast<T*>(smem + NS * Cfg::RAW_STAGE);
+  float* __restrict__ w_dt = reinterpret_cast<float*>(smem + NS * Cfg::RAW_STAGE + Cfg::OBUF);
+  float* __restrict__ w_u = w_dt + TT * CHP;
+  float* __restrict__ w_g = w_u + TT * CHP;
+  float* __restrict__ w_B = w_g + TT * CHP;
+  float* __restrict__ w_C = w_B + TT * kNState;
+  float* __restrict__ s_bias = w_C + TT * kNState;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + CH);
 
   const int tid = threadIdx.x;
   const int nchunk = p.D / CH;
   const int b = blockIdx.x / nchunk;
   const int c0 = (blockIdx.x % nchunk) * CH;
-  const int c = tid / LPC;    // channel within the CTA
-  const int sub = tid % LPC;  // which S-state slice of the channel
+  const int sub = tid % LPC;          // which S-state slice
+  const int ch0 = (tid / LPC) * CPT;  // first of this thread's CPT channels (within the CTA)
   const int ntiles = (p.L + TT - 1) / TT;
   const bool has_z = p.z != nullptr;
 
@@ -91,6 +133,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < CH; i += NT) s_bias[i] = p.dbias ? p.dbias[c0 + i] : 0.f;
   __syncthreads();
 
   // producer (one thread): one tensor copy per operand per tile; rows past L are zero-filled by the TMA unit
@@ -110,18 +153,19 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
   }
 
   // per-thread constants: A pre-scaled by log2(e) so exp(dt*A) = ex2(dt*A2)
-  float2 A2[S / 2];
-  float2 h[S / 2];
+  float2 A2[CPT][S / 2];
+  float2 h[CPT][S / 2];
+  float Dc[CPT];
 #pragma unroll
-  for (int j = 0; j < S / 2; ++j) {
-    const float* Ap = p.A + (long)(c0 + c) * kNState + sub * S + 2 * j;
-    A2[j] = make_float2(Ap[0] * kLog2e, Ap[1] * kLog2e);
-    h[j] = make_float2(0.f, 0.f);
+  for (int cp = 0; cp < CPT; ++cp) {
+#pragma unroll
+    for (int j = 0; j < S / 2; ++j) {
+      const float* Ap = p.A + (long)(c0 + ch0 + cp) * kNState + sub * S + 2 * j;
+      A2[cp][j] = make_float2(Ap[0] * kLog2e, Ap[1] * kLog2e);
+      h[cp][j] = make_float2(0.f, 0.f);
+    }
+    Dc[cp] = p.Dv ? p.Dv[c0 + ch0 + cp] : 0.f;
   }
-  const float Dc = p.Dv ? p.Dv[c0 + c] : 0.f;
-  // pre-pass mapping: element e = r*CH + cc; NT is a multiple of CH so cc is fixed per thread
-  const int cc = tid % CH;
-  const float bias_cc = p.dbias ? p.dbias[c0 + cc] : 0.f;
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int s = tile % NS;
@@ -137,17 +181,27 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
 
     // ---- pre-pass: softplus(delta + bias), silu(z), widen to fp32.  Always the whole tile: rows past L were
     // zero-filled by the TMA unit, their results are clipped by the TMA store and nothing after them is used.
-#pragma unroll
-    for (int r = tid / CH; r < TT; r += NT / CH) {
-      const int e = r * CH + cc;
-      const float dv = to_f32<T>(sd[e]) + bias_cc;
-      w_dt[e] = p.softplus ? softplus_f(dv) : dv;
-      w_u[e] = to_f32<T>(su[e]);
-      w_g[e] = has_z ? silu_f(to_f32<T>(sz[e])) : 1.f;
+    // Four adjacent channels per thread and iteration (128-bit LDS / STS); ncu showed this pass at ~35% of all
+    // issued instructions when done element-wise.
+#pragma unroll 2
+    for (int g = tid; g < TT * CH / 4; g += NT) {
+      const int r = g / (CH / 4), cc = (g % (CH / 4)) * 4;
+      const float4 bs = *reinterpret_cast<const float4*>(s_bias + cc);
+      float4 dv = lds4<T>(sd + r * CH + cc);
+      dv.x += bs.x, dv.y += bs.y, dv.z += bs.z, dv.w += bs.w;
+      if (p.softplus) dv = make_float4(softplus_f(dv.x), softplus_f(dv.y), softplus_f(dv.z), softplus_f(dv.w));
+      *reinterpret_cast<float4*>(w_dt + r * CHP + cc) = dv;
+      *reinterpret_cast<float4*>(w_u + r * CHP + cc) = lds4<T>(su + r * CH + cc);
+      float4 gv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_z) {
+        const float4 zv = lds4<T>(sz + r * CH + cc);
+        gv = make_float4(silu_f(zv.x), silu_f(zv.y), silu_f(zv.z), silu_f(zv.w));
+      }
+      *reinterpret_cast<float4*>(w_g + r * CHP + cc) = gv;
     }
-    for (int e = tid; e < TT * kNState; e += NT) {
-      w_B[e] = to_f32<T>(sB[e]);
-      w_C[e] = to_f32<T>(sC[e]);
+    for (int g = tid; g < TT * kNState / 4; g += NT) {
+      *reinterpret_cast<float4*>(w_B + 4 * g) = lds4<T>(sB + 4 * g);
+      *reinterpret_cast<float4*>(w_C + 4 * g) = lds4<T>(sC + 4 * g);
     }
     // the previous tile's TMA store must have finished reading obuf before it is rewritten
     if (tid == 0) bulk_wait_read0();
@@ -159,55 +213,60 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     // ---- the recurrence over this tile, GRP steps at a time: all shared-memory operands of a group are
     // fetched up front (independent LDS in flight), then the dependent FMUL2 / MUFU / FFMA2 chain runs.
     constexpr int GRP = LPC >= 2 ? LPC : 2;
-#pragma unroll 1
+#pragma unroll
     for (int r0 = 0; r0 < TT; r0 += GRP) {
-      float dtv[GRP], uv[GRP];
-      float2 Bv[GRP][S / 2], Cv[GRP][S / 2];
+      float dtv[GRP][CPT], uv[GRP][CPT], Bv[GRP][S], Cv[GRP][S];
 #pragma unroll
       for (int q = 0; q < GRP; ++q) {
         const int r = r0 + q;
-        dtv[q] = w_dt[r * CH + c];
-        uv[q] = w_u[r * CH + c];
-        const float2* Bp = reinterpret_cast<const float2*>(w_B + r * kNState + sub * S);
-        const float2* Cp = reinterpret_cast<const float2*>(w_C + r * kNState + sub * S);
-#pragma unroll
-        for (int j = 0; j < S / 2; ++j) {
-          Bv[q][j] = Bp[j];
-          Cv[q][j] = Cp[j];
-        }
+        lds_vec<CPT>(w_dt + r * CHP + ch0, dtv[q]);
+        lds_vec<CPT>(w_u + r * CHP + ch0, uv[q]);
+        lds_vec<S>(w_B + r * kNState + sub * S, Bv[q]);
+        lds_vec<S>(w_C + r * kNState + sub * S, Cv[q]);
       }
-      float part[GRP];
+      float part[GRP][CPT];
 #pragma unroll
       for (int q = 0; q < GRP; ++q) {
-        const float dtu = dtv[q] * uv[q];
-        const float2 dt2 = make_float2(dtv[q], dtv[q]);
-        const float2 dtu2 = make_float2(dtu, dtu);
-        float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < S / 2; ++j) {
-          const float2 x = __fmul2_rn(dt2, A2[j]);
-          const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          const float2 bu = __fmul2_rn(dtu2, Bv[q][j]);
-          h[j] = __ffma2_rn(a, h[j], bu);
-          acc2 = __ffma2_rn(h[j], Cv[q][j], acc2);
+        for (int cp = 0; cp < CPT; ++cp) {
+          const float dtu = dtv[q][cp] * uv[q][cp];
+          const float2 dt2 = make_float2(dtv[q][cp], dtv[q][cp]);
+          const float2 dtu2 = make_float2(dtu, dtu);
+          float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < S / 2; ++j) {
+            const float2 x = __fmul2_rn(dt2, A2[cp][j]);
+            const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            const float2 bu = __fmul2_rn(dtu2, make_float2(Bv[q][2 * j], Bv[q][2 * j + 1]));
+            h[cp][j] = __ffma2_rn(a, h[cp][j], bu);
+            acc2 = __ffma2_rn(h[cp][j], make_float2(Cv[q][2 * j], Cv[q][2 * j + 1]), acc2);
+          }
+          part[q][cp] = acc2.x + acc2.y;
         }
-        part[q] = acc2.x + acc2.y;
       }
 #pragma unroll
       for (int g2 = 0; g2 < GRP; g2 += LPC) {
-        // transposed butterfly: lane `sub` ends with the full sum of step r0 + g2 + sub
+        // transposed butterfly: lane `sub` ends with the full sums of step r0 + g2 + sub
 #pragma unroll
         for (int o = LPC / 2; o >= 1; o >>= 1) {
           const bool up = (sub & o) != 0;
 #pragma unroll
           for (int i = 0; i < o; ++i) {
-            const float send = up ? part[g2 + i] : part[g2 + i + o];
-            const float keep = up ? part[g2 + i + o] : part[g2 + i];
-            part[g2 + i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+#pragma unroll
+            for (int cp = 0; cp < CPT; ++cp) {
+              const float send = up ? part[g2 + i][cp] : part[g2 + i + o][cp];
+              const float keep = up ? part[g2 + i + o][cp] : part[g2 + i][cp];
+              part[g2 + i][cp] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
           }
         }
-        const int e = (r0 + g2 + sub) * CH + c;
-        obuf[e] = from_f32<T>((part[g2] + Dc * w_u[e]) * w_g[e]);
+        const int r = r0 + g2 + sub;
+        float uu[CPT], gg[CPT];
+        lds_vec<CPT>(w_u + r * CHP + ch0, uu);
+        lds_vec<CPT>(w_g + r * CHP + ch0, gg);
+#pragma unroll
+        for (int cp = 0; cp < CPT; ++cp)
+          obuf[r * CH + ch0 + cp] = from_f32<T>((part[g2][cp] + Dc[cp] * uu[cp]) * gg[cp]);
       }
     }
 
@@ -221,9 +280,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
   if (tid == 0) bulk_wait0();
 }
 
-template <typename T, int S, int CH, int TT, int NS>
+template <typename T, int S, int CPT, int CH, int TT, int NS>
 static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = ScanCfg<T, S, CH, TT, NS>;
+  using Cfg = ScanCfg<T, S, CPT, CH, TT, NS>;
   auto kern = selective_scan_fwd_kernel<Cfg, T>;
   static bool attr_done = false;  // idempotent; a benign race only repeats the call
   if (!attr_done) {
@@ -250,25 +309,26 @@ static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
 
 template <typename T>
 static int dispatch_scan(const ScanParams& p, int dtype, int variant, cudaStream_t stream) {
-  // variant: states per thread.  0 = heuristic on the amount of independent work.
+  // variant = 100 * (channels per thread) + (states per thread); 0 = heuristic on the independent work available.
   const long rows = (long)p.batch * p.D;
-  if (variant == 0) variant = rows >= 148L * 4 * 32 * 16 ? 16 : (rows >= 148L * 4 * 32 * 4 ? 8 : 4);
+  if (variant == 0) variant = rows >= 148L * 4 * 32 * 16 ? 216 : (rows >= 148L * 4 * 32 * 4 ? 208 : 204);
+  if (variant < 100) variant += 100;
   if (p.D % 64 == 0) {
     switch (variant) {
-      case 16: return launch_scan<T, 16, 64, 16, 3>(p, dtype, stream);
-      case 8: return launch_scan<T, 8, 64, 16, 3>(p, dtype, stream);
-      case 4: return launch_scan<T, 4, 64, 16, 3>(p, dtype, stream);
-      case 2: return launch_scan<T, 2, 32, 16, 3>(p, dtype, stream);
-      // tuning alternatives (100*k + S): narrower CTAs / longer tiles
-      case 104: return launch_scan<T, 4, 32, 16, 3>(p, dtype, stream);
-      case 108: return launch_scan<T, 8, 32, 16, 3>(p, dtype, stream);
-      case 204: return launch_scan<T, 4, 64, 32, 2>(p, dtype, stream);
-      case 208: return launch_scan<T, 8, 64, 32, 2>(p, dtype, stream);
-      case 304: return launch_scan<T, 4, 32, 32, 2>(p, dtype, stream);
-      case 102: return launch_scan<T, 2, 64, 16, 3>(p, dtype, stream);
+      case 102: return launch_scan<T, 2, 1, 32, 16, 3>(p, dtype, stream);
+      case 104: return launch_scan<T, 4, 1, 64, 16, 3>(p, dtype, stream);
+      case 108: return launch_scan<T, 8, 1, 64, 16, 3>(p, dtype, stream);
+      case 116: return launch_scan<T, 16, 1, 64, 16, 3>(p, dtype, stream);
+      case 202: return launch_scan<T, 2, 2, 64, 16, 3>(p, dtype, stream);
+      case 204: return launch_scan<T, 4, 2, 64, 16, 3>(p, dtype, stream);
+      case 208: return launch_scan<T, 8, 2, 64, 16, 3>(p, dtype, stream);
+      case 216: return launch_scan<T, 16, 2, 64, 16, 3>(p, dtype, stream);
+      case 402: return launch_scan<T, 2, 4, 64, 16, 3>(p, dtype, stream);
+      case 404: return launch_scan<T, 4, 4, 64, 16, 3>(p, dtype, stream);
+      case 408: return launch_scan<T, 8, 4, 64, 16, 3>(p, dtype, stream);
     }
   } else if (p.D % 16 == 0) {
-    return launch_scan<T, 4, 16, 32, 2>(p, dtype, stream);
+    return launch_scan<T, 2, 1, 16, 32, 2>(p, dtype, stream);
   }
   set_error("selective_scan_fwd: unsupported D=%d / variant=%d (D must be a multiple of 16)", p.D, variant);
   return SIM_ERR_INVALID;

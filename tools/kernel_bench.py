@@ -82,7 +82,7 @@ def main():
     shapes = [(32, 512, 768), (32, 1024, 768), (256, 512, 768)] if not quick else [(32, 512, 768)]
     for (B, L, D) in (shapes if want("scan") else []):
         for dtype in (torch.float32, torch.bfloat16):
-            variants = (2, 4, 8, 16, 102, 104, 108, 204, 208, 304) if "--variants" in sys.argv else (0, 4, 8)
+            variants = (102, 104, 108, 116, 202, 204, 208, 216, 402, 404, 408) if "--variants" in sys.argv else (0,)
             for variant in variants:
                 nsets = max(2, int(300e6 // (4 * B * L * D * (4 if dtype == torch.float32 else 2))) + 1)
                 fns, alg = scan_case(B, L, D, dtype, variant, min(nsets, 4))

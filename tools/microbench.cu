@@ -84,6 +84,78 @@ void run(const char* name, double ops_per_iter_per_thread, float* out) {
          total / (ms * 1e-3) / 148.0 / (clk_khz * 1e3), clk_khz / 1000);
 }
 
+// ---- shared-memory broadcast patterns: how many LSU wavefronts does a warp-wide LDS cost when lanes share addresses?
+template <int MODE>
+__global__ void __launch_bounds__(256) ks(float* out, int stride_sel) {
+  __shared__ __align__(16) float sm[4096];
+  for (int i = threadIdx.x; i < 4096; i += 256) sm[i] = i;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  int base;
+  if (MODE == 0) base = 0;                       // LDS.128, all lanes same address
+  else if (MODE == 1) base = (lane & 3) * 4;     // LDS.128, 4 distinct addresses (8 lanes each, interleaved)
+  else if (MODE == 2) base = lane * 4;           // LDS.128, all distinct (512 B)
+  else if (MODE == 3) base = 0;                  // LDS.32, all lanes same word
+  else if (MODE == 4) base = lane;               // LDS.32, all distinct
+  else if (MODE == 5) base = (lane >> 3) * 4;    // LDS.128, 4 distinct addresses, one per quarter-warp
+  else base = (lane & 1) * 4;                    // LDS.128, 2 distinct addresses interleaved
+  base += stride_sel;  // 0 at run time; keeps the address opaque
+  float acc = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      const int off = (base + i * 128 + (it & 7) * 16) & 4095;
+      if (MODE == 3 || MODE == 4) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(sm + off)));
+        acc += v;
+      } else {
+        float x, y, z, w;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
+                     : "r"((unsigned)__cvta_generic_to_shared(sm + (off & ~3))));
+        acc += x + w;
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) kshfl(float* out, float seed) {
+  float a[UNR];
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) a[i] = seed + i + threadIdx.x;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], 1 + (i & 3));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+void run_generic(const char* name, F launch) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch();
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  launch();
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  int clk_khz;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  // warp-instructions per SM: grid*block/32*ITERS*UNR / 148
+  const double winst = (double)148 * 8 * 256 / 32 * ITERS * UNR / 148.0;
+  printf("%-44s %8.3f ms  %6.2f cycles per warp-instruction per SM (at %d MHz)\n", name, ms,
+         ms * 1e-3 * clk_khz * 1e3 / winst, clk_khz / 1000);
+}
+
 int main() {
   float* out;
   cudaMalloc(&out, 148 * 8 * 256 * sizeof(float));
@@ -94,6 +166,14 @@ int main() {
   run<6>("FFMA+EX2 1:1 (pairs)", 1, out);
   run<3>("scan mix scalar (updates)", 1, out);
   run<4>("scan mix packed (updates)", 2, out);
+  run_generic("LDS.128 all lanes same address", [&] { ks<0><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.128 4 addresses interleaved (lane&3)", [&] { ks<1><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.128 4 addresses, one per quarter-warp", [&] { ks<5><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.128 2 addresses interleaved (lane&1)", [&] { ks<6><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.128 all distinct", [&] { ks<2><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.32 all lanes same word", [&] { ks<3><<<148 * 8, 256>>>(out, 0); });
+  run_generic("LDS.32 all distinct", [&] { ks<4><<<148 * 8, 256>>>(out, 0); });
+  run_generic("SHFL.BFLY", [&] { kshfl<<<148 * 8, 256>>>(out, 0.5f); });
   printf("cuda error: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
