@@ -116,8 +116,29 @@ int sim_causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float*
  * N must be 16.  variant: 0 = auto, else states per thread (2, 4, 8, 16). */
 int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
                            const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
-                           long ld_z, const float* delta_bias, void* out, long ld_out, int batch, int L, int D,
-                           int N, int delta_softplus, int dtype, int variant, sim_stream_t stream);
+                           long ld_z, const float* delta_bias, void* out, long ld_out, float* checkpoints, int batch,
+                           int L, int D, int N, int delta_softplus, int dtype, int variant, sim_stream_t stream);
+
+/* Training forward only: `checkpoints` (NULL for inference) receives the SSM state at the start of every
+ * 16-step tile, fp32 (batch, ceil(L/16), D, 16); it is the only tensor saved for the backward pass (mamba-ssm
+ * recomputes from chunk states in the same spirit).  Size in bytes: */
+size_t sim_selective_scan_checkpoint_bytes(int batch, int L, int D);
+
+/* a-11  selective scan backward (recompute from checkpoints).  du, ddelta, dz (batch*L, D) in the input dtype;
+ * dB, dC (batch*L, N) f32, dA (D,N), dD, ddelta_bias (D) f32 are ACCUMULATED into (the caller zeroes them).
+ * z / dz / Dvec / delta_bias / dD / ddelta_bias may be NULL. */
+int sim_selective_scan_bwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                           const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
+                           long ld_z, const float* delta_bias, const void* dout, long ld_dout,
+                           const float* checkpoints, void* du, long ld_du, void* ddelta, long ld_ddelta, void* dz,
+                           long ld_dz, float* dB, float* dC, float* dA, float* dD, float* ddelta_bias, int batch,
+                           int L, int D, int N, int delta_softplus, int dtype, sim_stream_t stream);
+
+/* a-12  causal conv1d backward (recomputes the pre-activation from x).  dx (batch*L, D) in the input dtype;
+ * dw (D, width) and dbias (D) f32 are ACCUMULATED into (the caller zeroes them); dbias may be NULL. */
+int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float* bias, const void* dy, long ld_dy,
+                          void* dx, long ld_dx, float* dw, float* dbias, int batch, int L, int D, int width,
+                          int silu, int dtype, sim_stream_t stream);
 
 #ifdef __cplusplus
 }

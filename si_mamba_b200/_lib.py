@@ -39,8 +39,13 @@ SIGNATURES = {
     "sim_gather_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sim_add_layernorm": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _f, _i, _i, _p]),
     "sim_causal_conv1d_fwd": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
-    "sim_selective_scan_fwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l,
+    "sim_selective_scan_fwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p,
                                     _i, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_selective_scan_checkpoint_bytes": (_sz, [_i, _i, _i]),
+    "sim_selective_scan_bwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p,
+                                    _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _p,
+                                    _i, _i, _i, _i, _i, _i, _p]),
+    "sim_causal_conv1d_bwd": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }
 
 _lib = None

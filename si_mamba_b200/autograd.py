@@ -20,33 +20,6 @@ def _amp_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
-class CausalConv1dTM(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight, bias)
-        return ops.causal_conv1d_tm(x, weight, bias, silu=True)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, weight, bias = ctx.saved_tensors
-        dx, dw, db = ops.causal_conv1d_bwd_tm(x, weight, bias, dy)
-        return dx, dw.reshape(weight.shape).to(weight.dtype), db.to(bias.dtype)
-
-
-class SelectiveScanTM(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, u, delta, A, Bm, Cm, D, z, delta_bias):
-        ctx.save_for_backward(u, delta, A, Bm, Cm, D, z, delta_bias)
-        return ops.selective_scan_tm(u, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus=True)
-
-    @staticmethod
-    def backward(ctx, dout):
-        u, delta, A, Bm, Cm, D, z, delta_bias = ctx.saved_tensors
-        du, ddelta, dA, dB, dC, dD, dz, dbias = ops.selective_scan_bwd_tm(
-            u, delta, A, Bm, Cm, D, z, delta_bias, dout, delta_softplus=True)
-        return du, ddelta, dA, dB, dC, dD, dz, dbias
-
-
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
                    dt_rank: int, d_state: int) -> torch.Tensor:
     """Token-major Mamba mixer body.  hidden (B, L, d_model) -> (B, L, d_model)."""
@@ -59,7 +32,7 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     x, z = xz[..., :d_inner], xz[..., d_inner:]
     A = -torch.exp(A_log.float())
     if need_grad:
-        u = CausalConv1dTM.apply(x, conv_w, conv_b)
+        u = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
     else:
         u = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
     x_dbl = F.linear(u, x_proj_w.to(act))  # (B, L, dt_rank + 2*d_state)
@@ -67,7 +40,7 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]
     Cm = x_dbl[..., dt_rank + d_state:]
     if need_grad:
-        y = SelectiveScanTM.apply(u, dt, A, Bm, Cm, D.float(), z, dt_proj_b.float())
+        y = ops.SelectiveScanTM.apply(u, dt, A, Bm, Cm, D, z, dt_proj_b, True)
     else:
         y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True)
     return F.linear(y, out_proj_w.to(act))

@@ -106,8 +106,8 @@ int sim_causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float*
 
 int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
                            const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
-                           long ld_z, const float* delta_bias, void* out, long ld_out, int batch, int L, int D,
-                           int N, int delta_softplus, int dtype, int variant, sim_stream_t stream) {
+                           long ld_z, const float* delta_bias, void* out, long ld_out, float* checkpoints, int batch,
+                           int L, int D, int N, int delta_softplus, int dtype, int variant, sim_stream_t stream) {
   if (N != 16) {
     sim::set_error("sim_selective_scan_fwd: d_state must be 16 (got %d)", N);
     return SIM_ERR_INVALID;
@@ -117,7 +117,40 @@ int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_
   p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
   p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_out = ld_out;
   p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  p.ckpt = checkpoints;
   return sim::selective_scan_fwd(p, dtype, variant, static_cast<cudaStream_t>(stream));
+}
+
+size_t sim_selective_scan_checkpoint_bytes(int batch, int L, int D) {
+  if (batch <= 0 || L <= 0 || D <= 0) return 0;
+  return (size_t)batch * ((L + sim::kScanTile - 1) / sim::kScanTile) * D * 16 * sizeof(float);
+}
+
+int sim_selective_scan_bwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                           const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
+                           long ld_z, const float* delta_bias, const void* dout, long ld_dout,
+                           const float* checkpoints, void* du, long ld_du, void* ddelta, long ld_ddelta, void* dz,
+                           long ld_dz, float* dB, float* dC, float* dA, float* dD, float* ddelta_bias, int batch,
+                           int L, int D, int N, int delta_softplus, int dtype, sim_stream_t stream) {
+  if (N != 16) {
+    sim::set_error("sim_selective_scan_bwd: d_state must be 16 (got %d)", N);
+    return SIM_ERR_INVALID;
+  }
+  sim::ScanBwdParams p;
+  p.u = u, p.delta = delta, p.z = z, p.Bm = Bm, p.Cm = Cm, p.dout = dout;
+  p.A = A, p.Dv = Dvec, p.dbias = delta_bias, p.ckpt = checkpoints;
+  p.du = du, p.ddelta = ddelta, p.dz = dz, p.dB = dB, p.dC = dC, p.dA = dA, p.dD = dD, p.ddbias = ddelta_bias;
+  p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_dout = ld_dout;
+  p.ld_du = ld_du, p.ld_ddelta = ld_ddelta, p.ld_dz = ld_dz;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  return sim::selective_scan_bwd(p, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float* bias, const void* dy, long ld_dy,
+                          void* dx, long ld_dx, float* dw, float* dbias, int batch, int L, int D, int width,
+                          int silu, int dtype, sim_stream_t stream) {
+  return sim::causal_conv1d_bwd(x, ld_x, w, bias, dy, ld_dy, dx, ld_dx, dw, dbias, batch, L, D, width, silu, dtype,
+                                static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -118,4 +118,133 @@ int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bia
   return check_launch("causal_conv1d_fwd");
 }
 
+// ----------------------------------------------------------------------------- backward
+// p = bias + sum_j w_j x[t-3+j];  y = silu(p).  dp = dy * silu'(p);  dx[t] = sum_j w_j dp[t+3-j];
+// dw_j += sum_t dp[t] x[t-3+j];  db += sum_t dp[t].  Each thread owns 4 adjacent channels and a chunk of TC steps;
+// it recomputes p over [t0, t0+TC+3) from x (halo 3 rows each side), keeps dp in a 4-deep register window and
+// accumulates its dw / db partials in registers -> one fp32 atomic per (thread, channel, tap).
+template <typename T, int TC>
+__global__ void __launch_bounds__(128) causal_conv1d_bwd_kernel(const T* __restrict__ x, long ld_x,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                const T* __restrict__ dy, long ld_dy,
+                                                                T* __restrict__ dx, long ld_dx, float* __restrict__ dw,
+                                                                float* __restrict__ db, int batch, int L, int D,
+                                                                int silu) {
+  const int nv = D / 4;
+  const int nchunk = (L + TC - 1) / TC;
+  const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long)batch * nchunk * nv) return;
+  const int v = item % nv;
+  const int ch = (item / nv) % nchunk;
+  const int b = item / ((long)nv * nchunk);
+  const int d0 = v * 4;
+  const int t0 = ch * TC;
+  const int t1 = min(L, t0 + TC);
+
+  float wr[4][kConvW];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long)(d0 + c) * kConvW);
+    wr[c][0] = wv.x, wr[c][1] = wv.y, wr[c][2] = wv.z, wr[c][3] = wv.w;
+  }
+  const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const T* xb = x + ((long)b * L) * ld_x + d0;
+  const T* gb = dy + ((long)b * L) * ld_dy + d0;
+  T* ob = dx + ((long)b * L) * ld_dx + d0;
+
+  auto ldx = [&](int t) { return (t >= 0 && t < L) ? Vec4<T>::load(xb + (long)t * ld_x) : make_float4(0.f, 0.f, 0.f, 0.f); };
+  // xw[j] = x[s-3+j] for the step s whose dp is being produced
+  float4 xw[kConvW];
+#pragma unroll
+  for (int j = 0; j < kConvW - 1; ++j) xw[j + 1] = ldx(t0 - (kConvW - 1) + j);
+  float4 dpw[kConvW];  // dpw[j] = dp[s-3+j] after producing step s
+#pragma unroll
+  for (int j = 0; j < kConvW; ++j) dpw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dwa[4][kConvW] = {};
+  float dba[4] = {};
+
+  // produce dp for s = t0 .. t1+2 (clipped to L); once dp[s] is known, dx[s-3] is complete
+  for (int s = t0; s < t1 + kConvW - 1; ++s) {
+#pragma unroll
+    for (int j = 0; j < kConvW - 1; ++j) xw[j] = xw[j + 1];
+    xw[kConvW - 1] = ldx(s);
+    float4 dps = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < L) {
+      float4 pre = bv;
+#pragma unroll
+      for (int j = 0; j < kConvW; ++j) {
+        pre.x = fmaf(wr[0][j], xw[j].x, pre.x);
+        pre.y = fmaf(wr[1][j], xw[j].y, pre.y);
+        pre.z = fmaf(wr[2][j], xw[j].z, pre.z);
+        pre.w = fmaf(wr[3][j], xw[j].w, pre.w);
+      }
+      const float4 g = Vec4<T>::load(gb + (long)s * ld_dy);
+      if (silu) {
+        const float sx = sigmoid_f(pre.x), sy = sigmoid_f(pre.y), sz = sigmoid_f(pre.z), sw = sigmoid_f(pre.w);
+        dps.x = g.x * sx * (1.f + pre.x * (1.f - sx));
+        dps.y = g.y * sy * (1.f + pre.y * (1.f - sy));
+        dps.z = g.z * sz * (1.f + pre.z * (1.f - sz));
+        dps.w = g.w * sw * (1.f + pre.w * (1.f - sw));
+      } else {
+        dps = g;
+      }
+      if (s < t1) {  // parameter gradients: each time step is owned by exactly one chunk
+#pragma unroll
+        for (int j = 0; j < kConvW; ++j) {
+          dwa[0][j] = fmaf(dps.x, xw[j].x, dwa[0][j]);
+          dwa[1][j] = fmaf(dps.y, xw[j].y, dwa[1][j]);
+          dwa[2][j] = fmaf(dps.z, xw[j].z, dwa[2][j]);
+          dwa[3][j] = fmaf(dps.w, xw[j].w, dwa[3][j]);
+        }
+        dba[0] += dps.x, dba[1] += dps.y, dba[2] += dps.z, dba[3] += dps.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kConvW - 1; ++j) dpw[j] = dpw[j + 1];
+    dpw[kConvW - 1] = dps;
+    const int t = s - (kConvW - 1);  // dx[t] = sum_j w_j dp[t+3-j] = sum_j w_j dpw[3-j]
+    if (t >= t0 && t < t1) {
+      float4 o;
+      o.x = wr[0][0] * dpw[3].x + wr[0][1] * dpw[2].x + wr[0][2] * dpw[1].x + wr[0][3] * dpw[0].x;
+      o.y = wr[1][0] * dpw[3].y + wr[1][1] * dpw[2].y + wr[1][2] * dpw[1].y + wr[1][3] * dpw[0].y;
+      o.z = wr[2][0] * dpw[3].z + wr[2][1] * dpw[2].z + wr[2][2] * dpw[1].z + wr[2][3] * dpw[0].z;
+      o.w = wr[3][0] * dpw[3].w + wr[3][1] * dpw[2].w + wr[3][2] * dpw[1].w + wr[3][3] * dpw[0].w;
+      Vec4<T>::store(ob + (long)t * ld_dx, o);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int j = 0; j < kConvW; ++j) atomicAdd(dw + (long)(d0 + c) * kConvW + j, dwa[c][j]);
+    if (db) atomicAdd(db + d0 + c, dba[c]);
+  }
+}
+
+int causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float* bias, const void* dy, long ld_dy,
+                      void* dx, long ld_dx, float* dw, float* db, int batch, int L, int D, int width, int silu,
+                      int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(width == kConvW, SIM_ERR_INVALID, "causal_conv1d_bwd: only width 4 is built (got %d)", width);
+  SIM_REQUIRE(D % 4 == 0 && batch > 0 && L > 0, SIM_ERR_INVALID, "causal_conv1d_bwd: D must be a multiple of 4");
+  SIM_REQUIRE(dtype == 0 || dtype == 1, SIM_ERR_INVALID, "causal_conv1d_bwd: dtype must be 0 (fp32) or 1 (bf16)");
+  SIM_REQUIRE(x && w && dy && dx && dw, SIM_ERR_INVALID, "causal_conv1d_bwd: null tensor");
+  const int es = dtype == 0 ? 4 : 2;
+  const uintptr_t vmask = 4 * es - 1;
+  SIM_REQUIRE(((uintptr_t)x & vmask) == 0 && ((uintptr_t)dy & vmask) == 0 && ((uintptr_t)dx & vmask) == 0 &&
+                  aligned16(w) && ld_x % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && (!bias || aligned16(bias)),
+              SIM_ERR_ALIGN, "causal_conv1d_bwd: tensors need vector-aligned bases and row strides");
+  constexpr int TC = 64;
+  const long items = (long)batch * ((L + TC - 1) / TC) * (D / 4);
+  const int grid = (int)((items + 127) / 128);
+  if (dtype == 0)
+    causal_conv1d_bwd_kernel<float, TC><<<grid, 128, 0, stream>>>(
+        static_cast<const float*>(x), ld_x, w, bias, static_cast<const float*>(dy), ld_dy, static_cast<float*>(dx),
+        ld_dx, dw, db, batch, L, D, silu);
+  else
+    causal_conv1d_bwd_kernel<__nv_bfloat16, TC><<<grid, 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<const __nv_bfloat16*>(dy), ld_dy,
+        static_cast<__nv_bfloat16*>(dx), ld_dx, dw, db, batch, L, D, silu);
+  return check_launch("causal_conv1d_bwd");
+}
+
 }  // namespace sim

@@ -30,8 +30,37 @@ struct ScanParams {
   long ld_u, ld_delta, ld_z, ld_B, ld_C, ld_out;
   int batch, L, D;
   int softplus;
+  float* ckpt;  // optional (batch, ceil(L/kScanTile), D, 16) fp32: state at the START of every tile (for backward)
 };
+constexpr int kScanTile = 16;  // time steps per tile of the scan kernels == checkpoint interval
 int selective_scan_fwd(const ScanParams&, int, int, cudaStream_t);
+
+struct ScanBwdParams {
+  const void* u;
+  const void* delta;
+  const void* z;
+  const void* Bm;
+  const void* Cm;
+  const void* dout;
+  const float* A;
+  const float* Dv;
+  const float* dbias;
+  const float* ckpt;
+  void* du;
+  void* ddelta;
+  void* dz;
+  float* dB;      // (batch*L, 16) fp32, accumulated into (caller zeroes)
+  float* dC;
+  float* dA;      // (D, 16) fp32, accumulated into
+  float* dD;      // (D)
+  float* ddbias;  // (D)
+  long ld_u, ld_delta, ld_z, ld_B, ld_C, ld_dout, ld_du, ld_ddelta, ld_dz;
+  int batch, L, D;
+  int softplus;
+};
+int selective_scan_bwd(const ScanBwdParams&, int, cudaStream_t);
+int causal_conv1d_bwd(const void*, long, const float*, const float*, const void*, long, void*, long, float*, float*,
+                      int, int, int, int, int, int, cudaStream_t);
 
 struct SpectralParams {
   const float* center;

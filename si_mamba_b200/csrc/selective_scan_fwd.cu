@@ -50,6 +50,7 @@ struct ScanCfg {
   static constexpr int CPT = CPT_;              // adjacent channels per thread
   static constexpr int CH = CH_;                // channels per CTA
   static constexpr int TT = TT_;                // time steps per tile
+  static_assert(TT_ == kScanTile, "checkpoint interval is fixed by kScanTile");
   static constexpr int NS = NS_;                // raw stages in flight
   static constexpr int NT = (CH_ / CPT_) * LPC; // threads per CTA
   static constexpr int CHP = CH_ + 8;           // padded row stride (floats) of the work arrays
@@ -177,6 +178,15 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     const T* sB = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN);
     const T* sC = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC);
 
+    if (p.ckpt) {  // training forward: state at the start of this tile, layout (batch, tile, D, 16)
+#pragma unroll
+      for (int cp = 0; cp < CPT; ++cp) {
+        float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + ch0 + cp) * kNState +
+                                                sub * S);
+#pragma unroll
+        for (int j = 0; j < S / 2; ++j) dst[j] = h[cp][j];
+      }
+    }
     mbar_wait(&full[s], (tile / NS) & 1);
 
     // ---- pre-pass: softplus(delta + bias), silu(z), widen to fp32.  Always the whole tile: rows past L were
@@ -328,7 +338,7 @@ static int dispatch_scan(const ScanParams& p, int dtype, int variant, cudaStream
       case 408: return launch_scan<T, 8, 4, 64, 16, 3>(p, dtype, stream);
     }
   } else if (p.D % 16 == 0) {
-    return launch_scan<T, 2, 1, 16, 32, 2>(p, dtype, stream);
+    return launch_scan<T, 2, 1, 16, 16, 3>(p, dtype, stream);
   }
   set_error("selective_scan_fwd: unsupported D=%d / variant=%d (D must be a multiple of 16)", p.D, variant);
   return SIM_ERR_INVALID;

@@ -229,7 +229,7 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
 # ----------------------------------------------------------------------------- causal conv1d (a-12)
 def causal_conv1d_tm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool = True,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Token-major causal depthwise conv: x (B,L,D) (any uniform row stride), weight (D,W) -> (B,L,D)."""
+    """Token-major causal depthwise conv (forward only): x (B,L,D) (any uniform row stride), weight (D,W) -> (B,L,D)."""
     _cuda(x, weight, bias)
     B, L, D = x.shape
     ld_x = _tm(x)
@@ -241,22 +241,54 @@ def causal_conv1d_tm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
     return out
 
 
+def causal_conv1d_bwd_tm(x, weight, bias, dy, silu: bool = True):
+    """-> (dx (B,L,D) in x's dtype, dw (D,W) fp32, dbias (D) fp32)."""
+    _cuda(x, weight, bias, dy)
+    B, L, D = x.shape
+    dy = dy.contiguous()
+    dx = torch.empty(B, L, D, dtype=x.dtype, device=x.device)
+    w = _f32c(weight.reshape(D, -1))
+    dw = torch.zeros_like(w)
+    db = torch.zeros(D, dtype=torch.float32, device=x.device) if bias is not None else None
+    _lib.call("sim_causal_conv1d_bwd", _p(x), _tm(x), _p(w), _p(_f32c(bias)), _p(dy), _tm(dy), _p(dx), _tm(dx),
+              _p(dw), _p(db), B, L, D, w.shape[1], int(silu), _dt(x), _stream())
+    return dx, dw, db
+
+
+class CausalConv1dTM(torch.autograd.Function):
+    """Token-major causal conv1d + SiLU with the CUDA backward (recomputes the pre-activation from x)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        ctx.save_for_backward(x, weight, bias)
+        ctx.silu = silu
+        return causal_conv1d_tm(x, weight, bias, silu=silu)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dx, dw, db = causal_conv1d_bwd_tm(x, weight, bias, dy, ctx.silu)
+        return dx, dw.reshape(weight.shape).to(weight.dtype), None if bias is None else db.to(bias.dtype), None
+
+
 def causal_conv1d_fn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
                      activation: Optional[str] = None) -> torch.Tensor:
-    """causal-conv1d compatible signature: x (B,D,L) channel-major -> (B,D,L)."""
+    """causal-conv1d compatible signature: x (B,D,L) channel-major -> (B,D,L); differentiable."""
     assert activation in (None, "silu", "swish")
     xt = x.transpose(1, 2)
     if xt.stride(2) != 1 or (xt.shape[0] > 1 and xt.stride(0) != xt.shape[1] * xt.stride(1)):
         xt = xt.contiguous()
-    y = causal_conv1d_tm(xt, weight, bias, silu=activation is not None)
+    y = CausalConv1dTM.apply(xt, weight, bias, activation is not None)
     return y.transpose(1, 2)
 
 
 # ----------------------------------------------------------------------------- selective scan (a-11)
 def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False,
-                      out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
-    """Token-major selective scan.  u, delta, z (B,L,D); Bm, Cm (B,L,N) - all may be column slices of wider
-    row-major buffers; A (D,N) fp32.  Returns out (B,L,D) in u's dtype."""
+                      out: Optional[torch.Tensor] = None, variant: int = 0,
+                      checkpoints: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-major selective scan (forward only).  u, delta, z (B,L,D); Bm, Cm (B,L,N) - all may be column slices of
+    wider row-major buffers; A (D,N) fp32.  Returns out (B,L,D) in u's dtype.  ``checkpoints`` (fp32,
+    scan_checkpoint_shape) receives the tile-start states the backward kernel needs."""
     _cuda(u, delta, A, Bm, Cm, D, z, delta_bias)
     B, L, Dm = u.shape
     N = A.shape[1]
@@ -266,16 +298,63 @@ def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delt
     assert delta.dtype == u.dtype and Bm.dtype == u.dtype and Cm.dtype == u.dtype and (z is None or z.dtype == u.dtype)
     _lib.call("sim_selective_scan_fwd", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm), _tm(Bm), _p(Cm),
               _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(out), _tm(out),
-              B, L, Dm, N, int(delta_softplus), _dt(u), int(variant), _stream())
+              _p(checkpoints), B, L, Dm, N, int(delta_softplus), _dt(u), int(variant), _stream())
     return out
 
 
+def scan_checkpoint_shape(B: int, L: int, D: int):
+    return (B, (L + 15) // 16, D, 16)
+
+
+def selective_scan_bwd_tm(u, delta, A, Bm, Cm, D, z, delta_bias, dout, checkpoints, delta_softplus=True):
+    """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); du/ddelta/dz/dB/dC in u's dtype, the rest fp32."""
+    _cuda(u, delta, A, Bm, Cm, D, z, delta_bias, dout, checkpoints)
+    B, L, Dm = u.shape
+    N = A.shape[1]
+    dev = u.device
+    u, delta, Bm, Cm, z, dout = (_bulk_ok(t) for t in (u, delta, Bm, Cm, z, dout))
+    du = torch.empty(B, L, Dm, dtype=u.dtype, device=dev)
+    ddelta = torch.empty_like(du)
+    dz = torch.empty_like(du) if z is not None else None
+    dB = torch.zeros(B, L, N, dtype=torch.float32, device=dev)
+    dC = torch.zeros_like(dB)
+    dA = torch.zeros(Dm, N, dtype=torch.float32, device=dev)
+    dD = torch.zeros(Dm, dtype=torch.float32, device=dev) if D is not None else None
+    dbias = torch.zeros(Dm, dtype=torch.float32, device=dev) if delta_bias is not None else None
+    _lib.call("sim_selective_scan_bwd", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm), _tm(Bm), _p(Cm),
+              _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(dout), _tm(dout),
+              _p(checkpoints), _p(du), _tm(du), _p(ddelta), _tm(ddelta), _p(dz), 0 if dz is None else _tm(dz),
+              _p(dB), _p(dC), _p(dA), _p(dD), _p(dbias), B, L, Dm, N, int(delta_softplus), _dt(u), _stream())
+    return du, ddelta, dA, dB.to(u.dtype), dC.to(u.dtype), dD, dz, dbias
+
+
+class SelectiveScanTM(torch.autograd.Function):
+    """Token-major selective scan with the CUDA backward; saves the inputs and one checkpoint tensor."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus):
+        B, L, Dm = u.shape
+        ckpt = torch.empty(scan_checkpoint_shape(B, L, Dm), dtype=torch.float32, device=u.device)
+        out = selective_scan_tm(u, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, checkpoints=ckpt)
+        ctx.save_for_backward(u, delta, A, Bm, Cm, D, z, delta_bias, ckpt)
+        ctx.delta_softplus = delta_softplus
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u, delta, A, Bm, Cm, D, z, delta_bias, ckpt = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dz, dbias = selective_scan_bwd_tm(
+            u, delta, A, Bm, Cm, D, z, delta_bias, dout.contiguous(), ckpt, ctx.delta_softplus)
+        cast = lambda g, ref: None if (g is None or ref is None) else g.to(ref.dtype)
+        return du, ddelta, cast(dA, A), dB, dC, cast(dD, D), dz, cast(dbias, delta_bias), None
+
+
 def _bulk_ok(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """TMA bulk copies need 16-byte aligned row starts; copy the (rare) slices that are not."""
+    """TMA tensor maps need 16-byte aligned row starts; copy the (rare) slices that are not."""
     if t is None:
         return None
-    ok = t.stride(2) == 1 and (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1)) \
-        and (t.stride(1) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0
+    ok = t.stride(2) == 1 and (t.shape[0] == 1 or t.shape[1] == 1 or t.stride(0) == t.shape[1] * t.stride(1)) \
+        and (_tm(t) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0
     return t if ok else t.contiguous()
 
 
@@ -290,12 +369,15 @@ def _to_tm(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
-    """mamba-ssm compatible signature (channel-major): u, delta, z (B,D,L); B, C (B,N,L); A (D,N).
+    """mamba-ssm compatible signature (channel-major): u, delta, z (B,D,L); B, C (B,N,L); A (D,N); differentiable.
 
     Channel-major arguments that are transposed views of token-major memory are used in place;
     anything else is transposed once."""
     if return_last_state:
         raise NotImplementedError("return_last_state is not on SI-Mamba's path (inference_params is always None)")
-    out = selective_scan_tm(_to_tm(u), _to_tm(delta), A, _to_tm(B), _to_tm(C), D, _to_tm(z), delta_bias,
-                            delta_softplus)
+    args = (_to_tm(u), _to_tm(delta), A, _to_tm(B), _to_tm(C), D, _to_tm(z), delta_bias)
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in args):
+        out = SelectiveScanTM.apply(*args, bool(delta_softplus))
+    else:
+        out = selective_scan_tm(*args, delta_softplus)
     return out.transpose(1, 2)

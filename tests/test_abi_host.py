@@ -39,9 +39,10 @@ def test_invalid_arguments_fail_without_gpu(lib):
     """Argument validation happens before any CUDA call, so it can be exercised on CPU."""
     rc = lib.sim_fps(None, 1, 16, 4, None, None, None)
     assert rc == -1 and b"null" in lib.sim_last_error_string()
-    rc = lib.sim_selective_scan_fwd(None, 0, None, 0, None, None, 0, None, 0, None, None, 0, None, None, 0,
+    rc = lib.sim_selective_scan_fwd(None, 0, None, 0, None, None, 0, None, 0, None, None, 0, None, None, 0, None,
                                     1, 8, 64, 8, 1, 0, 0, None)
     assert rc == -1 and b"d_state" in lib.sim_last_error_string()
+    assert lib.sim_selective_scan_checkpoint_bytes(32, 512, 768) == 32 * 32 * 768 * 16 * 4
     rc = lib.sim_spectral_eig(None, 1, 2, 1, 1.0, 0, 1, None, None, None, None, None, None, 0, None)
     assert rc == -1
     assert lib.sim_spectral_eig_workspace_bytes(4, 128, 4) == 0      # fits shared memory

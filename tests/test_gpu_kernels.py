@@ -296,3 +296,56 @@ def test_conv_vs_oracle(ops, dtype, tol, B, D, L):
     ref = mamba.causal_conv1d_ref(x[..., :D].float().transpose(1, 2), w, b, "silu").transpose(1, 2)
     out = ops.causal_conv1d_tm(dev(x)[..., :D], dev(w), dev(b), True)
     assert torch.allclose(out.cpu().float(), ref, rtol=tol, atol=tol)
+
+
+# ----------------------------------------------------------------------------- backward (C2-C4 training configs)
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,D,L", [(2, 64, 37), (1, 128, 16), (2, 768, 130)])
+def test_scan_backward_vs_oracle(ops, dtype, tol, B, D, L):
+    """Gradients of the CUDA scan (autograd through the C ABI) vs autograd of selective_scan_ref."""
+    u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 3 * L + D)
+    cast = lambda t: t.to(dtype).float()
+    g = torch.Generator().manual_seed(L)
+    dout = torch.randn(B, D, L, generator=g)
+    ref_in = [cast(t).clone().requires_grad_(True) for t in (u, delta, Bm, Cm, z)]
+    ref_p = [t.clone().requires_grad_(True) for t in (A, Dv, bias)]
+    out_ref = mamba.selective_scan_ref(ref_in[0], ref_in[1], ref_p[0], ref_in[2], ref_in[3], ref_p[1], ref_in[4],
+                                       ref_p[2], True)
+    out_ref.backward(cast(dout))
+    tm = lambda t: dev(t.to(dtype).transpose(1, 2).contiguous()).requires_grad_(True)
+    cu_in = [tm(t) for t in (u, delta, Bm, Cm, z)]
+    cu_p = [dev(t).requires_grad_(True) for t in (A, Dv, bias)]
+    out = ops.SelectiveScanTM.apply(cu_in[0], cu_in[1], cu_p[0], cu_in[2], cu_in[3], cu_p[1], cu_in[4], cu_p[2], True)
+    assert rel_err(out.detach().cpu().float().transpose(1, 2), out_ref.detach()) < tol
+    out.backward(dev(dout.to(dtype).transpose(1, 2).contiguous()))
+    names = ["du", "ddelta", "dB", "dC", "dz"]
+    for name, a, r in zip(names, cu_in, ref_in):
+        assert rel_err(a.grad.cpu().float().transpose(1, 2), r.grad) < tol, name
+    for name, a, r in zip(["dA", "dD", "dbias"], cu_p, ref_p):
+        assert rel_err(a.grad.cpu(), r.grad) < tol, name
+
+
+def test_scan_backward_channel_major_api(ops):
+    """mamba-ssm style call (channel-major, no z / D / bias) is differentiable too."""
+    u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(2, 64, 40, 9)
+    ref_in = [t.clone().requires_grad_(True) for t in (u, delta, Bm, Cm)]
+    mamba.selective_scan_ref(ref_in[0], ref_in[1], A, ref_in[2], ref_in[3], None, None, bias, True).sum().backward()
+    cu_in = [dev(t).requires_grad_(True) for t in (u, delta, Bm, Cm)]
+    ops.selective_scan_fn(cu_in[0], cu_in[1], dev(A), cu_in[2], cu_in[3], None, None, dev(bias), True).sum().backward()
+    for a, r in zip(cu_in, ref_in):
+        assert rel_err(a.grad.cpu(), r.grad) < 1e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,D,L", [(2, 64, 5), (2, 768, 130), (1, 128, 64)])
+def test_conv_backward_vs_oracle(ops, dtype, tol, B, D, L):
+    g = torch.Generator().manual_seed(L + D)
+    x = torch.randn(B, L, D, generator=g).to(dtype)
+    w, b = torch.randn(D, 4, generator=g) * 0.5, torch.randn(D, generator=g) * 0.1
+    dy = torch.randn(B, L, D, generator=g).to(dtype)
+    xr, wr, br = x.float().clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    mamba.causal_conv1d_ref(xr.transpose(1, 2), wr, br, "silu").transpose(1, 2).backward(dy.float())
+    xc, wc, bc = dev(x).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
+    ops.CausalConv1dTM.apply(xc, wc, bc, True).backward(dev(dy))
+    assert rel_err(xc.grad.cpu().float(), xr.grad) < tol
+    assert rel_err(wc.grad.cpu(), wr.grad) < tol and rel_err(bc.grad.cpu(), br.grad) < tol
