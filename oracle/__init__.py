@@ -25,4 +25,4 @@ The pins this build creates for itself are (a) committed golden vectors in
 for the mixer (tests/test_oracle_mamba.py).
 """
 
-from . import tokenizer, spectral, mamba, model, mae  # noqa: F401
+from . import tokenizer, spectral, mamba, model, mae, seg  # noqa: F401

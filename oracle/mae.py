@@ -54,3 +54,43 @@ def rand_mask(B: int, G: int, mask_ratio: float, seed: int) -> torch.Tensor:
         p = torch.randperm(G, generator=g)
         out[b, p[:m]] = True
     return out
+
+
+def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """pytorch3d chamfer_distance(x, y, batch_reduction=None)[0], squared L2, mean over points (:2950, :3203)."""
+    d = (x[:, :, None, :] - y[:, None, :, :]).pow(2).sum(-1)
+    return d.min(dim=2).values.mean(dim=1) + d.min(dim=1).values.mean(dim=1)
+
+
+def point_mae_forward(sd: dict, cfg: dict, pts: torch.Tensor, mask: torch.Tensor, perm_override=None):
+    """Point_MAE_Mamba.forward (models/point_mamba.py:3053-3213), spectral method, eval mode, given the (B,G) mask.
+
+    Spectral ordering uses the batched variant (:3001-3050, deg.clamp(1e-12)).  Returns (loss, intermediates)."""
+    from . import mamba, model, spectral, tokenizer
+    tc = cfg["transformer_config"]
+    k = tc["k_top_eigenvectors"]
+    nbr, center, org, fidx, kidx = tokenizer.group(pts, cfg["num_group"], cfg["group_size"])
+    vals, vecs, allv, S = spectral.spectral_eig(center, tc["knn_graph"], tc["alpha"], tc["symmetric"], tc["self_loop"],
+                                                tc["binary"], k, tc["smallest"], "laplacian", "clamp1e-12")
+    perm = spectral.sast_perm(vecs) if perm_override is None else perm_override
+    tok = model.encoder(sd, "MAE_encoder.encoder.", nbr)
+    pos = model.pos_embed(sd, "MAE_encoder.pos_embed.", center)
+    x_vis = compact_visible(tok, perm, mask)
+    pos_vis = compact_visible(pos, perm, mask)
+    x_vis = mamba.mixer_model(sd, "MAE_encoder.blocks.", x_vis, pos_vis, tc["depth"])
+    x_vis = mamba.layer_norm(sd, "MAE_encoder.norm.", x_vis)
+    mfull = mask_full(mask, perm)
+    x_full = restore(x_vis, mfull, sd["mask_token"].reshape(-1))
+    pos_full = spectral.order_gather(pos, perm, True)
+    x_rec = mamba.mixer_model(sd, "MAE_decoder.blocks.", x_full, pos_full, tc["decoder_depth"])
+    x_rec = mamba.layer_norm(sd, "MAE_decoder.norm.", x_rec)
+    x_rec = gather_masked(x_rec, mfull)
+    B, M, C = x_rec.shape
+    import torch.nn.functional as F
+    reb = F.conv1d(x_rec.transpose(1, 2), sd["increase_dim.0.weight"], sd["increase_dim.0.bias"]).transpose(1, 2)
+    reb = reb.reshape(B * M, -1, 3)
+    Gs = nbr.shape[2]
+    nbr_full = spectral.order_gather(nbr.reshape(nbr.shape[0], nbr.shape[1], -1), perm, True)
+    gt = nbr_full[mfull].reshape(B * M, Gs, 3)
+    loss = chamfer_l2(reb, gt).mean()
+    return loss, dict(perm=perm, x_vis=x_vis, x_full=x_full, mask_full=mfull, eigvecs=vecs)

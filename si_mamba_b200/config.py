@@ -35,3 +35,15 @@ def finetune_scan_hardest() -> Config:
     c = finetune_modelnet()
     c.update(cls_dim=15, num_group=128, drop_path=0.1, alpha=10.0, rotation=True)
     return c
+
+
+def pretrain() -> Config:
+    """model section of cfgs/pretrain.yaml:35-65 (config C3: MAE on ShapeNet55)."""
+    return Config(
+        NAME="Point_MAE_Mamba", group_size=32, num_group=64, loss="cdl2", rms_norm=False, use_cls_token=False,
+        drop_path=0.1, drop_out=0.1,
+        transformer_config=Config(
+            mask_ratio=0.6, mask_type="rand", trans_dim=384, encoder_dims=384, depth=12, drop_path_rate=0.1,
+            num_heads=6, decoder_depth=4, decoder_num_heads=6,
+            method="smallest_eigenvectors_seperate_learnable_tokens", reverse=True, knn_graph=20,
+            k_top_eigenvectors=4, smallest=True, alpha=10, symmetric=True, self_loop=False, binary=True))

@@ -1,0 +1,121 @@
+"""GPU parity of the MAE pre-training path (C3) and the part-segmentation encoder path (C4) against the oracle."""
+
+import pytest
+import torch
+
+from oracle import mae as omae, seg as oseg, tokenizer
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def randomize_bn(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+            mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+
+
+def test_mae_index_maps(lib):
+    from si_mamba_b200 import layout
+    from oracle import spectral
+    g = torch.Generator().manual_seed(0)
+    perm = spectral.sast_perm(torch.randn(3, 64, 4, generator=g, dtype=torch.float64))
+    mask = omae.rand_mask(3, 64, 0.6, 1)
+    maps = layout.mae_index_maps(perm.cuda().int(), mask.cuda())
+    x = torch.randn(3, 64, 8, generator=g)
+    x_vis = torch.gather(x, 1, maps["src_vis"].cpu().long()[..., None].expand(-1, -1, 8))
+    assert torch.equal(x_vis, omae.compact_visible(x, perm, mask))
+    assert torch.equal(maps["mask_full"].cpu(), omae.mask_full(mask, perm))
+    assert maps["rec_src"].shape == (3, 2 * 4 * 38)
+
+
+@pytest.mark.parametrize("depth,dec", [(2, 1), (12, 4)])
+def test_point_mae_forward_vs_oracle(lib, depth, dec):
+    import si_mamba_b200 as sm
+    cfg = sm.pretrain()
+    cfg.transformer_config.update(depth=depth, decoder_depth=dec)
+    torch.manual_seed(0)
+    m = sm.Point_MAE_Mamba(cfg)
+    randomize_bn(m, 1)
+    m.eval()
+    torch.nn.init.normal_(m.mask_token, std=0.5)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    B = 3
+    pts = tokenizer.synthetic_clouds(B, 1024, 31, "surface")
+    mask = omae.rand_mask(B, 64, 0.6, 5)
+    m = m.cuda()
+    with torch.no_grad():
+        center = m.group_divider(pts.cuda())[1]
+        perm = m.spectral_order(center)["perm"].cpu().long()
+        loss = m(pts.cuda(), bool_masked_pos=mask.cuda())
+    cfg_d = dict(cfg)
+    cfg_d["transformer_config"] = dict(cfg.transformer_config)
+    ref, inter = omae.point_mae_forward(sd, cfg_d, pts, mask, perm_override=perm)
+    # the kernel's ordering is a valid ascending order of the oracle eigenvectors
+    srt = torch.gather(inter["eigvecs"].transpose(1, 2), 2, perm)
+    assert (srt[..., 1:] - srt[..., :-1]).min() > -1e-9
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 2e-3, (loss.item(), ref.item())
+
+
+def test_point_mae_train_step(lib):
+    """One fwd+bwd in train mode under bf16 autocast (runner_pretrain.py:243): finite loss, gradients everywhere
+    the spectral path reaches (decoder_pos_embed is only used by the non-spectral branch, like the reference)."""
+    import si_mamba_b200 as sm
+    cfg = sm.pretrain()
+    cfg.transformer_config.update(depth=2, decoder_depth=1)
+    torch.manual_seed(0)
+    m = sm.Point_MAE_Mamba(cfg).cuda().train()
+    pts = tokenizer.synthetic_clouds(4, 1024, 3, "ball").cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = m(pts)
+    loss.backward()
+    assert torch.isfinite(loss)
+    missing = [n for n, p in m.named_parameters() if p.grad is None and not n.startswith("decoder_pos_embed")]
+    assert not missing, missing
+    assert m.mask_token.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("method", ["HLT", "SAST"])
+def test_part_seg_forward_vs_oracle(lib, method):
+    import si_mamba_b200 as sm
+    cfg = sm.part_seg_config()
+    cfg.update(depth=4, fetch_idx=[1, 2, 3], method=method)
+    if method == "SAST":
+        cfg.update(knn_graph=20, self_loop=False, binary=True)
+    torch.manual_seed(0)
+    m = sm.get_model(50, cfg)
+    randomize_bn(m, 2)
+    m.eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    B, N = 2, 2048
+    pts = tokenizer.synthetic_clouds(B, N, 41, "surface").transpose(1, 2).contiguous()
+    lab = torch.zeros(B, 16)
+    lab[0, 3] = 1
+    lab[1, 7] = 1
+    noise = torch.rand(B, 128, generator=torch.Generator().manual_seed(9))
+    m = m.cuda()
+    with torch.no_grad():
+        out = m(pts.cuda(), lab.cuda(), hlt_noise=noise)
+    ref, inter = oseg.seg_forward(sd, dict(cfg), pts, lab, noise)
+    assert out.shape == (B, N, 50)
+    err = (out.cpu() - ref).abs().max() / ref.abs().max()
+    if err >= 2e-3 and method == "SAST":
+        # near-tied eigenvector entries: re-run the oracle under the kernel's (validated) permutation
+        from si_mamba_b200 import ops
+        with torch.no_grad():
+            center = m.group_divider(pts.transpose(1, 2).contiguous().cuda())[1]
+            perm = ops.spectral_eig(center, cfg.knn_graph, cfg.alpha, cfg.symmetric, cfg.self_loop, cfg.binary, 4,
+                                    True)["perm"].cpu().long()
+        ref, _ = oseg.seg_forward(sd, dict(cfg), pts, lab, noise, perm_override=perm)
+        err = (out.cpu() - ref).abs().max() / ref.abs().max()
+    assert err < 2e-3, err
