@@ -160,6 +160,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     # fp32 mirrors the reference's runtime defaults (no autocast in runner_finetune): fp32 matmuls, while
@@ -290,7 +291,12 @@ def run_ours(args):
             import torch.distributed as dist
             dist.destroy_process_group()
         return
-    cpu_val, cores = cpu_reference_rate(2)
+    # reported baseline, rank 0 at N=1 only (the scaling runs would only repeat it)
+    cpu_base = None
+    if world == 1:
+        cpu_val, cores = cpu_reference_rate(2)
+        cpu_base = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "2 clouds of the same workload, median of 3 runs (oracle/model.py)"}
     clouds = B * world * args.steps
     line = {
         "metric": METRIC, "value": clouds / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -311,8 +317,7 @@ def run_ours(args):
                      "alg_bytes_per_launch": alg_bytes, "us_per_launch": scan_s * 1e6,
                      "shape": {"B": B, "L": L, "D": Dm, "N": 16, "dtype": str(adt).split(".")[-1]},
                      "note": "fp32 scan on B200 is MUFU-bound (16 ex2/clk/SM) at ~0.72 of this roofline; see DESIGN.md"},
-        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "2 clouds of the same workload, median of 3 runs (oracle/model.py)"},
+        "cpu_baseline": cpu_base,
     }
     print(json.dumps(line))
     if world > 1:

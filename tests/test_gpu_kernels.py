@@ -230,7 +230,8 @@ def test_scan_conv_golden(ops, golden, case):
     assert torch.allclose(conv.cpu(), g["conv_out"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", [0, 102, 104, 108, 116, 202, 204, 208, 216, 402, 404, 408])
+@pytest.mark.parametrize("variant", [0, 102, 104, 108, 116, 202, 204, 208, 216, 402, 404, 408,
+                                     1002, 1004, 1008, 1016, 1104, 1108])
 @pytest.mark.parametrize("B,D,L", [(2, 768, 512), (1, 128, 1), (3, 64, 37), (1, 192, 1024)])
 def test_scan_vs_oracle_fp32(ops, variant, B, D, L):
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 10 * L + D)

@@ -166,6 +166,23 @@ int main() {
   run<6>("FFMA+EX2 1:1 (pairs)", 1, out);
   run<3>("scan mix scalar (updates)", 1, out);
   run<4>("scan mix packed (updates)", 2, out);
+  // occupancy sensitivity of the scan-like mix: k CTAs of 128 threads per SM = k warps per scheduler
+  for (int kk : {1, 2, 3, 4, 6, 8, 16}) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k<4><<<148 * kk, 128>>>(out, 0.001f);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k<4><<<148 * kk, 128>>>(out, 0.001f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double upd = (double)148 * kk * 128 * ITERS * UNR * 2;
+    printf("scan mix packed, %2d warps/scheduler: %7.3f ms  %5.2f updates/clk/SM\n", kk, ms,
+           upd / (ms * 1e-3) / 148.0 / 1.965e9);
+  }
   run_generic("LDS.128 all lanes same address", [&] { ks<0><<<148 * 8, 256>>>(out, 0); });
   run_generic("LDS.128 4 addresses interleaved (lane&3)", [&] { ks<1><<<148 * 8, 256>>>(out, 0); });
   run_generic("LDS.128 4 addresses, one per quarter-warp", [&] { ks<5><<<148 * 8, 256>>>(out, 0); });
