@@ -43,8 +43,10 @@ struct ScanTmaps {
 // shared memory for S*CPT state updates, i.e. 2/CPT + 2/S shared-memory wavefronts per warp-update.  ncu on the
 // first version (S=4, CPT=1: 2.5 + epilogue) showed the LSU shared pipe at 73% with MUFU at 46%, so B/C reuse
 // across channels (CPT > 1) is what moves the kernel towards its MUFU bound.
-template <typename T, int S_, int CPT_, int CH_, int TT_, int NS_>
+template <typename T, int S_, int CPT_, int CH_, int TT_, int NS_, int DBG_ = 0>
 struct ScanCfg {
+  static constexpr int DBG = DBG_;  // bench-only ablation switches (results are WRONG when non-zero): 1 no MUFU in the
+                                    // recurrence, 2 no activation math in the pre-pass, 4 no butterfly, 8 no B/C loads
   static constexpr int S = S_;                  // states per thread
   static constexpr int LPC = kNState / S_;      // lanes per channel group
   static constexpr int CPT = CPT_;              // adjacent channels per thread
@@ -199,11 +201,11 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
       const float4 bs = *reinterpret_cast<const float4*>(s_bias + cc);
       float4 dv = lds4<T>(sd + r * CH + cc);
       dv.x += bs.x, dv.y += bs.y, dv.z += bs.z, dv.w += bs.w;
-      if (p.softplus) dv = make_float4(softplus_f(dv.x), softplus_f(dv.y), softplus_f(dv.z), softplus_f(dv.w));
+      if (p.softplus && !(Cfg::DBG & 2)) dv = make_float4(softplus_f(dv.x), softplus_f(dv.y), softplus_f(dv.z), softplus_f(dv.w));
       *reinterpret_cast<float4*>(w_dt + r * CHP + cc) = dv;
       *reinterpret_cast<float4*>(w_u + r * CHP + cc) = lds4<T>(su + r * CH + cc);
       float4 gv = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (has_z) {
+      if (has_z && !(Cfg::DBG & 2)) {
         const float4 zv = lds4<T>(sz + r * CH + cc);
         gv = make_float4(silu_f(zv.x), silu_f(zv.y), silu_f(zv.z), silu_f(zv.w));
       }
@@ -220,65 +222,89 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     // raw stage s is free again: refill it with tile + NS
     if (tid == 0 && tile + NS < ntiles) issue_tile(tile + NS);
 
-    // ---- the recurrence over this tile, GRP steps at a time: all shared-memory operands of a group are
-    // fetched up front (independent LDS in flight), then the dependent FMUL2 / MUFU / FFMA2 chain runs.
-    constexpr int GRP = LPC >= 2 ? LPC : 2;
+    // ---- the recurrence over this tile, fully unrolled and software-pipelined by hand.
+    // Warps issue in order, so a consumer stalled on a MUFU result also blocks the warp's NEXT MUFUs; with only
+    // 2-3 warps per scheduler at B=32 the XU queue then drains (ncu: XU 62 % busy, per-step critical path ~370
+    // cycles).  Stage A of step t+PD (LDS dt/u, FMUL2, MUFU.EX2) is therefore issued ahead of stage B of step t
+    // (h update, <h,C> on two accumulators), and B/C operands are fetched one step ahead of their use.
+    if constexpr ((Cfg::DBG & 16) != 0) {  // ablation: data movement only
+      for (int e = tid; e < TT * CH; e += NT) obuf[e] = from_f32<T>(w_u[(e / CH) * CHP + e % CH] + w_dt[(e / CH) * CHP + e % CH] + w_g[(e / CH) * CHP + e % CH]);
+    } else {
+    constexpr int PD = 2;
+    float2 ar[PD + 1][CPT][S / 2];
+    float dtu_r[PD + 1][CPT];
+    auto stage_a = [&](int t) {
+      const int slot = t % (PD + 1);
+      float dtv[CPT], uv[CPT];
+      lds_vec<CPT>(w_dt + t * CHP + ch0, dtv);
+      lds_vec<CPT>(w_u + t * CHP + ch0, uv);
 #pragma unroll
-    for (int r0 = 0; r0 < TT; r0 += GRP) {
-      float dtv[GRP][CPT], uv[GRP][CPT], Bv[GRP][S], Cv[GRP][S];
+      for (int cp = 0; cp < CPT; ++cp) {
+        dtu_r[slot][cp] = dtv[cp] * uv[cp];
+        const float2 dt2 = make_float2(dtv[cp], dtv[cp]);
 #pragma unroll
-      for (int q = 0; q < GRP; ++q) {
-        const int r = r0 + q;
-        lds_vec<CPT>(w_dt + r * CHP + ch0, dtv[q]);
-        lds_vec<CPT>(w_u + r * CHP + ch0, uv[q]);
-        lds_vec<S>(w_B + r * kNState + sub * S, Bv[q]);
-        lds_vec<S>(w_C + r * kNState + sub * S, Cv[q]);
-      }
-      float part[GRP][CPT];
-#pragma unroll
-      for (int q = 0; q < GRP; ++q) {
-#pragma unroll
-        for (int cp = 0; cp < CPT; ++cp) {
-          const float dtu = dtv[q][cp] * uv[q][cp];
-          const float2 dt2 = make_float2(dtv[q][cp], dtv[q][cp]);
-          const float2 dtu2 = make_float2(dtu, dtu);
-          float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < S / 2; ++j) {
-            const float2 x = __fmul2_rn(dt2, A2[cp][j]);
-            const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-            const float2 bu = __fmul2_rn(dtu2, make_float2(Bv[q][2 * j], Bv[q][2 * j + 1]));
-            h[cp][j] = __ffma2_rn(a, h[cp][j], bu);
-            acc2 = __ffma2_rn(h[cp][j], make_float2(Cv[q][2 * j], Cv[q][2 * j + 1]), acc2);
-          }
-          part[q][cp] = acc2.x + acc2.y;
+        for (int j = 0; j < S / 2; ++j) {
+          const float2 x = __fmul2_rn(dt2, A2[cp][j]);
+          ar[slot][cp][j] = (Cfg::DBG & 1) ? make_float2(x.x + 1.f, x.y + 1.f) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
         }
       }
+    };
 #pragma unroll
-      for (int g2 = 0; g2 < GRP; g2 += LPC) {
-        // transposed butterfly: lane `sub` ends with the full sums of step r0 + g2 + sub
+    for (int t = 0; t < PD; ++t) stage_a(t);
+    float Bc[S], Cc[S], Bn[S], Cn[S];
+    lds_vec<S>(w_B + sub * S, Bc);
+    lds_vec<S>(w_C + sub * S, Cc);
+    float part[LPC][CPT];
 #pragma unroll
-        for (int o = LPC / 2; o >= 1; o >>= 1) {
+    for (int t = 0; t < TT; ++t) {
+      if (t + PD < TT) stage_a(t + PD);
+      if (t + 1 < TT && !(Cfg::DBG & 8)) {
+        lds_vec<S>(w_B + (t + 1) * kNState + sub * S, Bn);
+        lds_vec<S>(w_C + (t + 1) * kNState + sub * S, Cn);
+      }
+      const int slot = t % (PD + 1);
+#pragma unroll
+      for (int cp = 0; cp < CPT; ++cp) {
+        const float2 dtu2 = make_float2(dtu_r[slot][cp], dtu_r[slot][cp]);
+        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int j = 0; j < S / 2; ++j) {
+          const float2 bu = __fmul2_rn(dtu2, make_float2(Bc[2 * j], Bc[2 * j + 1]));
+          h[cp][j] = __ffma2_rn(ar[slot][cp][j], h[cp][j], bu);
+          acc[j & 1] = __ffma2_rn(h[cp][j], make_float2(Cc[2 * j], Cc[2 * j + 1]), acc[j & 1]);
+        }
+        part[t % LPC][cp] = (acc[0].x + acc[1].x) + (acc[0].y + acc[1].y);
+      }
+      if ((t + 1) % LPC == 0) {
+        // transposed butterfly: lane `sub` ends with the full sums of step t + 1 - LPC + sub, and writes it
+#pragma unroll
+        for (int o = (Cfg::DBG & 4) ? 0 : LPC / 2; o >= 1; o >>= 1) {
           const bool up = (sub & o) != 0;
 #pragma unroll
           for (int i = 0; i < o; ++i) {
 #pragma unroll
             for (int cp = 0; cp < CPT; ++cp) {
-              const float send = up ? part[g2 + i][cp] : part[g2 + i + o][cp];
-              const float keep = up ? part[g2 + i + o][cp] : part[g2 + i][cp];
-              part[g2 + i][cp] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              const float send = up ? part[i][cp] : part[i + o][cp];
+              const float keep = up ? part[i + o][cp] : part[i][cp];
+              part[i][cp] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
         }
-        const int r = r0 + g2 + sub;
-        float uu[CPT], gg[CPT];
-        lds_vec<CPT>(w_u + r * CHP + ch0, uu);
-        lds_vec<CPT>(w_g + r * CHP + ch0, gg);
+        const int r = t + 1 - LPC + sub;
+        float uw[CPT], gw[CPT];
+        lds_vec<CPT>(w_u + r * CHP + ch0, uw);
+        lds_vec<CPT>(w_g + r * CHP + ch0, gw);
 #pragma unroll
         for (int cp = 0; cp < CPT; ++cp)
-          obuf[r * CH + ch0 + cp] = from_f32<T>((part[g2][cp] + Dc[cp] * uu[cp]) * gg[cp]);
+          obuf[r * CH + ch0 + cp] = from_f32<T>((part[0][cp] + Dc[cp] * uw[cp]) * gw[cp]);
+      }
+      if (t + 1 < TT && !(Cfg::DBG & 8)) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) Bc[i] = Bn[i], Cc[i] = Cn[i];
       }
     }
+    }  // DBG & 16
+
 
     fence_proxy_async();
     __syncthreads();
@@ -507,9 +533,9 @@ static int launch_scan_wa(const ScanParams& p, int dtype, cudaStream_t stream) {
   return check_launch("selective_scan_fwd_wa");
 }
 
-template <typename T, int S, int CPT, int CH, int TT, int NS>
+template <typename T, int S, int CPT, int CH, int TT, int NS, int DBG = 0>
 static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = ScanCfg<T, S, CPT, CH, TT, NS>;
+  using Cfg = ScanCfg<T, S, CPT, CH, TT, NS, DBG>;
   auto kern = selective_scan_fwd_kernel<Cfg, T>;
   static bool attr_done = false;  // idempotent; a benign race only repeats the call
   if (!attr_done) {
@@ -556,6 +582,14 @@ static int dispatch_scan(const ScanParams& p, int dtype, int variant, cudaStream
       case 402: return launch_scan<T, 2, 4, 64, 16, 3>(p, dtype, stream);
       case 404: return launch_scan<T, 4, 4, 64, 16, 3>(p, dtype, stream);
       case 408: return launch_scan<T, 8, 4, 64, 16, 3>(p, dtype, stream);
+      // bench-only ablations of variant 108 (WRONG results; see ScanCfg::DBG)
+      case 9001: return launch_scan<T, 8, 1, 64, 16, 3, 1>(p, dtype, stream);
+      case 9002: return launch_scan<T, 8, 1, 64, 16, 3, 2>(p, dtype, stream);
+      case 9004: return launch_scan<T, 8, 1, 64, 16, 3, 4>(p, dtype, stream);
+      case 9008: return launch_scan<T, 8, 1, 64, 16, 3, 8>(p, dtype, stream);
+      case 9015: return launch_scan<T, 8, 1, 64, 16, 3, 15>(p, dtype, stream);
+      case 9016: return launch_scan<T, 8, 1, 64, 16, 3, 16>(p, dtype, stream);
+      case 9018: return launch_scan<T, 8, 1, 64, 16, 3, 18>(p, dtype, stream);
       // warp-autonomous kernels: 1000 + states per thread (+ 100 for 32-channel CTAs)
       case 1002: return launch_scan_wa<T, 2, 32, 4>(p, dtype, stream);
       case 1004: return launch_scan_wa<T, 4, 64, 4>(p, dtype, stream);

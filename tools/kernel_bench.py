@@ -75,14 +75,15 @@ def scan_case(B, L, D, dtype, variant, nsets):
 
 def main():
     quick = "--quick" in sys.argv
+    only_f32 = "--f32" in sys.argv
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     want = lambda name: only is None or only == name
     torch.cuda.set_device(0)
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), hbm_peak_gbs=HBM)), flush=True)
     shapes = [(32, 512, 768), (256, 512, 768)] if not quick else [(32, 512, 768)]
     for (B, L, D) in (shapes if want("scan") else []):
-        for dtype in (torch.float32, torch.bfloat16):
-            variants = (108, 1008, 2004, 2008, 2016, 3008) if "--variants" in sys.argv else (0,)
+        for dtype in ((torch.float32,) if only_f32 else (torch.float32, torch.bfloat16)):
+            variants = (104, 108, 204, 1008, 2008, 9001, 9002, 9004, 9008, 9015, 9016, 9018) if "--variants" in sys.argv else (0,)
             for variant in variants:
                 nsets = max(2, int(300e6 // (4 * B * L * D * (4 if dtype == torch.float32 else 2))) + 1)
                 fns, alg = scan_case(B, L, D, dtype, variant, min(nsets, 4))

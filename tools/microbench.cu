@@ -135,6 +135,40 @@ __global__ void __launch_bounds__(256) kshfl(float* out, float seed) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// MUFU.EX2 next to shared-memory loads / shuffles: do the XU and LSU pipes overlap, or serialise in the MIO queue?
+// per inner step: 2 MUFU.EX2 + NL broadcast LDS.128 + NS SHFL
+template <int NL, int NSH>
+__global__ void __launch_bounds__(256) kmix(float* out, float seed, int zero) {
+  __shared__ __align__(16) float sm[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) sm[i] = i * 1e-3f;
+  __syncthreads();
+  float a[UNR], b[UNR];
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) a[i] = seed + i, b[i] = seed - i;
+  float acc = 0.f;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sm) + ((threadIdx.x & 3) * 16 + zero);
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      a[i] = ex2(a[i]);
+      b[i] = ex2(b[i]);
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        float x, y, z, w;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
+                     : "r"(base + ((i * NL + l) * 64 + (it & 3) * 1024) % 8192));
+        acc += x + w;
+      }
+#pragma unroll
+      for (int l = 0; l < NSH; ++l) acc += __shfl_xor_sync(0xffffffffu, acc, 1 + l);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) acc += a[i] + b[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <typename F>
 void run_generic(const char* name, F launch) {
   cudaEvent_t e0, e1;
@@ -182,6 +216,29 @@ int main() {
     const double upd = (double)148 * kk * 128 * ITERS * UNR * 2;
     printf("scan mix packed, %2d warps/scheduler: %7.3f ms  %5.2f updates/clk/SM\n", kk, ms,
            upd / (ms * 1e-3) / 148.0 / 1.965e9);
+  }
+  {
+    auto mix = [&](const char* name, auto launch) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      launch();
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0);
+      launch();
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double mufu = (double)148 * 8 * 256 * ITERS * UNR * 2;
+      printf("%-40s %7.3f ms  %5.2f MUFU/clk/SM\n", name, ms, mufu / (ms * 1e-3) / 148.0 / 1.965e9);
+    };
+    mix("2 MUFU + 0 LDS.128 + 0 SHFL", [&] { kmix<0, 0><<<148 * 8, 256>>>(out, 0.5f, 0); });
+    mix("2 MUFU + 1 LDS.128 (broadcast)", [&] { kmix<1, 0><<<148 * 8, 256>>>(out, 0.5f, 0); });
+    mix("2 MUFU + 2 LDS.128 (broadcast)", [&] { kmix<2, 0><<<148 * 8, 256>>>(out, 0.5f, 0); });
+    mix("2 MUFU + 4 LDS.128 (broadcast)", [&] { kmix<4, 0><<<148 * 8, 256>>>(out, 0.5f, 0); });
+    mix("2 MUFU + 1 SHFL", [&] { kmix<0, 1><<<148 * 8, 256>>>(out, 0.5f, 0); });
+    mix("2 MUFU + 1 LDS.128 + 1 SHFL", [&] { kmix<1, 1><<<148 * 8, 256>>>(out, 0.5f, 0); });
   }
   run_generic("LDS.128 all lanes same address", [&] { ks<0><<<148 * 8, 256>>>(out, 0); });
   run_generic("LDS.128 4 addresses interleaved (lane&3)", [&] { ks<1><<<148 * 8, 256>>>(out, 0); });
