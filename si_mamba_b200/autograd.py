@@ -1,8 +1,6 @@
-"""Autograd wiring of the mixer's CUDA kernels (forward + backward through the C ABI).
-
-``mamba_inner_tm`` is the token-major equivalent of mamba-ssm's ``mamba_inner_fn``:
-in_proj -> causal conv1d + SiLU -> x_proj -> dt_proj -> selective scan -> out_proj, with the
-GEMMs on cuBLAS (tensor cores) and conv / scan on the hand-written kernels.
+"""Wiring of the mixer body: ``mamba_inner_tm`` is the token-major equivalent of mamba-ssm's ``mamba_inner_fn``
+(in_proj -> causal conv1d + SiLU -> x_proj -> dt_proj -> selective scan -> out_proj) with the GEMMs on cuBLAS
+(tensor cores) and conv / scan on the hand-written kernels, through autograd nodes when a graph is needed.
 """
 
 from __future__ import annotations
@@ -20,6 +18,46 @@ def _amp_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
+class _ParamCache:
+    """Inference-only cache of derived parameter tensors (low-precision copies of the projection weights,
+    A = -exp(A_log)).  ncu showed 111 cast / elementwise launches per bf16 forward, most of them re-casting the
+    same weights; entries are keyed on the parameter's storage and version counter, so an optimizer step or a
+    load_state_dict invalidates them.  Never used while autograd is recording."""
+
+    def __init__(self):
+        from torch.utils.weak import WeakIdKeyDictionary  # identity-keyed: tensors do not compare with ==
+        self._d = WeakIdKeyDictionary()  # parameter object -> {tag: (version, data_ptr, value)}
+
+    def get(self, p: torch.Tensor, tag, fn):
+        per = self._d.get(p)
+        if per is None:
+            per = self._d[p] = {}
+        hit = per.get(tag)
+        if hit is not None and hit[0] == p._version and hit[1] == p.data_ptr():
+            return hit[2]
+        val = fn(p.detach())
+        per[tag] = (p._version, p.data_ptr(), val)
+        return val
+
+
+    def get_multi(self, anchor: torch.Tensor, tag, deps, fn):
+        """Like get(), for a value derived from several tensors (e.g. conv + BatchNorm folding): valid while the
+        versions and addresses of all ``deps`` are unchanged."""
+        per = self._d.get(anchor)
+        if per is None:
+            per = self._d[anchor] = {}
+        sig = tuple((t._version, t.data_ptr()) for t in deps)
+        hit = per.get(tag)
+        if hit is not None and hit[0] == sig:
+            return hit[2]
+        val = fn()
+        per[tag] = (sig, None, val)
+        return val
+
+
+_CACHE = _ParamCache()
+
+
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
                    dt_rank: int, d_state: int) -> torch.Tensor:
     """Token-major Mamba mixer body.  hidden (B, L, d_model) -> (B, L, d_model)."""
@@ -28,19 +66,25 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     need_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in (hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D,
                                   out_proj_w))
-    xz = F.linear(hidden.to(act), in_proj_w.to(act))  # (B, L, 2*d_inner)
+    if need_grad:
+        w_in, w_x, w_dt, w_out = (w.to(act) for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w))
+        A = -torch.exp(A_log.float())
+    else:
+        cast = (lambda w: w) if act == in_proj_w.dtype else (lambda w: _CACHE.get(w, act, lambda t: t.to(act)))
+        w_in, w_x, w_dt, w_out = (cast(w) for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w))
+        A = _CACHE.get(A_log, "A", lambda t: -torch.exp(t.float()))
+    xz = F.linear(hidden.to(act), w_in)  # (B, L, 2*d_inner)
     x, z = xz[..., :d_inner], xz[..., d_inner:]
-    A = -torch.exp(A_log.float())
     if need_grad:
         u = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
     else:
         u = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
-    x_dbl = F.linear(u, x_proj_w.to(act))  # (B, L, dt_rank + 2*d_state)
-    dt = F.linear(x_dbl[..., :dt_rank], dt_proj_w.to(act))  # bias is applied inside the scan
+    x_dbl = F.linear(u, w_x)  # (B, L, dt_rank + 2*d_state)
+    dt = F.linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]
     Cm = x_dbl[..., dt_rank + d_state:]
     if need_grad:
         y = ops.SelectiveScanTM.apply(u, dt, A, Bm, Cm, D, z, dt_proj_b, True)
     else:
         y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True)
-    return F.linear(y, out_proj_w.to(act))
+    return F.linear(y, w_out)

@@ -30,6 +30,23 @@ int check_launch(const char* what);    // cudaPeekAtLastError -> SIM_ERR_CUDA
     }                                           \
   } while (0)
 
+// Per-device, grow-only cache of cudaFuncAttributeMaxDynamicSharedMemorySize.  Function attributes are per device and
+// nn.DataParallel drives several devices from one process, so a process-wide flag is not enough.  The
+// first (warm-up) call on a device sets the attribute, outside any stream capture; later calls are free.
+struct SmemAttrCache {
+  size_t set[64] = {};
+};
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kern, size_t bytes, SmemAttrCache& c) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& cur = c.set[dev & 63];
+  if (bytes <= cur) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ----------------------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA unit)

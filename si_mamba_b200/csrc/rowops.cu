@@ -334,8 +334,8 @@ int argsort_rows(const float* keys, long ld, long es, int rows, int n, int* perm
   SIM_REQUIRE(rows > 0 && n > 0 && n <= 4096, SIM_ERR_INVALID, "argsort_rows: n must be in [1, 4096] (got %d)", n);
   SIM_REQUIRE(keys && perm, SIM_ERR_INVALID, "argsort_rows: null tensor");
   const size_t smem = (size_t)8 * n * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(argsort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrCache attr;
+  if (smem > 48 * 1024) ensure_dyn_smem(argsort_rows_kernel, smem, attr);
   argsort_rows_kernel<<<(rows + 7) / 8, 256, smem, stream>>>(keys, ld, es, rows, n, perm, inv_perm);
   return check_launch("argsort_rows");
 }

@@ -297,12 +297,8 @@ template <typename T, int CH>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
   using Cfg = BwdCfg<T, CH>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
-      return check_launch("selective_scan_bwd attr");
-    attr_done = true;
-  }
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
   BwdTmaps tm;
   int rc;
   if ((rc = make_tmap_tokens(&tm.u, p.u, dtype, p.D, p.L, p.batch, p.ld_u, CH, TT))) return rc;

@@ -511,12 +511,8 @@ static int launch_scan_wa(const ScanParams& p, int dtype, cudaStream_t stream) {
   using Cfg = ScanWaCfg<T, S, CH, NS>;
   constexpr int TT = Cfg::TT;
   auto kern = selective_scan_fwd_wa_kernel<Cfg, T>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
-      return check_launch("selective_scan_fwd_wa attr");
-    attr_done = true;
-  }
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_fwd_wa attr");
   ScanTmaps tm;
   int rc;
   if ((rc = make_tmap_tokens(&tm.u, p.u, dtype, p.D, p.L, p.batch, p.ld_u, CH, TT))) return rc;
@@ -537,12 +533,8 @@ template <typename T, int S, int CPT, int CH, int TT, int NS, int DBG = 0>
 static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
   using Cfg = ScanCfg<T, S, CPT, CH, TT, NS, DBG>;
   auto kern = selective_scan_fwd_kernel<Cfg, T>;
-  static bool attr_done = false;  // idempotent; a benign race only repeats the call
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
-      return check_launch("selective_scan_fwd attr");
-    attr_done = true;
-  }
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_fwd attr");
   ScanTmaps tm;
   int rc;
   if ((rc = make_tmap_tokens(&tm.u, p.u, dtype, p.D, p.L, p.batch, p.ld_u, CH, TT))) return rc;

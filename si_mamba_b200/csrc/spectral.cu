@@ -530,12 +530,9 @@ int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cuda
 #define SIM_SPEC_LAUNCH(NT_, INS)                                                                   \
   do {                                                                                              \
     auto kern = spectral_kernel<NT_, INS>;                                                          \
-    static size_t attr_smem = 0; /* grow-only, set outside stream capture by the first (warm-up) call */ \
-    if (smem > 48 * 1024 && smem > attr_smem) {                                                     \
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-        return check_launch("spectral_eig attr");                                                   \
-      attr_smem = smem;                                                                             \
-    }                                                                                               \
+    static SmemAttrCache attr; /* per device, grow-only, set by the first (warm-up) call */             \
+    if (smem > 48 * 1024 && ensure_dyn_smem(kern, smem, attr) != cudaSuccess)                        \
+      return check_launch("spectral_eig attr");                                                     \
     kern<<<P.B, NT_, smem, stream>>>(P);                                                            \
   } while (0)
   if (NT == 256) {

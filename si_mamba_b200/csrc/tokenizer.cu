@@ -96,11 +96,8 @@ int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStre
 #define SIM_FPS_LAUNCH(NT, PPT)                                                                         \
   do {                                                                                                  \
     auto kern = fps_kernel<NT, PPT>;                                                                    \
-    static size_t attr_smem = 0; /* grow-only: set once, outside any stream capture, by the warm-up call */ \
-    if (smem + 2048 > 48 * 1024 && smem > attr_smem) {                                                  \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-      attr_smem = smem;                                                                                 \
-    }                                                                                                   \
+    static SmemAttrCache attr; /* per device, grow-only, set by the first (warm-up) call */               \
+    if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                     \
     kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center);                                              \
   } while (0)
   if (N <= 512)
@@ -192,11 +189,8 @@ int knn_group(const float* xyz, const float* center, int B, int N, int G, int M,
   const size_t smem = ((size_t)N * 3 + (size_t)WARPS * N + (size_t)WARPS * M) * 4;
   SIM_REQUIRE(smem <= 227 * 1024, SIM_ERR_INVALID, "knn_group: N=%d does not fit the shared-memory staging", N);
   auto kern = knn_group_kernel<WARPS>;
-  static size_t attr_smem = 0;  // grow-only: set once, outside any stream capture, by the warm-up call
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
-  }
+  static SmemAttrCache attr;  // per device, grow-only, set by the first (warm-up) call
+  if (smem > 48 * 1024) ensure_dyn_smem(kern, smem, attr);
   const int grid = B * ((G + WARPS - 1) / WARPS);
   kern<<<grid, WARPS * 32, smem, stream>>>(xyz, center, N, G, M, idx, nbr, nbr_org);
   return check_launch("knn_group");

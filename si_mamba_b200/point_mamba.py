@@ -50,8 +50,13 @@ class Encoder(nn.Module):
     @staticmethod
     def _fold_bn(conv: nn.Conv1d, bn: nn.BatchNorm1d):
         """Eval-mode BatchNorm folded into the preceding 1x1 conv: y = (W x + b - mean) * gamma / sqrt(var + eps) + beta."""
-        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-        return conv.weight[:, :, 0] * scale[:, None], (conv.bias - bn.running_mean) * scale + bn.bias
+        def fold():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            return (conv.weight[:, :, 0] * scale[:, None]).detach(), ((conv.bias - bn.running_mean) * scale + bn.bias).detach()
+
+        from .autograd import _CACHE  # inference-only cache, invalidated by the tensors' version counters
+        deps = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        return _CACHE.get_multi(conv.weight, "bn_fold", deps, fold)
 
     def _forward_eval(self, point_groups):
         """Inference form of forward(): the same arithmetic written as row-major GEMMs on the (B*G*M, C) point
