@@ -140,6 +140,14 @@ int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float*
                           void* dx, long ld_dx, float* dw, float* dbias, int batch, int L, int D, int width,
                           int silu, int dtype, sim_stream_t stream);
 
+/* a-10  fp32-accurate projection GEMM on the tensor cores: Y[M,N] = X[M,K] . W[N,K]^T with fp32 in / out / accumulate,
+ * operands split on the fly into 3 bf16 terms (tcgen05 "9xBF16" emulation).  Replaces the fp32 F.linear calls of
+ * Mamba.forward (in_proj / x_proj / dt_proj / out_proj, models/block.py:72) on the no-autocast finetune / test path.
+ * Row strides lda / ldb / ldd in elements; all of K, N, lda, ldb, ldd must be multiples of 4. */
+size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K);
+int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
+                    void* workspace, size_t workspace_bytes, sim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ SIGNATURES = {
     "sim_selective_scan_bwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p,
                                     _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _p,
                                     _i, _i, _i, _i, _i, _i, _p]),
+    "sim_gemm_f32_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sim_gemm_f32_tc": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _sz, _p]),
     "sim_causal_conv1d_bwd": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }
 

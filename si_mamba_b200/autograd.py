@@ -56,6 +56,7 @@ class _ParamCache:
 
 
 _CACHE = _ParamCache()
+_USE_TC_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "tc") != "cublas"
 
 
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
@@ -73,18 +74,23 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         cast = (lambda w: w) if act == in_proj_w.dtype else (lambda w: _CACHE.get(w, act, lambda t: t.to(act)))
         w_in, w_x, w_dt, w_out = (cast(w) for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w))
         A = _CACHE.get(A_log, "A", lambda t: -torch.exp(t.float()))
-    xz = F.linear(hidden.to(act), w_in)  # (B, L, 2*d_inner)
+    # fp32 inference: the four projections run on the tensor cores with fp32-accurate 3 x bf16 operand splitting
+    # (sim_gemm_f32_tc, 1.7x cuBLAS SGEMM and 3x closer to the fp64 result); SIM_FP32_GEMM=cublas restores F.linear
+    linear = F.linear
+    if not need_grad and act == torch.float32 and hidden.is_cuda and _USE_TC_GEMM:
+        linear = ops.linear_f32_tc
+    xz = linear(hidden.to(act), w_in)  # (B, L, 2*d_inner)
     x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:
         u = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
     else:
         u = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
-    x_dbl = F.linear(u, w_x)  # (B, L, dt_rank + 2*d_state)
-    dt = F.linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
+    x_dbl = linear(u, w_x)  # (B, L, dt_rank + 2*d_state)
+    dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]
     Cm = x_dbl[..., dt_rank + d_state:]
     if need_grad:
         y = ops.SelectiveScanTM.apply(u, dt, A, Bm, Cm, D, z, dt_proj_b, True)
     else:
         y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True)
-    return F.linear(y, w_out)
+    return linear(y, w_out)

@@ -153,4 +153,12 @@ int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float*
                                 static_cast<cudaStream_t>(stream));
 }
 
+size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K) { return sim::gemm_f32_tc_workspace_bytes(M, N, K); }
+
+int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
+                    void* workspace, size_t workspace_bytes, sim_stream_t stream) {
+  return sim::gemm_f32_tc(X, lda, W, ldb, Y, ldd, M, N, K, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -83,4 +83,8 @@ struct SpectralParams {
 size_t spectral_workspace_bytes(int, int, int);
 int spectral_eig(SpectralParams, void*, size_t, cudaStream_t);
 
+size_t gemm_f32_tc_workspace_bytes(int M, int N, int K);
+int gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
+                void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace sim

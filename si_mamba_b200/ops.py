@@ -226,6 +226,33 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
     return y, res_out
 
 
+# ----------------------------------------------------------------------------- fp32 GEMM on tensor cores (a-10)
+def linear_f32_tc(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ weight.T for fp32 tensors, fp32-accurate, on the tcgen05 tensor cores (forward only).
+    x (..., K) with unit inner stride and a uniform row stride (column slices of wider buffers are fine),
+    weight (N, K) = nn.Linear.weight."""
+    _cuda(x, weight)
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else _as_rows(x)
+    M = x2.shape[0]
+    w = weight if weight.stride(1) == 1 else weight.contiguous()
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+    ws_bytes = _lib.load().sim_gemm_f32_tc_workspace_bytes(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 256 else None
+    _lib.call("sim_gemm_f32_tc", _p(x2), x2.stride(0), _p(w), w.stride(0), _p(out), N, M, N, K, _p(ws),
+              ws_bytes if ws is not None else 0, _stream())
+    return out
+
+
+def _as_rows(x: torch.Tensor) -> torch.Tensor:
+    """(B, L, K) view with unit inner stride and batch stride == L * row stride -> (B*L, K) strided 2-D view."""
+    assert x.dim() == 3 and x.stride(2) == 1 and (x.shape[0] == 1 or x.stride(0) == x.shape[1] * x.stride(1))
+    return x.as_strided((x.shape[0] * x.shape[1], x.shape[2]), (x.stride(1), 1))
+
+
 # ----------------------------------------------------------------------------- causal conv1d (a-12)
 def causal_conv1d_tm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool = True,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -350,3 +350,19 @@ def test_conv_backward_vs_oracle(ops, dtype, tol, B, D, L):
     ops.CausalConv1dTM.apply(xc, wc, bc, True).backward(dev(dy))
     assert rel_err(xc.grad.cpu().float(), xr.grad) < tol
     assert rel_err(wc.grad.cpu(), wr.grad) < tol and rel_err(bc.grad.cpu(), br.grad) < tol
+
+
+# ----------------------------------------------------------------------------- a-10 fp32 GEMM on tensor cores
+@pytest.mark.parametrize("M,N,K,lda", [(16384, 1536, 384, 384), (16384, 56, 768, 768), (16384, 768, 24, 56),
+                                       (16384, 384, 768, 768), (100, 64, 36, 36), (7, 384, 128, 128)])
+def test_gemm_f32_tc(ops, M, N, K, lda):
+    """tcgen05 3 x bf16 emulated fp32 GEMM vs an fp64 reference: at least as accurate as a true fp32 GEMM."""
+    g = torch.Generator().manual_seed(M + N)
+    xb = torch.randn(M, lda, generator=g)
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    ref = xb[:, :K].double() @ w.double().t()
+    y = ops.linear_f32_tc(dev(xb)[:, :K], dev(w))
+    assert y.shape == (M, N)
+    assert rel_err(y.cpu().double(), ref) < 2e-6
+    x3 = dev(xb)[:, :K].reshape(1, M, K) if lda == K else dev(xb).view(1, M, lda)[..., :K]
+    assert torch.equal(ops.linear_f32_tc(x3, dev(w)).view(M, N), y)
