@@ -28,16 +28,9 @@
 // Roofline: HBM.  Algorithmic bytes per launch = (3 reads + 1 write) * B*L*D*s
 // + 2 * B*L*16*s (s = bytes per element); see DESIGN.md.
 
-#include "kernels.cuh"
-#include "tma.cuh"
+#include "scan_common.cuh"
 
 namespace sim {
-
-constexpr int kNState = 16;
-
-struct ScanTmaps {
-  CUtensorMap u, delta, z, B, C, out;
-};
 
 // S states x CPT channels per thread: every step a thread needs 2*S words of B/C and 2*CPT words of dt/u from
 // shared memory for S*CPT state updates, i.e. 2/CPT + 2/S shared-memory wavefronts per warp-update.  ncu on the
@@ -66,38 +59,6 @@ struct ScanCfg {
                 "TMA tiles must stay 128-B aligned");
   static_assert(NT % 32 == 0 && (CH_ & (CH_ - 1)) == 0, "whole warps, power-of-two channel tile");
 };
-
-// four consecutive elements of T from shared memory as fp32
-template <typename T>
-__device__ __forceinline__ float4 lds4(const T* p);
-template <>
-__device__ __forceinline__ float4 lds4<float>(const float* p) {
-  return *reinterpret_cast<const float4*>(p);
-}
-template <>
-__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const __nv_bfloat16* p) {
-  const uint2 r = *reinterpret_cast<const uint2*>(p);
-  // bf16 -> fp32 is a 16-bit shift
-  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
-                     __uint_as_float(r.y & 0xffff0000u));
-}
-
-template <int N>
-__device__ __forceinline__ void lds_vec(const float* p, float (&v)[N]) {
-  if constexpr (N == 1) {
-    v[0] = p[0];
-  } else if constexpr (N == 2) {
-    const float2 t = *reinterpret_cast<const float2*>(p);
-    v[0] = t.x, v[1] = t.y;
-  } else {
-    static_assert(N % 4 == 0, "vector width");
-#pragma unroll
-    for (int i = 0; i < N / 4; ++i) {
-      const float4 t = reinterpret_cast<const float4*>(p)[i];
-      v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
-    }
-  }
-}
 
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __grid_constant__ ScanTmaps tm,
@@ -341,42 +302,6 @@ struct ScanWaCfg {
   static_assert(NT % 32 == 0, "whole warps");
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// S consecutive elements of T (a broadcast row slice of B or C) from shared memory as fp32
-template <typename T, int N>
-__device__ __forceinline__ void lds_row(const T* p, float (&v)[N]) {
-  if constexpr (sizeof(T) == 4) {
-    lds_vec<N>(reinterpret_cast<const float*>(p), v);
-  } else {
-    static_assert(N % 2 == 0, "pairs");
-    if constexpr (N % 8 == 0) {
-#pragma unroll
-      for (int i = 0; i < N / 8; ++i) {
-        const uint4 r = reinterpret_cast<const uint4*>(p)[i];
-        const unsigned w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
-          v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-        }
-      }
-    } else if constexpr (N % 4 == 0) {
-#pragma unroll
-      for (int i = 0; i < N / 4; ++i) {
-        const uint2 r = reinterpret_cast<const uint2*>(p)[i];
-        v[4 * i] = __uint_as_float(r.x << 16), v[4 * i + 1] = __uint_as_float(r.x & 0xffff0000u);
-        v[4 * i + 2] = __uint_as_float(r.y << 16), v[4 * i + 3] = __uint_as_float(r.y & 0xffff0000u);
-      }
-    } else {
-      const unsigned r = *reinterpret_cast<const unsigned*>(p);
-      v[0] = __uint_as_float(r << 16), v[1] = __uint_as_float(r & 0xffff0000u);
-    }
-  }
-}
-
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_wa_kernel(const __grid_constant__ ScanTmaps tm,
                                                                         const ScanParams p) {
@@ -555,11 +480,12 @@ static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
 template <typename T>
 static int dispatch_scan(const ScanParams& p, int dtype, int variant, cudaStream_t stream) {
   // variant = 100 * (channels per thread) + (states per thread); 0 = heuristic on the independent work available.
-  const long rows = (long)p.batch * p.D;
-  // Measured on B200 (profiles/r01_kernel_bench_scan_variants.jsonl): S=8 is the best split at every batch size;
-  // once the batch provides more CTAs than fit, the warp-autonomous kernel with a 2-deep ring (29 KB/CTA, 7 CTAs/SM)
-  // wins for fp32 (0.47 vs 0.40 of the HBM roofline at B=256), the tile-synchronous one otherwise.
-  if (variant == 0) variant = (sizeof(T) == 4 && rows >= 148L * 3 * 64) ? 2008 : 108;
+  // Measured on B200 (profiles/r01_kernel_bench_scan_variants.jsonl, r01_kernel_bench_scan_ws.jsonl): the
+  // warp-specialised kernel (selective_scan_fwd_ws.cu, S = 8, 64-channel CTAs) is the fastest at every batch size
+  // and both dtypes (84 vs 93 us at B=32, 532 vs 536-609 us at B=256); the tile-synchronous kernel below remains
+  // for channel counts that are not a multiple of 64.
+  if (variant == 0) variant = (p.D % 64 == 0) ? 5008 : 108;
+  if (variant >= 5000 && variant < 9000) return selective_scan_fwd_ws(p, dtype, variant, stream);
   if (variant < 100) variant += 100;
   if (p.D % 64 == 0) {
     switch (variant) {

@@ -84,6 +84,8 @@ def main():
     for (B, L, D) in (shapes if want("scan") else []):
         for dtype in ((torch.float32,) if only_f32 else (torch.float32, torch.bfloat16)):
             variants = (104, 108, 204, 1008, 2008, 9001, 9002, 9004, 9008, 9015, 9016, 9018) if "--variants" in sys.argv else (0,)
+            if "--vlist" in sys.argv:
+                variants = tuple(int(v) for v in sys.argv[sys.argv.index("--vlist") + 1].split(","))
             for variant in variants:
                 nsets = max(2, int(300e6 // (4 * B * L * D * (4 if dtype == torch.float32 else 2))) + 1)
                 fns, alg = scan_case(B, L, D, dtype, variant, min(nsets, 4))
