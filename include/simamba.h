@@ -148,6 +148,15 @@ size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K);
 int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
                     void* workspace, size_t workspace_bytes, sim_stream_t stream);
 
+/* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
+ * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
+ * elements, row stride ldo); the weights are split once per model, activations by their producer.
+ * sim_gemm_bf16x3: Y[M,N] = sum of the six leading plane products X_i . W_j^T, fp32 accumulation in tensor memory.
+ * ldx / ldw / plane strides multiples of 8 elements, ldd and N multiples of 4. */
+int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
+int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
+                    int M, int N, int K, sim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

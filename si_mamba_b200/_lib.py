@@ -46,6 +46,8 @@ SIGNATURES = {
                                     _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _p,
                                     _i, _i, _i, _i, _i, _i, _p]),
     "sim_gemm_f32_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
+    "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),
     "sim_gemm_f32_tc": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _sz, _p]),
     "sim_causal_conv1d_bwd": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }

@@ -56,7 +56,7 @@ class _ParamCache:
 
 
 _CACHE = _ParamCache()
-_USE_TC_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "tc") != "cublas"
+_FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
@@ -74,11 +74,16 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         cast = (lambda w: w) if act == in_proj_w.dtype else (lambda w: _CACHE.get(w, act, lambda t: t.to(act)))
         w_in, w_x, w_dt, w_out = (cast(w) for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w))
         A = _CACHE.get(A_log, "A", lambda t: -torch.exp(t.float()))
-    # fp32 inference: the four projections run on the tensor cores with fp32-accurate 3 x bf16 operand splitting
-    # (sim_gemm_f32_tc, 1.7x cuBLAS SGEMM and 3x closer to the fp64 result); SIM_FP32_GEMM=cublas restores F.linear
+    # fp32 inference: the four projections run on the tensor cores with fp32-accurate 3 x bf16 operand splitting.
+    # x3: hand-written TMA + tcgen05 kernel on pre-split planes (weights split once and cached, 3.7x cuBLAS SGEMM on
+    # in_proj); tc: CUTLASS FastF32 collectives (1.8x); cublas: F.linear (SIMT SGEMM).
     linear = F.linear
-    if not need_grad and act == torch.float32 and hidden.is_cuda and _USE_TC_GEMM:
-        linear = ops.linear_f32_tc
+    if not need_grad and act == torch.float32 and hidden.is_cuda and _FP32_GEMM != "cublas":
+        if _FP32_GEMM == "tc":
+            linear = ops.linear_f32_tc
+        else:
+            def linear(x, w):
+                return ops.linear_f32_x3(x, _CACHE.get(w, "x3", ops.split3), w.shape[1])
     xz = linear(hidden.to(act), w_in)  # (B, L, 2*d_inner)
     x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:

@@ -1,0 +1,306 @@
+// fp32-accurate projection GEMM on the 5th-gen tensor cores from PRE-SPLIT bf16 operands, hand-written for sm_100a
+// (TMA tensor loads -> shared memory -> tcgen05.mma with the accumulator in TMEM -> tcgen05.ld epilogue).
+//
+//   Y[M,N] (fp32) = X[M,K] . W[N,K]^T      (in_proj / x_proj / dt_proj / out_proj of Mamba.forward, models/block.py:72,
+//                                            on the reference's no-autocast fp32 finetune / test path)
+//
+// Every fp32 operand is carried as three bf16 planes x = x0 + x1 + x2 (8 + 8 + 8 significand bits, residuals formed
+// exactly in fp32: sim_split3_bf16 below, or the producing kernel's epilogue).  The product keeps the six partial
+// products whose weight is >= 2^-16 of the leading one,
+//       x0.w2 + x2.w0 + x1.w1 + x0.w1 + x1.w0 + x0.w0       (dropped: x1.w2, x2.w1, x2.w2 <= 2^-24 relative)
+// accumulated in fp32 in tensor memory - the same "3 x bf16" emulation as CUTLASS' FastF32 kernels (gemm_fastf32.cu),
+// but with the operand split hoisted out of the main loop: the weights are split once per model, the activations by
+// the kernel that produces them, so the GEMM main loop is pure TMA + MMA (no transform warps, 6 instead of 9 MMAs).
+// The tensor core's fp32 accumulation truncates (measured: one shared accumulator drifts to 5e-6 at K = 768, 5x a
+// true fp32 GEMM), so the leading product x0.w0 and the five correction products (2^-8 .. 2^-16 of it) accumulate in
+// TWO TMEM accumulators that are only added in the epilogue: the truncation of the small one is 2^-8 smaller, the
+// large one sees 6x fewer accumulations.
+//
+// Roofline: tensor pipe, 6 x (2 M N K) bf16 flops.  One CTA per 128 x BN output tile, 6 warps: warp 0 = TMA producer
+// (one thread), warp 1 = TMEM allocator + MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers -> padded
+// shared-memory staging -> coalesced 16-byte global stores).
+
+#include "kernels.cuh"
+#include "tma.cuh"
+
+namespace sim {
+
+namespace {
+
+constexpr int kBM = 128;  // rows of X per CTA == TMEM lanes
+constexpr int kBK = 32;   // K elements per pipeline stage = one 64-byte swizzle row of bf16
+constexpr int kUK = 16;   // K of one tcgen05.mma.kind::f16
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_TILE = kBM * kBK * 2;
+  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
+  static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr int STG_LD = 36;  // padded row stride (floats) of the epilogue staging tile: 16-B aligned, conflict-free
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+  static_assert(4 * 32 * STG_LD * 4 <= STAGE, "epilogue staging reuses pipeline stage 0");
+  static_assert(A_TILE % 1024 == 0 && B_TILE % 512 == 0, "swizzle-64B tiles need 512-byte aligned bases");
+};
+
+// ---- PTX wrappers (tcgen05 / TMEM)
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, both K-major, bf16 in, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor of a K-major bf16 tile whose rows are one 64-byte swizzle span (kBK = 32):
+// start address >> 4 in bits [0,14), stride between 8-row groups (8 x 64 B) >> 4 in bits [32,46), descriptor version 1
+// in bits [46,48), layout SWIZZLE_64B (= 4) in bits [61,64).  (Field layout: cute/arch/mma_sm100_desc.hpp.)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// Instruction descriptor: D fp32 (bits [4,6) = 1), A and B bf16 (bits [7,10) and [10,13) = 1), both K-major,
+// N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmTmaps {
+  CUtensorMap x, w;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
+                                                             long ldd, int M, int N, int K, int n_tiles) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ unsigned char smem_raw[];
+  // swizzled tiles: align the carve-up to 1024 bytes of the shared ADDRESS space
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* accum_full = empty + NSTAGE;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (blockIdx.x / n_tiles) * kBM;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int nk = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.x);
+    tma_prefetch_desc(&tm.w);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);  // columns [0, BN): x0.w0, [BN, 2 BN): the five corrections
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: one tensor copy per operand and stage brings all three planes of the tile
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
+        unsigned char* st = smem + s * Cfg::STAGE;
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+        tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
+        tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      // (X plane, W plane) pairs, smallest contributions first
+      constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
+      constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % NSTAGE;
+        mbar_wait(&full[s], (kb / NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
+        const uint32_t b0 = a0 + 3 * Cfg::A_TILE;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+#pragma unroll
+          for (int k = 0; k < kBK / kUK; ++k) {
+            const uint64_t da = umma_desc_sw64(a0 + PA[q] * Cfg::A_TILE + k * kUK * 2);
+            const uint64_t db = umma_desc_sw64(b0 + PB[q] * Cfg::B_TILE + k * kUK * 2);
+            umma_bf16(tmem_d + (q == 5 ? 0 : BN), da, db, idesc, q == 5 ? (kb | k) != 0 : (kb | q | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);  // stage s may be refilled once these MMAs have read it
+      }
+      umma_commit(accum_full);
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes [32 (w % 4), +32) = rows m0 + 32 (w % 4) + lane
+    const int quad = warp & 3;
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + quad * 32 * Cfg::STG_LD;  // stage 0 is idle now
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (n0 + c * 32 >= N) break;
+      float v[32], sm[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + BN + c * 32, sm);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sm[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
+        const int gm = m0 + quad * 32 + row, gn = n0 + c * 32 + col;
+        if (gm < M && gn < N)
+          *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, 2 * BN);
+  }
+}
+
+// 3-D map over the three bf16 planes of a row-major (rows, K) operand: dims (K, rows, 3), 64-byte swizzle.
+int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows) {
+  PFN_tmapEncodeTiled enc = tmap_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SIM_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 3u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (planes) failed with CUresult %d (K=%d rows=%d ld=%ld plane=%ld)", (int)r, K, rows, ld,
+              plane);
+    return SIM_ERR_CUDA;
+  }
+  return SIM_OK;
+}
+
+template <int BN>
+int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_split3_kernel<BN>;
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 attr");
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
+  kern<<<m_tiles * n_tiles, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles);
+  return check_launch("gemm_split3");
+}
+
+// x = x0 + x1 + x2 with every residual formed exactly in fp32 (the differences are representable)
+__global__ void split3_kernel(const float* __restrict__ x, long ld, int rows, int K, __nv_bfloat16* __restrict__ out,
+                              long ldo, long plane) {
+  const int kq = K / 4;
+  const long n = (long)rows * kq;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / kq;
+    const int c = (int)(i % kq) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 p[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[0][j] = __float2bfloat16_rn(f[j]);
+      const float r1 = f[j] - __bfloat162float(p[0][j]);
+      p[1][j] = __float2bfloat16_rn(r1);
+      p[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][j]));
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) *reinterpret_cast<uint2*>(out + q * plane + r * ldo + c) = *reinterpret_cast<const uint2*>(p[q]);
+  }
+}
+
+}  // namespace
+
+int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream) {
+  SIM_REQUIRE(x && out && rows > 0 && K > 0, SIM_ERR_INVALID, "split3_bf16: empty problem / null tensor");
+  SIM_REQUIRE(K % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && plane % 4 == 0 && aligned16(x) &&
+                  (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+              SIM_ERR_ALIGN, "split3_bf16: K, strides must be multiples of 4 and bases 16-byte aligned");
+  const long n = (long)rows * (K / 4);
+  const int grid = (int)((n + 255) / 256 < 148L * 16 ? (n + 255) / 256 : 148L * 16);
+  split3_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, K, static_cast<__nv_bfloat16*>(out), ldo, plane);
+  return check_launch("split3_bf16");
+}
+
+int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
+                int N, int K, cudaStream_t stream) {
+  SIM_REQUIRE(Xs && Ws && Y && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_bf16x3: empty problem / null tensor");
+  SIM_REQUIRE(aligned16(Xs) && aligned16(Ws) && aligned16(Y) && ldx % 8 == 0 && ldw % 8 == 0 && xplane % 8 == 0 &&
+                  wplane % 8 == 0 && ldd % 4 == 0 && N % 4 == 0,
+              SIM_ERR_ALIGN, "gemm_bf16x3: TMA needs 16-byte aligned bases / strides, the epilogue N and ldd multiples of 4");
+  // widest tile that still gives every SM work; the two operand tiles of a stage share one tensor copy each
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int bn = N <= 64 ? 64 : ((N % 256 == 0 && (long)m_tiles * (N / 256) >= 2 * 148) ? 256 : 128);
+  GemmTmaps tm;
+  int rc;
+  if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
+  if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn))) return rc;
+  switch (bn) {
+    case 64: return launch_gemm<64>(tm, Y, ldd, M, N, K, stream);
+    case 128: return launch_gemm<128>(tm, Y, ldd, M, N, K, stream);
+    default: return launch_gemm<256>(tm, Y, ldd, M, N, K, stream);
+  }
+}
+
+}  // namespace sim

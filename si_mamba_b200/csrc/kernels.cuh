@@ -87,4 +87,8 @@ size_t gemm_f32_tc_workspace_bytes(int M, int N, int K);
 int gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
+int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
+                int N, int K, cudaStream_t stream);
+
 }  // namespace sim

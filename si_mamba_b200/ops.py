@@ -247,6 +247,37 @@ def linear_f32_tc(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Ten
     return out
 
 
+def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (..., K) -> (3, rows, Kp) bf16 planes with x = p0 + p1 + p2 (exact residuals), Kp = K rounded up to 8."""
+    _cuda(x)
+    assert x.dtype == torch.float32
+    K = x.shape[-1]
+    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else _as_rows(x)
+    rows, Kp = x2.shape[0], (K + 7) // 8 * 8
+    if out is None:
+        out = (torch.zeros if Kp != K else torch.empty)(3, rows, Kp, dtype=torch.bfloat16, device=x.device)
+    _lib.call("sim_split3_bf16", _p(x2), x2.stride(0), rows, K, _p(out), out.stride(1), out.stride(0), _stream())
+    return out
+
+
+def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y (rows, N) fp32 = x @ w.T from pre-split planes xs (3, rows, >=K), ws (3, N, >=K) (tcgen05 kernel)."""
+    _cuda(xs, ws)
+    assert xs.dtype == torch.bfloat16 and ws.dtype == torch.bfloat16 and xs.stride(2) == 1 and ws.stride(2) == 1
+    M, N = xs.shape[1], ws.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=xs.device)
+    _lib.call("sim_gemm_bf16x3", _p(xs), xs.stride(1), xs.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out),
+              out.stride(0), M, N, K, _stream())
+    return out
+
+
+def linear_f32_x3(x: torch.Tensor, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
+    """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is split here."""
+    y = linear_split3(split3(x), weight_planes, K)
+    return y.view(*x.shape[:-1], weight_planes.shape[1])
+
+
 def _as_rows(x: torch.Tensor) -> torch.Tensor:
     """(B, L, K) view with unit inner stride and batch stride == L * row stride -> (B*L, K) strided 2-D view."""
     assert x.dim() == 3 and x.stride(2) == 1 and (x.shape[0] == 1 or x.stride(0) == x.shape[1] * x.stride(1))

@@ -369,3 +369,19 @@ def test_gemm_f32_tc(ops, M, N, K, lda):
     assert rel_err(y.cpu().double(), ref) < 2e-6
     x3 = dev(xb)[:, :K].reshape(1, M, K) if lda == K else dev(xb).view(1, M, lda)[..., :K]
     assert torch.equal(ops.linear_f32_tc(x3, dev(w)).view(M, N), y)
+
+
+@pytest.mark.parametrize("M,N,K,lda", [(16384, 1536, 384, 384), (16384, 56, 768, 768), (16384, 768, 24, 56),
+                                       (16384, 384, 768, 768), (100, 64, 36, 36), (7, 384, 128, 128), (300, 256, 40, 40)])
+def test_gemm_bf16x3(ops, M, N, K, lda):
+    """Hand-written tcgen05 GEMM on pre-split bf16 planes vs an fp64 reference: fp32-GEMM class accuracy."""
+    g = torch.Generator().manual_seed(M + N)
+    xb = torch.randn(M, lda, generator=g)
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    ref = xb[:, :K].double() @ w.double().t()
+    xs = ops.split3(dev(xb)[:, :K])
+    assert torch.equal(xs.float().sum(0)[:, :K].cpu(), xb[:, :K])  # the three planes carry all 24 bits
+    ws = ops.split3(dev(w))
+    y = ops.linear_split3(xs, ws, K)
+    assert y.shape == (M, N)
+    assert rel_err(y.cpu().double(), ref) < 2e-6
