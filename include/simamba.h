@@ -153,6 +153,18 @@ int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y
  * elements, row stride ldo); the weights are split once per model, activations by their producer.
  * sim_gemm_bf16x3: Y[M,N] = sum of the six leading plane products X_i . W_j^T, fp32 accumulation in tensor memory.
  * ldx / ldw / plane strides multiples of 8 elements, ldd and N multiples of 4. */
+/* Producers that emit the split operand directly (fp32 activations), so no separate split pass is needed:
+ * LayerNorm output -> in_proj, conv output (fp32 u for the scan AND planes for x_proj), scan output -> out_proj. */
+int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                             float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
+                             sim_stream_t stream);
+int sim_causal_conv1d_fwd_split3(const float* x, long ld_x, const float* w, const float* bias, float* y, long ld_y,
+                                 void* planes, long ld_p, long plane, int batch, int L, int D, int width, int silu,
+                                 sim_stream_t stream);
+int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                                  const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec,
+                                  const void* z, long ld_z, const float* delta_bias, void* out_planes, long ld_planes,
+                                  long plane, int batch, int L, int D, int N, int delta_softplus, sim_stream_t stream);
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
                     int M, int N, int K, sim_stream_t stream);

@@ -46,6 +46,10 @@ SIGNATURES = {
                                     _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _p,
                                     _i, _i, _i, _i, _i, _i, _p]),
     "sim_gemm_f32_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sim_add_layernorm_split3": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _i, _p]),
+    "sim_causal_conv1d_fwd_split3": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _i, _i, _i, _i, _i, _p]),
+    "sim_selective_scan_fwd_split3": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _l,
+                                           _i, _i, _i, _i, _i, _p]),
     "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
     "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),
     "sim_gemm_f32_tc": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _sz, _p]),

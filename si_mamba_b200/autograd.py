@@ -59,11 +59,19 @@ _CACHE = _ParamCache()
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
+def wants_split3(hidden_dtype: torch.dtype, in_proj_w: torch.Tensor, d_model: int) -> bool:
+    """True when the mixer would consume its input as a Split3 (fp32 inference on the x3 GEMM path): the Block's
+    fused add + LayerNorm then writes the split planes directly instead of an fp32 tensor."""
+    return (_FP32_GEMM not in ("cublas", "tc") and hidden_dtype == torch.float32 and in_proj_w.dtype == torch.float32
+            and in_proj_w.is_cuda and d_model % 8 == 0
+            and not (torch.is_grad_enabled() and in_proj_w.requires_grad))
+
+
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
                    dt_rank: int, d_state: int) -> torch.Tensor:
     """Token-major Mamba mixer body.  hidden (B, L, d_model) -> (B, L, d_model)."""
     d_inner = conv_w.shape[0]
-    act = _amp_dtype(hidden)
+    act = _amp_dtype(hidden) if not isinstance(hidden, ops.Split3) else torch.float32
     need_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in (hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D,
                                   out_proj_w))
@@ -78,24 +86,29 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     # x3: hand-written TMA + tcgen05 kernel on pre-split planes (weights split once and cached, 3.7x cuBLAS SGEMM on
     # in_proj); tc: CUTLASS FastF32 collectives (1.8x); cublas: F.linear (SIMT SGEMM).
     linear = F.linear
+    x3 = False
     if not need_grad and act == torch.float32 and hidden.is_cuda and _FP32_GEMM != "cublas":
         if _FP32_GEMM == "tc":
             linear = ops.linear_f32_tc
         else:
+            x3 = d_inner % 64 == 0  # every producer below then emits the split operand of the next projection itself
+
             def linear(x, w):
                 return ops.linear_f32_x3(x, _CACHE.get(w, "x3", ops.split3), w.shape[1])
-    xz = linear(hidden.to(act), w_in)  # (B, L, 2*d_inner)
+    xz = linear(hidden if isinstance(hidden, ops.Split3) else hidden.to(act), w_in)  # (B, L, 2*d_inner)
     x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:
-        u = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
+        u = u_op = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
+    elif x3:
+        u, u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True, split=True)
     else:
-        u = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
-    x_dbl = linear(u, w_x)  # (B, L, dt_rank + 2*d_state)
+        u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
+    x_dbl = linear(u_op, w_x)  # (B, L, dt_rank + 2*d_state)
     dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]
     Cm = x_dbl[..., dt_rank + d_state:]
     if need_grad:
         y = ops.SelectiveScanTM.apply(u, dt, A, Bm, Cm, D, z, dt_proj_b, True)
     else:
-        y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True)
+        y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True, split=x3)
     return linear(y, w_out)

@@ -35,7 +35,8 @@ class DropPath(nn.Module):
         return x.div(keep) * mask
 
 
-def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor], want_residual: bool = True):
+def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor], want_residual: bool = True,
+                   split: bool = False):
     """(LayerNorm(hidden + residual), hidden + residual) through the CUDA kernel when no autograd graph is
     needed; plain torch ops (so autograd works) when training."""
     needs_grad = torch.is_grad_enabled() and (hidden.requires_grad or (residual is not None and residual.requires_grad)
@@ -44,8 +45,9 @@ def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor
         res = hidden + residual if residual is not None else hidden
         res = res.float() if res.dtype != torch.float32 else res
         return norm(res.to(dtype=norm.weight.dtype)), res
-    return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=_amp_dtype(hidden),
-                             want_residual=want_residual)
+    out_dtype = _amp_dtype(hidden)
+    return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=out_dtype,
+                             want_residual=want_residual, split=split and out_dtype == torch.float32)
 
 
 class Block(nn.Module):
@@ -60,7 +62,10 @@ class Block(nn.Module):
 
     def forward(self, hidden_states: Tensor, residual: Optional[Tensor] = None, inference_params=None):
         """residual = drop_path(hidden) + residual; hidden = mixer(LN(residual)).  block.py:47-73."""
-        hidden_states, residual = fused_add_norm(self.norm, self.drop_path(hidden_states), residual)
+        # fp32 inference: LayerNorm writes the in_proj operand (three bf16 planes) directly, see autograd.wants_split3
+        want = getattr(self.mixer, "wants_split3", None)
+        split = bool(want and want(hidden_states))
+        hidden_states, residual = fused_add_norm(self.norm, self.drop_path(hidden_states), residual, split=split)
         hidden_states = self.mixer(hidden_states, inference_params=inference_params)
         return hidden_states, residual
 

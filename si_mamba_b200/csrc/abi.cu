@@ -121,6 +121,38 @@ int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_
   return sim::selective_scan_fwd(p, dtype, variant, static_cast<cudaStream_t>(stream));
 }
 
+int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
+                                  const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec,
+                                  const void* z, long ld_z, const float* delta_bias, void* out_planes, long ld_planes,
+                                  long plane, int batch, int L, int D, int N, int delta_softplus, sim_stream_t stream) {
+  if (N != 16) {
+    sim::set_error("sim_selective_scan_fwd_split3: d_state must be 16 (got %d)", N);
+    return SIM_ERR_INVALID;
+  }
+  sim::ScanParams p;
+  p.u = u, p.delta = delta, p.z = z, p.Bm = Bm, p.Cm = Cm, p.out = nullptr;
+  p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
+  p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_out = 0;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  p.ckpt = nullptr;
+  p.out_planes = out_planes, p.ld_planes = ld_planes, p.plane = plane;
+  return sim::selective_scan_fwd(p, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                             float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
+                             sim_stream_t stream) {
+  return sim::add_layernorm(x, x2, res_in, gamma, beta, res_out, nullptr, rows, C, eps, dtype_x, 0,
+                            static_cast<cudaStream_t>(stream), planes, plane);
+}
+
+int sim_causal_conv1d_fwd_split3(const float* x, long ld_x, const float* w, const float* bias, float* y, long ld_y,
+                                 void* planes, long ld_p, long plane, int batch, int L, int D, int width, int silu,
+                                 sim_stream_t stream) {
+  return sim::causal_conv1d_fwd(x, ld_x, w, bias, y, ld_y, batch, L, D, width, silu, 0,
+                                static_cast<cudaStream_t>(stream), planes, ld_p, plane);
+}
+
 size_t sim_selective_scan_checkpoint_bytes(int batch, int L, int D) {
   if (batch <= 0 || L <= 0 || D <= 0) return 0;
   return (size_t)batch * ((L + sim::kScanTile - 1) / sim::kScanTile) * D * 16 * sizeof(float);

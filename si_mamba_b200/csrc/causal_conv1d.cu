@@ -48,7 +48,9 @@ template <typename T, int TC>
 __global__ void __launch_bounds__(256) causal_conv1d_fwd_kernel(const T* __restrict__ x, long ld_x,
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ bias, T* __restrict__ y,
-                                                                long ld_y, int batch, int L, int D, int silu) {
+                                                                long ld_y, int batch, int L, int D, int silu,
+                                                                __nv_bfloat16* __restrict__ planes, long ld_p,
+                                                                long plane) {
   const int nv = D / 4;
   const int nchunk = (L + TC - 1) / TC;
   const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(256) causal_conv1d_fwd_kernel(const T* __restr
       acc.x = silu_f(acc.x), acc.y = silu_f(acc.y), acc.z = silu_f(acc.z), acc.w = silu_f(acc.w);
     }
     Vec4<T>::store(yb + (long)t * ld_y, acc);
+    if (planes) split3_store4(planes + ((long)b * L + t) * ld_p + d0, plane, acc);  // x_proj operand (gemm_split3.cu)
   }
 }
 
@@ -165,7 +168,10 @@ __global__ void __launch_bounds__(256) causal_conv1d_fwd_bf16x8_kernel(const __n
 }
 
 int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y, int batch,
-                      int L, int D, int width, int silu, int dtype, cudaStream_t stream) {
+                      int L, int D, int width, int silu, int dtype, cudaStream_t stream, void* planes, long ld_p,
+                      long plane) {
+  SIM_REQUIRE(!planes || (dtype == 0 && (reinterpret_cast<uintptr_t>(planes) & 7u) == 0 && ld_p % 4 == 0 && plane % 4 == 0),
+              SIM_ERR_INVALID, "causal_conv1d_fwd: split planes need fp32 activations and 8-byte alignment");
   SIM_REQUIRE(width == kConvW, SIM_ERR_INVALID, "causal_conv1d_fwd: only width 4 is built (got %d)", width);
   SIM_REQUIRE(D % 4 == 0 && batch > 0 && L > 0, SIM_ERR_INVALID, "causal_conv1d_fwd: D must be a multiple of 4");
   SIM_REQUIRE(dtype == 0 || dtype == 1, SIM_ERR_INVALID, "causal_conv1d_fwd: dtype must be 0 (fp32) or 1 (bf16)");
@@ -188,10 +194,11 @@ int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bia
   const int grid = (int)((items + 255) / 256);
   if (dtype == 0)
     causal_conv1d_fwd_kernel<float, TC><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld_x, w, bias,
-                                                                  static_cast<float*>(y), ld_y, batch, L, D, silu);
+                                                                  static_cast<float*>(y), ld_y, batch, L, D, silu,
+                                                                  static_cast<__nv_bfloat16*>(planes), ld_p, plane);
   else
     causal_conv1d_fwd_kernel<__nv_bfloat16, TC><<<grid, 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<__nv_bfloat16*>(y), ld_y, batch, L, D, silu);
+        static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<__nv_bfloat16*>(y), ld_y, batch, L, D, silu, nullptr, 0, 0);
   return check_launch("causal_conv1d_fwd");
 }
 

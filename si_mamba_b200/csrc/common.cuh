@@ -163,4 +163,20 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
 
+// x = p0 + p1 + p2 as three bf16 values with exactly formed fp32 residuals (operand format of gemm_split3.cu);
+// four adjacent elements -> one 8-byte store per plane.
+__device__ __forceinline__ void split3_store4(__nv_bfloat16* dst, long plane, float4 v) {
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 q[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    q[0][j] = __float2bfloat16_rn(f[j]);
+    const float r1 = f[j] - __bfloat162float(q[0][j]);
+    q[1][j] = __float2bfloat16_rn(r1);
+    q[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(q[1][j]));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(dst + k * plane) = *reinterpret_cast<const uint2*>(q[k]);
+}
+
 }  // namespace sim

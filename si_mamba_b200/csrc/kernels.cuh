@@ -9,13 +9,13 @@ namespace sim {
 int fps(const float*, int, int, int, int*, float*, cudaStream_t);
 int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t);
 int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
-                  int, int, cudaStream_t);
+                  int, int, cudaStream_t, void* planes = nullptr, long plane = 0);
 int order_gather_fwd(const void*, const void*, const int*, void*, void*, int, int, int, int, int, int, cudaStream_t);
 int order_gather_bwd(const void*, const int*, void*, int, int, int, int, int, int, cudaStream_t);
 int gather_rows(const void*, const int*, const void*, void*, int, int, int, int, int, cudaStream_t);
 int argsort_rows(const float*, long, long, int, int, int*, int*, cudaStream_t);
 int causal_conv1d_fwd(const void*, long, const float*, const float*, void*, long, int, int, int, int, int, int,
-                      cudaStream_t);
+                      cudaStream_t, void* planes = nullptr, long ld_p = 0, long plane = 0);
 
 struct ScanParams {
   const void* u;
@@ -31,6 +31,10 @@ struct ScanParams {
   int batch, L, D;
   int softplus;
   float* ckpt;  // optional (batch, ceil(L/kScanTile), D, 16) fp32: state at the START of every tile (for backward)
+  // optional (fp32 activations, warp-specialised kernel): write the result as three bf16 planes instead of `out`
+  // (operand format of gemm_split3.cu: out_proj consumes it directly); plane q at out_planes + q * plane elements
+  void* out_planes = nullptr;
+  long ld_planes = 0, plane = 0;
 };
 constexpr int kScanTile = 16;  // time steps per tile of the scan kernels == checkpoint interval
 int selective_scan_fwd(const ScanParams&, int, int, cudaStream_t);

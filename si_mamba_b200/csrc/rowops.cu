@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             float* __restrict__ res_out, TY* __restrict__ y,
-                                                            long rows, int C, float eps) {
+                                                            long rows, int C, float eps,
+                                                            __nv_bfloat16* __restrict__ planes, long plane) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -103,25 +104,29 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
       o.y = (v[i].y - mean) * rstd * g.y + bb.y;
       o.z = (v[i].z - mean) * rstd * g.z + bb.z;
       o.w = (v[i].w - mean) * rstd * g.w + bb.w;
-      st4<TY>(y + row * C + 4 * q, o);
+      if (y) st4<TY>(y + row * C + 4 * q, o);
+      if (planes) split3_store4(planes + row * C + 4 * q, plane, o);
     }
   }
 }
 
 int add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
                   float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, void* planes, long plane) {
   SIM_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
               "add_layernorm: C must be a multiple of 4 and <= 1024 (got %d)", C);
-  SIM_REQUIRE(x && gamma && beta && y, SIM_ERR_INVALID, "add_layernorm: null tensor");
-  SIM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!x2 || aligned16(x2)) &&
+  SIM_REQUIRE(x && gamma && beta && (y || planes), SIM_ERR_INVALID, "add_layernorm: null tensor");
+  SIM_REQUIRE((!planes || ((reinterpret_cast<uintptr_t>(planes) & 7u) == 0 && plane % 4 == 0)), SIM_ERR_ALIGN,
+              "add_layernorm: split planes need 8-byte alignment");
+  SIM_REQUIRE(aligned16(x) && (!y || aligned16(y)) && aligned16(gamma) && aligned16(beta) && (!x2 || aligned16(x2)) &&
                   (!res_in || aligned16(res_in)) && (!res_out || aligned16(res_out)),
               SIM_ERR_ALIGN, "add_layernorm: tensors must be 16-byte aligned");
   const int grid = (int)((rows + 7) / 8);
 #define SIM_LN_LAUNCH(TX, TY, MAXV)                                                                          \
   add_layernorm_kernel<TX, TY, MAXV><<<grid, 256, 0, stream>>>(static_cast<const TX*>(x),                    \
                                                                static_cast<const TX*>(x2), res_in, gamma,    \
-                                                               beta, res_out, static_cast<TY*>(y), rows, C, eps)
+                                                               beta, res_out, static_cast<TY*>(y), rows, C, eps,  \
+                                                               static_cast<__nv_bfloat16*>(planes), plane)
 #define SIM_LN_MAXV(TX, TY)                     \
   if (C <= 384) {                               \
     SIM_LN_LAUNCH(TX, TY, 3);                   \

@@ -532,7 +532,11 @@ int selective_scan_fwd(const ScanParams& p, int dtype, int variant, cudaStream_t
   const int es = dtype == 0 ? 4 : 2;
   SIM_REQUIRE(dtype == 0 || dtype == 1, SIM_ERR_INVALID, "selective_scan_fwd: dtype must be 0 (fp32) or 1 (bf16)");
   SIM_REQUIRE(p.batch > 0 && p.L > 0 && p.D > 0, SIM_ERR_INVALID, "selective_scan_fwd: empty problem");
-  SIM_REQUIRE(p.u && p.delta && p.Bm && p.Cm && p.out && p.A, SIM_ERR_INVALID, "selective_scan_fwd: null tensor");
+  SIM_REQUIRE(p.u && p.delta && p.Bm && p.Cm && (p.out || p.out_planes) && p.A, SIM_ERR_INVALID,
+              "selective_scan_fwd: null tensor");
+  SIM_REQUIRE(!p.out_planes || (dtype == 0 && p.D % 64 == 0 && (variant == 0 || variant >= 5000) && aligned16(p.out_planes) &&
+                                p.ld_planes % 8 == 0 && p.plane % 8 == 0),
+              SIM_ERR_INVALID, "selective_scan_fwd: split-plane output needs fp32 activations, D %% 64 == 0 and 16-byte aligned planes");
   const void* ptrs[] = {p.u, p.delta, p.z, p.Bm, p.Cm, p.out};
   const long lds[] = {p.ld_u, p.ld_delta, p.ld_z, p.ld_B, p.ld_C, p.ld_out};
   for (int i = 0; i < 6; ++i) {

@@ -50,7 +50,7 @@ struct ScanWsCfg {
   static constexpr int WORK_DT = TT * CH_ * 8;
   static constexpr int WORK_BC = TT * kNState * 4;
   static constexpr int WORK = WORK_DT + 2 * WORK_BC;
-  static constexpr int YBUF = TT * CH_ * 4;
+  static constexpr int YBUF = TT * CH_ * 6;  // fp32 <h, C> sums (4 B) / results in place, or three bf16 result planes (6 B)
   static constexpr int SMEM = NS_ * RAW_STAGE + 2 * WORK + 2 * YBUF + (NS_ + 4) * 8 + 16;
   static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && WORK % 128 == 0 && YBUF % 128 == 0,
                 "TMA tiles must stay 128-B aligned");
@@ -122,8 +122,13 @@ __device__ __forceinline__ void sts_out4<__nv_bfloat16>(__nv_bfloat16* dst, floa
   *reinterpret_cast<uint2*>(dst) = r;
 }
 
+struct PlaneTmaps {
+  CUtensorMap p[3];
+};
+
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kernel(const __grid_constant__ ScanTmaps tm,
+                                                                        const __grid_constant__ PlaneTmaps ptm,
                                                                         const ScanParams p) {
   constexpr int S = Cfg::S, LPC = Cfg::LPC, CH = Cfg::CH, TT = Cfg::TT, NS = Cfg::NS, NR = Cfg::NR, NE = Cfg::NE,
                 CQ = Cfg::CQ, RPP = Cfg::RPP, GPT = Cfg::GPT;
@@ -147,7 +152,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
     tma_prefetch_desc(&tm.delta);
     tma_prefetch_desc(&tm.B);
     tma_prefetch_desc(&tm.C);
-    tma_prefetch_desc(&tm.out);
+    if (p.out_planes) {
+      for (int q = 0; q < 3; ++q) tma_prefetch_desc(&ptm.p[q]);
+    } else {
+      tma_prefetch_desc(&tm.out);
+    }
     if (has_z) tma_prefetch_desc(&tm.z);
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     for (int s = 0; s < 2; ++s) {
@@ -241,13 +250,27 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
           o[i] = make_float4((y.x + du[q][i].x) * gate[q][i].x, (y.y + du[q][i].y) * gate[q][i].y,
                              (y.z + du[q][i].z) * gate[q][i].z, (y.w + du[q][i].w) * gate[q][i].w);
         }
-        if constexpr (sizeof(T) != 4) bar_sync(2, NE);  // narrower outputs overlap other threads' fp32 sums
+        const bool split = p.out_planes != nullptr;
+        if (sizeof(T) != 4 || split) bar_sync(2, NE);  // narrower outputs overlap other threads' fp32 sums
+        if (split) {
+          // out_proj operand: three bf16 planes, each a dense (TT, CH) tile
 #pragma unroll
-        for (int i = 0; i < GPT; ++i) sts_out4<T>(reinterpret_cast<T*>(yb) + (r0 + i * RPP) * CH + cc, o[i]);
+          for (int i = 0; i < GPT; ++i)
+            split3_store4(reinterpret_cast<__nv_bfloat16*>(yb) + (r0 + i * RPP) * CH + cc, TT * CH, o[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < GPT; ++i) sts_out4<T>(reinterpret_cast<T*>(yb) + (r0 + i * RPP) * CH + cc, o[i]);
+        }
         fence_proxy_async();
         bar_sync(1, NE);
         if (te == 0) {
-          tma_store_3d(&tm.out, c0, j * TT, b, yb);  // rows past L are clipped by the TMA unit
+          if (split) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              tma_store_3d(&ptm.p[q], c0, j * TT, b, reinterpret_cast<__nv_bfloat16*>(yb) + q * TT * CH);
+          } else {
+            tma_store_3d(&tm.out, c0, j * TT, b, yb);  // rows past L are clipped by the TMA unit
+          }
           bulk_commit();
         }
       }
@@ -338,8 +361,22 @@ int launch_scan_ws(const ScanParams& p, int dtype, cudaStream_t stream) {
   }
   if ((rc = make_tmap_tokens(&tm.B, p.Bm, dtype, kNState, p.L, p.batch, p.ld_B, kNState, TT))) return rc;
   if ((rc = make_tmap_tokens(&tm.C, p.Cm, dtype, kNState, p.L, p.batch, p.ld_C, kNState, TT))) return rc;
-  if ((rc = make_tmap_tokens(&tm.out, p.out, dtype, p.D, p.L, p.batch, p.ld_out, CH, TT))) return rc;
-  kern<<<p.batch * (p.D / CH), Cfg::NT, Cfg::SMEM, stream>>>(tm, p);
+  PlaneTmaps ptm;
+  if (p.out_planes) {
+    if (dtype != 0) {
+      set_error("selective_scan_fwd_ws: split bf16 planes are an fp32-activation output format");
+      return SIM_ERR_INVALID;
+    }
+    for (int q = 0; q < 3; ++q)
+      if ((rc = make_tmap_tokens(&ptm.p[q], static_cast<const __nv_bfloat16*>(p.out_planes) + q * p.plane, 1, p.D, p.L,
+                                 p.batch, p.ld_planes, CH, TT)))
+        return rc;
+    tm.out = tm.u;
+  } else {
+    if ((rc = make_tmap_tokens(&tm.out, p.out, dtype, p.D, p.L, p.batch, p.ld_out, CH, TT))) return rc;
+    ptm.p[0] = ptm.p[1] = ptm.p[2] = tm.out;
+  }
+  kern<<<p.batch * (p.D / CH), Cfg::NT, Cfg::SMEM, stream>>>(tm, ptm, p);
   return check_launch("selective_scan_fwd_ws");
 }
 

@@ -78,5 +78,13 @@ class Mamba(nn.Module):
                               self.x_proj.weight, self.dt_proj.weight, self.dt_proj.bias, self.A_log, self.D,
                               self.out_proj.weight, self.dt_rank, self.d_state)
 
+    def wants_split3(self, hidden_states) -> bool:
+        """Whether forward() takes its input as an ops.Split3 (written by the Block's fused add + LayerNorm)."""
+        from .autograd import wants_split3
+        return (hidden_states.is_cuda and not hidden_states.requires_grad
+                and wants_split3(hidden_states.dtype if not torch.is_autocast_enabled("cuda") else
+                                 torch.get_autocast_dtype("cuda"), self.in_proj.weight, self.d_model)
+                and self.d_inner % 64 == 0)
+
     def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
         raise NotImplementedError("step-wise decoding is not on SI-Mamba's path")

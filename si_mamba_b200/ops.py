@@ -208,19 +208,26 @@ def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Ten
 # ----------------------------------------------------------------------------- add + LayerNorm (a-9)
 def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
                   eps: float = 1e-5, x2: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-                  want_residual: bool = True):
-    """res = x (+ x2) (+ residual) in fp32;  y = LayerNorm(res).  -> (y, res or None).  Forward only."""
+                  want_residual: bool = True, split: bool = False):
+    """res = x (+ x2) (+ residual) in fp32;  y = LayerNorm(res).  -> (y, res or None).  Forward only.
+    ``split``: y is returned as a Split3 (three bf16 planes of the fp32 result) for linear_split3."""
     _cuda(x, residual, weight, bias, x2)
     x = x.contiguous()
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     out_dtype = out_dtype or x.dtype
-    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     res_out = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_residual else None
     if residual is not None:
         residual = residual.float().contiguous()
     if x2 is not None:
         x2 = x2.to(x.dtype).contiguous()
+    if split:
+        assert Cc % 8 == 0
+        planes = torch.empty(3, rows, Cc, dtype=torch.bfloat16, device=x.device)
+        _lib.call("sim_add_layernorm_split3", _p(x), _p(x2), _p(residual), _p(_f32c(weight)), _p(_f32c(bias)),
+                  _p(res_out), _p(planes), planes.stride(0), rows, Cc, float(eps), _dt(x), _stream())
+        return Split3(planes, x.shape), res_out
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     _lib.call("sim_add_layernorm", _p(x), _p(x2), _p(residual), _p(_f32c(weight)), _p(_f32c(bias)), _p(res_out),
               _p(y), rows, Cc, float(eps), _dt(x), _dt(y), _stream())
     return y, res_out
@@ -245,6 +252,29 @@ def linear_f32_tc(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Ten
     _lib.call("sim_gemm_f32_tc", _p(x2), x2.stride(0), _p(w), w.stride(0), _p(out), N, M, N, K, _p(ws),
               ws_bytes if ws is not None else 0, _stream())
     return out
+
+
+class Split3:
+    """An fp32 activation (..., K) carried as three bf16 planes (3, rows, K): the operand format of the tcgen05
+    projection GEMM (csrc/gemm_split3.cu).  Produced by add_layernorm / causal_conv1d_tm / selective_scan_tm with
+    ``split=True`` or by split3(); consumed by linear_split3."""
+
+    __slots__ = ("planes", "shape")
+
+    def __init__(self, planes: torch.Tensor, shape):
+        self.planes, self.shape = planes, tuple(shape)
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    @property
+    def is_cuda(self):
+        return True
+
+    @property
+    def requires_grad(self):
+        return False
 
 
 def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -272,9 +302,11 @@ def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torc
     return out
 
 
-def linear_f32_x3(x: torch.Tensor, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
-    """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is split here."""
-    y = linear_split3(split3(x), weight_planes, K)
+def linear_f32_x3(x, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
+    """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is a Split3 from its producer, or an
+    fp32 tensor that is split here."""
+    xs = x.planes if isinstance(x, Split3) else split3(x)
+    y = linear_split3(xs, weight_planes, K)
     return y.view(*x.shape[:-1], weight_planes.shape[1])
 
 
@@ -286,14 +318,21 @@ def _as_rows(x: torch.Tensor) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- causal conv1d (a-12)
 def causal_conv1d_tm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool = True,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Token-major causal depthwise conv (forward only): x (B,L,D) (any uniform row stride), weight (D,W) -> (B,L,D)."""
+                     out: Optional[torch.Tensor] = None, split: bool = False):
+    """Token-major causal depthwise conv (forward only): x (B,L,D) (any uniform row stride), weight (D,W) -> (B,L,D).
+    ``split`` (fp32): also returns the result as a Split3 for linear_split3 -> (out, Split3)."""
     _cuda(x, weight, bias)
     B, L, D = x.shape
     ld_x = _tm(x)
     if out is None:
         out = torch.empty(B, L, D, dtype=x.dtype, device=x.device)
     w = _f32c(weight.reshape(D, -1))
+    if split:
+        assert x.dtype == torch.float32 and D % 8 == 0
+        planes = torch.empty(3, B * L, D, dtype=torch.bfloat16, device=x.device)
+        _lib.call("sim_causal_conv1d_fwd_split3", _p(x), ld_x, _p(w), _p(_f32c(bias)), _p(out), _tm(out), _p(planes),
+                  planes.stride(1), planes.stride(0), B, L, D, w.shape[1], int(silu), _stream())
+        return out, Split3(planes, (B, L, D))
     _lib.call("sim_causal_conv1d_fwd", _p(x), ld_x, _p(w), _p(_f32c(bias)), _p(out), _tm(out), B, L, D,
               w.shape[1], int(silu), _dt(x), _stream())
     return out
@@ -343,17 +382,24 @@ def causal_conv1d_fn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
 # ----------------------------------------------------------------------------- selective scan (a-11)
 def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False,
                       out: Optional[torch.Tensor] = None, variant: int = 0,
-                      checkpoints: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      checkpoints: Optional[torch.Tensor] = None, split: bool = False):
     """Token-major selective scan (forward only).  u, delta, z (B,L,D); Bm, Cm (B,L,N) - all may be column slices of
     wider row-major buffers; A (D,N) fp32.  Returns out (B,L,D) in u's dtype.  ``checkpoints`` (fp32,
     scan_checkpoint_shape) receives the tile-start states the backward kernel needs."""
     _cuda(u, delta, A, Bm, Cm, D, z, delta_bias)
     B, L, Dm = u.shape
     N = A.shape[1]
-    if out is None:
-        out = torch.empty(B, L, Dm, dtype=u.dtype, device=u.device)
     u, delta, Bm, Cm, z = (_bulk_ok(t) for t in (u, delta, Bm, Cm, z))
     assert delta.dtype == u.dtype and Bm.dtype == u.dtype and Cm.dtype == u.dtype and (z is None or z.dtype == u.dtype)
+    if split:  # fp32 only: the result leaves as the three bf16 planes out_proj consumes (returns a Split3)
+        assert u.dtype == torch.float32 and Dm % 64 == 0 and checkpoints is None
+        planes = torch.empty(3, B * L, Dm, dtype=torch.bfloat16, device=u.device)
+        _lib.call("sim_selective_scan_fwd_split3", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm),
+                  _tm(Bm), _p(Cm), _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)),
+                  _p(planes), planes.stride(1), planes.stride(0), B, L, Dm, N, int(delta_softplus), _stream())
+        return Split3(planes, (B, L, Dm))
+    if out is None:
+        out = torch.empty(B, L, Dm, dtype=u.dtype, device=u.device)
     _lib.call("sim_selective_scan_fwd", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm), _tm(Bm), _p(Cm),
               _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(out), _tm(out),
               _p(checkpoints), B, L, Dm, N, int(delta_softplus), _dt(u), int(variant), _stream())

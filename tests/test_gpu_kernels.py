@@ -385,3 +385,26 @@ def test_gemm_bf16x3(ops, M, N, K, lda):
     y = ops.linear_split3(xs, ws, K)
     assert y.shape == (M, N)
     assert rel_err(y.cpu().double(), ref) < 2e-6
+
+
+def test_split3_producers(ops):
+    """LayerNorm / conv / scan can emit their fp32 result as the three bf16 planes the tcgen05 GEMM consumes:
+    the planes must add up to the plain fp32 result bit for bit."""
+    g = torch.Generator().manual_seed(3)
+    B, L, C, D = 2, 77, 384, 128
+    x, r = dev(torch.randn(B, L, C, generator=g)), dev(torch.randn(B, L, C, generator=g))
+    w, b = dev(torch.randn(C, generator=g)), dev(torch.randn(C, generator=g))
+    y, res = ops.add_layernorm(x, r, w, b)
+    ys, res2 = ops.add_layernorm(x, r, w, b, split=True)
+    assert torch.equal(ys.planes.float().sum(0).view(B, L, C), y) and torch.equal(res, res2) and ys.shape == y.shape
+    xc = dev(torch.randn(B, L, 2 * D, generator=g))
+    cw, cb = dev(torch.randn(D, 4, generator=g) * 0.5), dev(torch.randn(D, generator=g) * 0.1)
+    u = ops.causal_conv1d_tm(xc[..., :D], cw, cb, True)
+    u2, us = ops.causal_conv1d_tm(xc[..., :D], cw, cb, True, split=True)
+    assert torch.equal(u, u2) and torch.equal(us.planes.float().sum(0).view(B, L, D), u)
+    uu, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 11)
+    tm = lambda t: dev(t.transpose(1, 2).contiguous())
+    args = (tm(uu), tm(delta), dev(A), tm(Bm), tm(Cm), dev(Dv), tm(z), dev(bias), True)
+    out = ops.selective_scan_tm(*args)
+    outs = ops.selective_scan_tm(*args, split=True)
+    assert torch.equal(outs.planes.float().sum(0).view(B, L, D), out)
