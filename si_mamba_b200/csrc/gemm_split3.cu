@@ -20,6 +20,8 @@
 // (one thread), warp 1 = TMEM allocator + MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers -> padded
 // shared-memory staging -> coalesced 16-byte global stores).
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tma.cuh"
 
@@ -31,12 +33,13 @@ constexpr int kBM = 128;  // rows of X per CTA == TMEM lanes
 constexpr int kBK = 32;   // K elements per pipeline stage = one 64-byte swizzle row of bf16
 constexpr int kUK = 16;   // K of one tcgen05.mma.kind::f16
 
-template <int BN>
+template <int BN, int NSTAGE_>
 struct GemmCfg {
   static constexpr int A_TILE = kBM * kBK * 2;
   static constexpr int B_TILE = BN * kBK * 2;
   static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
-  static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int MINB = (NSTAGE_ * STAGE + 2304) * 2 <= 232448 && 4 * BN <= 512 ? 2 : 1;  // CTAs per SM
   static constexpr int STG_LD = 36;  // padded row stride (floats) of the epilogue staging tile: 16-B aligned, conflict-free
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
   static_assert(4 * 32 * STG_LD * 4 <= STAGE, "epilogue staging reuses pipeline stage 0");
@@ -105,10 +108,10 @@ struct GemmTmaps {
   CUtensorMap x, w;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
+template <int BN, int NSTAGE_>
+__global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
                                                              long ldd, int M, int N, int K, int n_tiles) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NSTAGE_>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
   // swizzled tiles: align the carve-up to 1024 bytes of the shared ADDRESS space
@@ -236,10 +239,10 @@ int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld,
   return SIM_OK;
 }
 
-template <int BN>
+template <int BN, int NSTAGE>
 int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_split3_kernel<BN>;
+  using Cfg = GemmCfg<BN, NSTAGE>;
+  auto kern = gemm_split3_kernel<BN, NSTAGE>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 attr");
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
@@ -291,15 +294,22 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
               SIM_ERR_ALIGN, "gemm_bf16x3: TMA needs 16-byte aligned bases / strides, the epilogue N and ldd multiples of 4");
   // widest tile that still gives every SM work; the two operand tiles of a stage share one tensor copy each
   const int m_tiles = (M + kBM - 1) / kBM;
-  const int bn = N <= 64 ? 64 : ((N % 256 == 0 && (long)m_tiles * (N / 256) >= 2 * 148) ? 256 : 128);
+  int bn = N <= 64 ? 64 : ((N % 256 == 0 && (long)m_tiles * (N / 256) >= 2 * 148) ? 256 : 128);
+  static const int force = [] { const char* e = getenv("SIM_GEMM_CFG"); return e ? atoi(e) : 0; }();  // bench-only override
+  if (force == 128 || force == 1282) bn = N <= 64 ? 64 : 128;
+  // one or two k-blocks (dt_proj, K = 24): the tile is all prologue + epilogue, so prefer two co-resident CTAs per SM
+  // that overlap each other's phases (measured 21.3 vs 27.3 us)
+  const bool shallow = K <= 2 * kBK && N > 64;
+  if (shallow) bn = 128;
   GemmTmaps tm;
   int rc;
   if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
   if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn))) return rc;
   switch (bn) {
-    case 64: return launch_gemm<64>(tm, Y, ldd, M, N, K, stream);
-    case 128: return launch_gemm<128>(tm, Y, ldd, M, N, K, stream);
-    default: return launch_gemm<256>(tm, Y, ldd, M, N, K, stream);
+    case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream);
+    case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream)
+                                   : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream);
+    default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream);
   }
 }
 
