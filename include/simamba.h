@@ -148,6 +148,37 @@ size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K);
 int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
                     void* workspace, size_t workspace_bytes, sim_stream_t stream);
 
+/* a-5 / a-7 / a-8  spectral permutation from sort keys: stable ascending argsort of an eigenvector column
+ * (sort_points_by_fiedler, models/point_mamba.py:817-826) or of the HLT bucket keys id + u with the caller's
+ * tie-break noise (part_segmentation/models/pt_mamba.py:670-680).  Same contract as sim_argsort_rows. */
+int sim_spectral_perm(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,
+                      sim_stream_t stream);
+
+/* a-16 / a-17  MAE masked sort + token restore (models/point_mamba.py:2734-2796, 3147-3197).
+ * sim_mae_index_maps: perm (B,k,G) i32 + mask (B,G) u8 (1 = masked, G - n_vis masked patches per cloud) -> every map
+ *   of the layout, T = 2kG decoder positions, R_vis = 2k n_vis encoder rows, R_msk = T - R_vis:
+ *     perm_full (B,T) patch behind each position; mask_full (B,T) u8; restore_src (B,T) encoder row of each position
+ *     or -1 (mask token); src_vis (B,R_vis) patch of each encoder row; vis_pos (B,R_vis) position of each encoder row;
+ *     rec_src (B,R_msk) masked positions, ascending; inv_vis (B,G,2k) encoder rows that show patch g (-1 = masked).
+ *   *err_flag (device int, caller zeroes) receives b+1 if cloud b does not have exactly n_vis visible patches.
+ * sim_mae_compact_fwd: x_vis[b,r] = tokens[b, src_vis[b,r]];   _bwd: dtokens[b,g] = sum_j dx_vis[b, inv_vis[b,g,j]].
+ * sim_mae_restore_fwd: x_full[b,t] = restore_src >= 0 ? x_vis[b, restore_src] : mask_token;
+ *   _bwd: dx_vis[b,r] = dx_full[b, vis_pos[b,r]], dmask_token[c] += sum of the masked rows (fp32, caller zeroes). */
+int sim_mae_index_maps(const int32_t* perm, const unsigned char* mask, int B, int k, int G, int n_vis,
+                       int32_t* perm_full, unsigned char* mask_full, int32_t* restore_src, int32_t* src_vis,
+                       int32_t* vis_pos, int32_t* rec_src, int32_t* inv_vis, int32_t* err_flag, sim_stream_t stream);
+int sim_mae_compact_fwd(const void* tokens, const int32_t* src_vis, void* x_vis, int B, int G, int R_vis, int C,
+                        int dtype, sim_stream_t stream);
+int sim_mae_compact_bwd(const void* dx_vis, const int32_t* inv_vis, void* dtokens, int B, int G, int R_vis, int J,
+                        int C, int dtype, sim_stream_t stream);
+int sim_mae_restore_fwd(const void* x_vis, const int32_t* restore_src, const void* mask_token, void* x_full, int B,
+                        int R_vis, int T, int C, int dtype, sim_stream_t stream);
+int sim_mae_restore_bwd(const void* dx_full, const int32_t* vis_pos, const int32_t* restore_src, void* dx_vis,
+                        float* dmask_token, int B, int R_vis, int T, int C, int dtype, sim_stream_t stream);
+/* out[b,r] = sum_j x[b, idx[b,r,j]] over idx >= 0: deterministic backward of any row gather given its inverse map */
+int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int R_in, int R_out, int J, int C,
+                        int dtype, sim_stream_t stream);
+
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
  * elements, row stride ldo); the weights are split once per model, activations by their producer.

@@ -50,6 +50,13 @@ SIGNATURES = {
     "sim_causal_conv1d_fwd_split3": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _i, _i, _i, _i, _i, _p]),
     "sim_selective_scan_fwd_split3": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _l,
                                            _i, _i, _i, _i, _i, _p]),
+    "sim_mae_index_maps": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "sim_mae_compact_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "sim_mae_compact_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_mae_restore_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "sim_mae_restore_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "sim_gather_sum_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_spectral_perm": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
     "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
     "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),
     "sim_gemm_f32_tc": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _sz, _p]),

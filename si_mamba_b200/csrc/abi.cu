@@ -193,6 +193,46 @@ int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y
                           static_cast<cudaStream_t>(stream));
 }
 
+int sim_mae_index_maps(const int32_t* perm, const unsigned char* mask, int B, int k, int G, int n_vis,
+                       int32_t* perm_full, unsigned char* mask_full, int32_t* restore_src, int32_t* src_vis,
+                       int32_t* vis_pos, int32_t* rec_src, int32_t* inv_vis, int32_t* err_flag, sim_stream_t stream) {
+  return sim::mae_index_maps(perm, mask, B, k, G, n_vis, perm_full, mask_full, restore_src, src_vis, vis_pos, rec_src,
+                             inv_vis, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+int sim_mae_compact_fwd(const void* tokens, const int32_t* src_vis, void* x_vis, int B, int G, int R_vis, int C,
+                        int dtype, sim_stream_t stream) {
+  return sim::gather_rows(tokens, src_vis, nullptr, x_vis, B, G, R_vis, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_mae_compact_bwd(const void* dx_vis, const int32_t* inv_vis, void* dtokens, int B, int G, int R_vis, int J,
+                        int C, int dtype, sim_stream_t stream) {
+  return sim::gather_sum_rows(dx_vis, inv_vis, dtokens, B, R_vis, G, J, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_mae_restore_fwd(const void* x_vis, const int32_t* restore_src, const void* mask_token, void* x_full, int B,
+                        int R_vis, int T, int C, int dtype, sim_stream_t stream) {
+  return sim::gather_rows(x_vis, restore_src, mask_token, x_full, B, R_vis, T, C, dtype,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int sim_mae_restore_bwd(const void* dx_full, const int32_t* vis_pos, const int32_t* restore_src, void* dx_vis,
+                        float* dmask_token, int B, int R_vis, int T, int C, int dtype, sim_stream_t stream) {
+  int rc = sim::gather_rows(dx_full, vis_pos, nullptr, dx_vis, B, T, R_vis, C, dtype, static_cast<cudaStream_t>(stream));
+  if (rc || !dmask_token) return rc;
+  return sim::masked_colsum(dx_full, restore_src, (long)B * T, C, dmask_token, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int R_in, int R_out, int J, int C,
+                        int dtype, sim_stream_t stream) {
+  return sim::gather_sum_rows(x, idx, out, B, R_in, R_out, J, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_spectral_perm(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,
+                      sim_stream_t stream) {
+  return sim::argsort_rows(keys, ld, es, rows, n, perm, inv_perm, static_cast<cudaStream_t>(stream));
+}
+
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
   return sim::split3_bf16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
 }

@@ -91,6 +91,12 @@ size_t gemm_f32_tc_workspace_bytes(int M, int N, int K);
 int gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int mae_index_maps(const int* perm, const unsigned char* mask, int B, int k, int G, int n_vis, int* perm_full,
+                   unsigned char* mask_full, int* restore_src, int* src_vis, int* vis_pos, int* rec_src, int* inv_vis,
+                   int* err_flag, cudaStream_t stream);
+int gather_sum_rows(const void* x, const int* idx, void* out, int B, int R_in, int R_out, int J, int C, int dtype,
+                    cudaStream_t stream);
+int masked_colsum(const void* x, const int* sel, long rows, int C, float* dfill, int dtype, cudaStream_t stream);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream);

@@ -12,7 +12,19 @@ import torch
 from . import ops
 
 
-def mae_index_maps(perm: torch.Tensor, mask: torch.Tensor):
+def mae_index_maps(perm: torch.Tensor, mask: torch.Tensor, n_vis: int = None, check: bool = False):
+    """Index maps of the MAE layout from ONE kernel (ops.mae_index_maps / sim_mae_index_maps); see
+    mae_index_maps_torch for the meaning of every map (kept as the in-tree description and for CPU use).
+    ``n_vis`` = visible patches per cloud (G - int(mask_ratio * G)); None counts them from the mask (host sync)."""
+    if not perm.is_cuda:
+        return mae_index_maps_torch(perm, mask)
+    if n_vis is None:
+        n_vis = int((~mask[0]).sum())
+        check = True
+    return ops.mae_index_maps(perm, mask, n_vis, check=check)
+
+
+def mae_index_maps_torch(perm: torch.Tensor, mask: torch.Tensor):
     """perm (B,k,G) int, mask (B,G) bool with the same number of masked patches in every cloud ->
     dict(src_vis (B, 2k*n_vis) patch feeding each encoder token,
          restore_src (B, 2kG) row of the encoder output for each decoder position, -1 = mask token,

@@ -79,15 +79,24 @@ class MaskMamba_2(nn.Module):
         """-> (x_vis (B, 2k*n_vis, C), maps) with ``maps`` the index maps of layout.mae_index_maps."""
         if not reverse:
             raise NotImplementedError("the MAE path is only defined for reverse=True (point_mamba.py:2778-2796)")
+        user_mask = bool_masked_pos is not None
         if bool_masked_pos is None:
             if self.mask_type != 'rand':
                 raise NotImplementedError("mask_type 'block' is not used by cfgs/pretrain.yaml")
             bool_masked_pos = self._mask_center_rand(center, noaug=noaug)
         tokens = self.encoder(neighborhood)
         pos = self.pos_embed(center)
-        maps = layout.mae_index_maps(perm, bool_masked_pos)
-        x_vis = layout.gather_rows(tokens, maps["src_vis"])
-        pos_vis = layout.gather_rows(pos, maps["src_vis"])
+        G = center.shape[1]
+        if user_mask:
+            n_vis = None  # counted from the caller's mask (host sync + validation)
+        elif noaug or self.mask_ratio == 0:
+            n_vis = G
+        else:
+            n_vis = G - int(self.mask_ratio * G)
+        maps = layout.mae_index_maps(perm, bool_masked_pos, n_vis)
+        # masked sort = row compaction through the index maps (sim_mae_compact_fwd / _bwd)
+        x_vis = ops.MaeCompact.apply(tokens, maps["src_vis"], maps["inv_vis"])
+        pos_vis = ops.MaeCompact.apply(pos, maps["src_vis"], maps["inv_vis"])
         x_vis = self.norm(self.blocks(x_vis, pos_vis))
         maps["pos"] = pos
         return x_vis, maps
@@ -169,7 +178,7 @@ class Point_MAE_Mamba(nn.Module):
             return x_vis
         B, _, C = x_vis.shape
         # token restore: decoder position t shows the mask token or the encoder row with the same visible rank
-        x_full = layout.gather_rows(x_vis, maps["restore_src"], fill=self.mask_token.reshape(-1))
+        x_full = ops.MaeRestore.apply(x_vis, self.mask_token, maps["restore_src"], maps["vis_pos"])
         pos_full = layout.gather_rows(maps["pos"], maps["perm_full"])
         x_rec = self.MAE_decoder(x_full, pos_full, None)
         x_rec = layout.gather_rows(x_rec, maps["rec_src"])                       # (B, 2k*m, C) masked positions

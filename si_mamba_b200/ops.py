@@ -205,6 +205,86 @@ def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Ten
     return out
 
 
+# ----------------------------------------------------------------------------- MAE layout (a-16 / a-17)
+def mae_index_maps(perm: torch.Tensor, mask: torch.Tensor, n_vis: int, check: bool = False) -> dict:
+    """perm (B,k,G) int32, mask (B,G) bool with G - n_vis masked patches per cloud -> the index maps of the masked
+    spectral sort and the token restore (include/simamba.h, sim_mae_index_maps), one kernel, no host sync unless
+    ``check`` (which raises if a cloud's visible count differs from n_vis)."""
+    _cuda(perm, mask)
+    B, k, G = perm.shape
+    T, RV = 2 * k * G, 2 * k * n_vis
+    dev, i32 = perm.device, torch.int32
+    perm = perm.to(i32).contiguous()
+    m8 = mask.to(torch.uint8).contiguous()
+    out = dict(perm_full=torch.empty(B, T, dtype=i32, device=dev), mask_full=torch.empty(B, T, dtype=torch.uint8, device=dev),
+               restore_src=torch.empty(B, T, dtype=i32, device=dev), inv_vis=torch.empty(B, G, 2 * k, dtype=i32, device=dev))
+    base = {}
+    for name, n in (("src_vis", RV), ("vis_pos", RV), ("rec_src", T - RV)):  # never hand the ABI a null (empty) buffer
+        base[name] = torch.empty(B * n + 1, dtype=i32, device=dev)
+        out[name] = base[name][:B * n].view(B, n)
+    err = torch.zeros(1, dtype=i32, device=dev)
+    _lib.call("sim_mae_index_maps", _p(perm), _p(m8), B, k, G, n_vis, _p(out["perm_full"]), _p(out["mask_full"]),
+              _p(out["restore_src"]), _p(base["src_vis"]), _p(base["vis_pos"]), _p(base["rec_src"]), _p(out["inv_vis"]),
+              _p(err), _stream())
+    if check and int(err.item()) != 0:
+        raise ValueError(f"mae_index_maps: cloud {int(err.item()) - 1} does not have {n_vis} visible patches")
+    out["mask_full"] = out["mask_full"].bool()
+    return out
+
+
+class MaeCompact(torch.autograd.Function):
+    """x_vis[b,r] = tokens[b, src_vis[b,r]] (sim_mae_compact_fwd / _bwd: the backward is a gather over inv_vis)."""
+
+    @staticmethod
+    def forward(ctx, tokens, src_vis, inv_vis):
+        tokens = tokens.contiguous()
+        B, G, C = tokens.shape
+        R = src_vis.shape[1]
+        out = torch.empty(B, R, C, dtype=tokens.dtype, device=tokens.device)
+        _lib.call("sim_mae_compact_fwd", _p(tokens), _p(src_vis), _p(out), B, G, R, C, _dt(tokens), _stream())
+        ctx.save_for_backward(inv_vis)
+        ctx.G = G
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (inv_vis,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, R, C = dout.shape
+        dx = torch.empty(B, ctx.G, C, dtype=dout.dtype, device=dout.device)
+        _lib.call("sim_mae_compact_bwd", _p(dout), _p(inv_vis), _p(dx), B, ctx.G, R, inv_vis.shape[2], C, _dt(dout),
+                  _stream())
+        return dx, None, None
+
+
+class MaeRestore(torch.autograd.Function):
+    """x_full[b,t] = restore_src >= 0 ? x_vis[b, restore_src[b,t]] : mask_token (sim_mae_restore_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x_vis, mask_token, restore_src, vis_pos):
+        x_vis = x_vis.contiguous()
+        B, R, C = x_vis.shape
+        T = restore_src.shape[1]
+        fill = mask_token.reshape(-1).to(x_vis.dtype).contiguous()
+        out = torch.empty(B, T, C, dtype=x_vis.dtype, device=x_vis.device)
+        _lib.call("sim_mae_restore_fwd", _p(x_vis), _p(restore_src), _p(fill), _p(out), B, R, T, C, _dt(x_vis), _stream())
+        ctx.save_for_backward(restore_src, vis_pos)
+        ctx.token_shape, ctx.token_dtype = mask_token.shape, mask_token.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        restore_src, vis_pos = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, T, C = dout.shape
+        R = vis_pos.shape[1]
+        dx = torch.empty(B, R, C, dtype=dout.dtype, device=dout.device)
+        dtok = torch.zeros(C, dtype=torch.float32, device=dout.device)
+        _lib.call("sim_mae_restore_bwd", _p(dout), _p(vis_pos), _p(restore_src), _p(dx), _p(dtok), B, R, T, C, _dt(dout),
+                  _stream())
+        return dx, dtok.to(ctx.token_dtype).reshape(ctx.token_shape), None, None
+
+
 # ----------------------------------------------------------------------------- add + LayerNorm (a-9)
 def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
                   eps: float = 1e-5, x2: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,

@@ -119,3 +119,46 @@ def test_part_seg_forward_vs_oracle(lib, method):
         ref, _ = oseg.seg_forward(sd, dict(cfg), pts, lab, noise, perm_override=perm)
         err = (out.cpu() - ref).abs().max() / ref.abs().max()
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("B,k,G,m", [(3, 4, 64, 38), (2, 2, 128, 76), (1, 4, 32, 0), (2, 3, 40, 39)])
+def test_mae_index_maps_and_row_kernels(B, k, G, m):
+    """sim_mae_index_maps against the torch restatement of the layout (layout.mae_index_maps_torch) bit for bit, and
+    the compact / restore row kernels' backward against autograd through torch indexing."""
+    from si_mamba_b200 import layout, ops
+    g = torch.Generator().manual_seed(B * 100 + G)
+    perm = torch.stack([torch.stack([torch.randperm(G, generator=g) for _ in range(k)]) for _ in range(B)]).int()
+    mask = torch.zeros(B, G, dtype=torch.bool)
+    for b in range(B):
+        mask[b, torch.randperm(G, generator=g)[:m]] = True
+    ref = layout.mae_index_maps_torch(perm, mask)
+    got = ops.mae_index_maps(perm.cuda(), mask.cuda(), G - m, check=True)
+    for key in ("perm_full", "mask_full", "restore_src", "src_vis", "rec_src"):
+        assert torch.equal(got[key].cpu(), ref[key]), key
+    T, RV, C = 2 * k * G, 2 * k * (G - m), 32
+    # vis_pos / inv_vis are the inverse maps: position of every encoder row, rows showing every patch
+    assert torch.equal(torch.gather(got["restore_src"], 1, got["vis_pos"].long()).cpu(), torch.arange(RV).expand(B, RV).int())
+    inv = got["inv_vis"].cpu()
+    for b in range(B):
+        for p in range(G):
+            rows = sorted(r for r in inv[b, p].tolist() if r >= 0)
+            assert rows == sorted(torch.nonzero(ref["src_vis"][b] == p).flatten().tolist())
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.mae_index_maps(perm.cuda(), mask.cuda(), G - m + 1, check=True)
+    # row kernels forward + backward vs torch indexing
+    tokens = torch.randn(B, G, C, generator=g).cuda().requires_grad_()
+    mtok = torch.randn(1, 1, C, generator=g).cuda().requires_grad_()
+    x_vis = ops.MaeCompact.apply(tokens, got["src_vis"], got["inv_vis"])
+    x_full = ops.MaeRestore.apply(x_vis, mtok, got["restore_src"], got["vis_pos"])
+    wgt = torch.randn(B, T, C, generator=g).cuda()
+    (x_full * wgt).sum().backward()
+    t2 = tokens.detach().clone().requires_grad_()
+    m2 = mtok.detach().clone().requires_grad_()
+    xv2 = torch.gather(t2, 1, ref["src_vis"].cuda().long()[..., None].expand(-1, -1, C))
+    rs = ref["restore_src"].cuda().long()
+    xf2 = torch.where((rs >= 0)[..., None], torch.gather(xv2, 1, rs.clamp(min=0)[..., None].expand(-1, -1, C)) if RV else m2.expand(B, T, C),
+                      m2.expand(B, T, C))
+    (xf2 * wgt).sum().backward()
+    assert torch.equal(x_full, xf2)
+    assert torch.allclose(tokens.grad, t2.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(mtok.grad, m2.grad, rtol=1e-4, atol=1e-4)
