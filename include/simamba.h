@@ -179,6 +179,22 @@ int sim_mae_restore_bwd(const void* dx_full, const int32_t* vis_pos, const int32
 int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int R_in, int R_out, int J, int C,
                         int dtype, sim_stream_t stream);
 
+/* f-1  data-prep farthest-point sampling with pointnet2_ops semantics, as the runners call it right before the model
+ * (utils/misc.py:14-21 fps(data, number); tools/runner_finetune.py:177-194): furthest_point_sample + gather_operation
+ * in one kernel.  Start index 0, running minima initialised to 1e10, points with |p|^2 <= 1e-3 never visited,
+ * FMA-contracted distance, upstream tie rule (lowest upstream thread, then lowest index).  xyz (B,N,3) ->
+ * idx (B,npoint) i32, sampled (B,npoint,3). */
+int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, float* sampled, sim_stream_t stream);
+
+/* a-18  Chamfer-L2 of R pairs of small point sets, x (R,P,3), y (R,Q,3) fp32, P, Q <= 256:
+ * loss[r] = mean_i min_j |x_i - y_j|^2 + mean_j min_i |x_i - y_j|^2  (pytorch3d chamfer_distance(x, y,
+ * batch_reduction=None)[0], models/point_mamba.py:2950, 3199-3213).  idx_x (R,P) / idx_y (R,Q) receive the arg-mins
+ * (lowest index on ties) that sim_chamfer_l2_bwd differentiates through; dx or dy may be NULL. */
+int sim_chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* loss, int32_t* idx_x,
+                       int32_t* idx_y, sim_stream_t stream);
+int sim_chamfer_l2_bwd(const float* x, const float* y, const int32_t* idx_x, const int32_t* idx_y, const float* gloss,
+                       long R, int P, int Q, float* dx, float* dy, sim_stream_t stream);
+
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
  * elements, row stride ldo); the weights are split once per model, activations by their producer.

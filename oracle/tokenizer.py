@@ -111,3 +111,40 @@ def synthetic_clouds(B: int, N: int, seed: int, kind: str = "ball") -> torch.Ten
     m = pts.norm(dim=-1).max(dim=1).values
     pts = pts / m[:, None, None]
     return pts.contiguous().float()
+
+
+def fps_pointnet2(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """pointnet2_ops ``furthest_point_sample`` (un-vendored git dependency, README.md:49; call sites utils/misc.py:19,
+    tools/runner_finetune.py:191-193) restated from its published CUDA kernel: idx[0] = 0; temp = 1e10; per step, for
+    every point k with |p_k|^2 > 1e-3: d = dx*dx + dy*dy + dz*dz (FMA-contracted, emulated in fp64 -> fp32),
+    temp[k] = min(temp[k], d); the next index is the arg-max of temp over the visited points, where each of the
+    bs = min(512, 2^floor(log2 N)) upstream threads keeps its first strict maximum over k = tid, tid + bs, ... and the
+    tree reduction keeps the lower thread on ties.  xyz (B,N,3) fp32 -> (B,npoint) int64.  Pure loops: small cases only."""
+    import numpy as np
+    B, N, _ = xyz.shape
+    bs = 1
+    while bs * 2 <= N and bs < 512:
+        bs *= 2
+    out = torch.zeros(B, npoint, dtype=torch.int64)
+    f32 = np.float32
+    for b in range(B):
+        p = xyz[b].numpy().astype(np.float64)
+        fma = lambda a, c: (a * a + c).astype(f32).astype(np.float64)  # round(a*a + c) to fp32
+        mag = fma(p[:, 2], fma(p[:, 1], (p[:, 0] * p[:, 0]).astype(f32).astype(np.float64)))
+        ok = mag > 1e-3
+        temp = np.full(N, 1e10, dtype=np.float64)
+        key = (np.arange(N) % bs) * 64 + np.arange(N) // bs
+        old = 0
+        for j in range(1, npoint):
+            d = p - p[old]
+            dist = fma(d[:, 2], fma(d[:, 1], (d[:, 0] * d[:, 0]).astype(f32).astype(np.float64)))
+            temp = np.where(ok, np.minimum(temp, dist), temp)
+            cand = np.where(ok, temp, -1.0)
+            best = cand.max()
+            if best < 0:
+                old = 0
+            else:
+                ties = np.nonzero(cand == best)[0]
+                old = int(ties[np.argmin(key[ties])])
+            out[b, j] = old
+    return out

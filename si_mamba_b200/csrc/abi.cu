@@ -233,6 +233,20 @@ int sim_spectral_perm(const float* keys, long ld, long es, int rows, int n, int3
   return sim::argsort_rows(keys, ld, es, rows, n, perm, inv_perm, static_cast<cudaStream_t>(stream));
 }
 
+int sim_chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* loss, int32_t* idx_x,
+                       int32_t* idx_y, sim_stream_t stream) {
+  return sim::chamfer_l2_fwd(x, y, R, P, Q, loss, idx_x, idx_y, static_cast<cudaStream_t>(stream));
+}
+
+int sim_chamfer_l2_bwd(const float* x, const float* y, const int32_t* idx_x, const int32_t* idx_y, const float* gloss,
+                       long R, int P, int Q, float* dx, float* dy, sim_stream_t stream) {
+  return sim::chamfer_l2_bwd(x, y, idx_x, idx_y, gloss, R, P, Q, dx, dy, static_cast<cudaStream_t>(stream));
+}
+
+int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, float* sampled, sim_stream_t stream) {
+  return sim::fps(xyz, B, N, npoint, idx, sampled, static_cast<cudaStream_t>(stream), 1);
+}
+
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
   return sim::split3_bf16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
 }

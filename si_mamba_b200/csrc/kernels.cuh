@@ -6,7 +6,7 @@
 namespace sim {
 
 // implemented in the kernel translation units
-int fps(const float*, int, int, int, int*, float*, cudaStream_t);
+int fps(const float*, int, int, int, int*, float*, cudaStream_t, int pointnet2 = 0);
 int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t);
 int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
                   int, int, cudaStream_t, void* planes = nullptr, long plane = 0);
@@ -97,6 +97,10 @@ int mae_index_maps(const int* perm, const unsigned char* mask, int B, int k, int
 int gather_sum_rows(const void* x, const int* idx, void* out, int B, int R_in, int R_out, int J, int C, int dtype,
                     cudaStream_t stream);
 int masked_colsum(const void* x, const int* sel, long rows, int C, float* dfill, int dtype, cudaStream_t stream);
+int chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* loss, int* idx_x, int* idx_y,
+                   cudaStream_t stream);
+int chamfer_l2_bwd(const float* x, const float* y, const int* idx_x, const int* idx_y, const float* gloss, long R, int P,
+                   int Q, float* dx, float* dy, cudaStream_t stream);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream);

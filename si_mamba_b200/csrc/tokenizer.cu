@@ -24,9 +24,14 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
 }
 
 // ----------------------------------------------------------------------------- FPS
-template <int NT, int PPT>
+// PN2 = false: pytorch3d semantics (Group.forward).  PN2 = true: pointnet2_ops furthest_point_sample as the runners
+// call it right before the model (utils/misc.py:14-21, tools/runner_finetune.py:177-194): running
+// minima start at 1e10, points with |p|^2 <= 1e-3 are never visited, the distance is the FMA-contracted
+// dx*dx + dy*dy + dz*dz of the upstream .cu, and ties go to the candidate of the lowest upstream thread
+// (index mod bs_up, bs_up = upstream block size) and then the lowest index - `key` below orders exactly that way.
+template <int NT, int PPT, bool PN2>
 __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, int N, int G, int* __restrict__ idx,
-                                                 float* __restrict__ center) {
+                                                 float* __restrict__ center, int bs_up) {
   extern __shared__ float s_xyz[];  // N*3
   constexpr int NW = NT / 32;
   __shared__ unsigned s_bits[2][NW];
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, 
     const int i = tid + j * NT;
     if (i < N) {
       px[j] = s_xyz[3 * i], py[j] = s_xyz[3 * i + 1], pz[j] = s_xyz[3 * i + 2];
-      md[j] = __int_as_float(0x7f800000);  // +inf
+      md[j] = PN2 ? 1e10f : __int_as_float(0x7f800000);  // +inf
     } else {
       px[j] = py[j] = pz[j] = 0.f;
       md[j] = 0.f;  // padding can never beat a real point (index tie-break)
@@ -63,12 +68,25 @@ __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, 
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       const int i = tid + j * NT;
-      const float d = sqdist3(px[j], py[j], pz[j], wx, wy, wz);
-      md[j] = fminf(md[j], d);
-      const unsigned bits = __float_as_uint(md[j]);
-      if (i < N && (best_idx == 0xffffffffu || bits > best_bits)) {  // strict >: keeps the lowest own index
-        best_bits = bits;
-        best_idx = (unsigned)i;
+      if constexpr (PN2) {
+        const float mag = fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j]));
+        if (i >= N || mag <= 1e-3f) continue;
+        const float dx = px[j] - wx, dy = py[j] - wy, dz = pz[j] - wz;
+        md[j] = fminf(md[j], fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        const unsigned bits = __float_as_uint(md[j]);
+        const unsigned key = (unsigned)(i % bs_up) * 64u + (unsigned)(i / bs_up);
+        if (best_idx == 0xffffffffu || bits > best_bits || (bits == best_bits && key < best_idx)) {
+          best_bits = bits;
+          best_idx = key;
+        }
+      } else {
+        const float d = sqdist3(px[j], py[j], pz[j], wx, wy, wz);
+        md[j] = fminf(md[j], d);
+        const unsigned bits = __float_as_uint(md[j]);
+        if (i < N && (best_idx == 0xffffffffu || bits > best_bits)) {  // strict >: keeps the lowest own index
+          best_bits = bits;
+          best_idx = (unsigned)i;
+        }
       }
     }
     // warp arg-max on (bits desc, idx asc)
@@ -86,19 +104,29 @@ __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, 
     m = __reduce_max_sync(0xffffffffu, wb);
     cand = (wb == m) ? wi : 0xffffffffu;
     last = __reduce_min_sync(0xffffffffu, cand);
+    if constexpr (PN2) last = last == 0xffffffffu ? 0u : (last % 64u) * (unsigned)bs_up + last / 64u;  // key -> index
   }
 }
 
-int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStream_t stream) {
+int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStream_t stream, int pointnet2) {
   SIM_REQUIRE(B > 0 && N > 0 && G > 0 && G <= N, SIM_ERR_INVALID, "fps: need 0 < G <= N (G=%d N=%d)", G, N);
   SIM_REQUIRE(xyz && idx && center, SIM_ERR_INVALID, "fps: null tensor");
   const size_t smem = (size_t)N * 3 * sizeof(float);
+  int bs_up = 1;  // pointnet2_ops opt_n_threads: largest power of two <= N, at most 512
+  while (bs_up * 2 <= N && bs_up < 512) bs_up *= 2;
 #define SIM_FPS_LAUNCH(NT, PPT)                                                                         \
   do {                                                                                                  \
-    auto kern = fps_kernel<NT, PPT>;                                                                    \
-    static SmemAttrCache attr; /* per device, grow-only, set by the first (warm-up) call */               \
-    if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                     \
-    kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center);                                              \
+    if (pointnet2) {                                                                                    \
+      auto kern = fps_kernel<NT, PPT, true>;                                                            \
+      static SmemAttrCache attr; /* per device, grow-only, set by the first (warm-up) call */             \
+      if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                   \
+      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up);                                     \
+    } else {                                                                                            \
+      auto kern = fps_kernel<NT, PPT, false>;                                                           \
+      static SmemAttrCache attr;                                                                        \
+      if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                   \
+      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up);                                     \
+    }                                                                                                   \
   } while (0)
   if (N <= 512)
     SIM_FPS_LAUNCH(128, 4);

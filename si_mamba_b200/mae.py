@@ -21,7 +21,10 @@ from .point_mamba import Encoder, Group, MixerModel
 
 def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """pytorch3d ``chamfer_distance(x, y, batch_reduction=None)[0]`` with squared L2 and point_reduction="mean"
-    (models/point_mamba.py:2950, 3203): (N,P,3), (N,Q,3) -> (N,).  Stays PyTorch."""
+    (models/point_mamba.py:2950, 3203): (N,P,3), (N,Q,3) -> (N,).  One warp per pair on the device
+    (csrc/chamfer.cu, sim_chamfer_l2_fwd / _bwd); plain torch only for CPU tensors or sets above 256 points."""
+    if x.is_cuda and x.shape[1] <= 256 and y.shape[1] <= 256:
+        return ops.chamfer_l2(x, y)
     d = (x[:, :, None, :] - y[:, None, :, :]).pow(2).sum(-1)
     return d.min(dim=2).values.mean(dim=1) + d.min(dim=1).values.mean(dim=1)
 

@@ -75,6 +75,18 @@ def fps(xyz: torch.Tensor, num_group: int):
     return center, idx
 
 
+def fps_pointnet2(data: torch.Tensor, number: int, return_idx: bool = False):
+    """utils/misc.py:14-21 ``fps(data, number)``: pointnet2_ops furthest_point_sample + gather_operation, data (B,N,3)
+    -> (B,number,3) (and the int32 indices).  One kernel (sim_fps_pointnet2)."""
+    _cuda(data)
+    x = data.float().contiguous()
+    B, N, _ = x.shape
+    idx = torch.empty(B, number, dtype=torch.int32, device=x.device)
+    out = torch.empty(B, number, 3, dtype=torch.float32, device=x.device)
+    _lib.call("sim_fps_pointnet2", _p(x), B, N, number, _p(idx), _p(out), _stream())
+    return (out, idx) if return_idx else out
+
+
 def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, want_org: bool = True):
     """-> (idx (B,G,M) int32 ascending, neighborhood centred, neighborhood_org).  point_mamba.py:96-110."""
     _cuda(xyz, center)
@@ -203,6 +215,42 @@ def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Ten
     f = None if fill is None else fill.to(x.dtype).contiguous()
     _lib.call("sim_gather_rows", _p(x), _p(src_idx), _p(f), _p(out), B, R_in, R_out, Cc, _dt(x), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- Chamfer-L2 (a-18)
+class ChamferL2(torch.autograd.Function):
+    """(R,P,3), (R,Q,3) fp32 -> (R,) pytorch3d chamfer_distance(..., batch_reduction=None)[0] (squared L2, mean over
+    points); backward through the recorded arg-mins (sim_chamfer_l2_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _cuda(x, y)
+        x, y = x.float().contiguous(), y.float().contiguous()
+        R, P, _ = x.shape
+        Q = y.shape[1]
+        loss = torch.empty(R, dtype=torch.float32, device=x.device)
+        ix = torch.empty(R, P, dtype=torch.int32, device=x.device)
+        iy = torch.empty(R, Q, dtype=torch.int32, device=x.device)
+        _lib.call("sim_chamfer_l2_fwd", _p(x), _p(y), R, P, Q, _p(loss), _p(ix), _p(iy), _stream())
+        ctx.save_for_backward(x, y, ix, iy)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x, y, ix, iy = ctx.saved_tensors
+        R, P, _ = x.shape
+        Q = y.shape[1]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if dx is None and dy is None:
+            return None, None
+        _lib.call("sim_chamfer_l2_bwd", _p(x), _p(y), _p(ix), _p(iy), _p(gloss.float().contiguous()), R, P, Q, _p(dx),
+                  _p(dy), _stream())
+        return dx, dy
+
+
+def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return ChamferL2.apply(x, y)
 
 
 # ----------------------------------------------------------------------------- MAE layout (a-16 / a-17)

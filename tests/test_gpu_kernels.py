@@ -408,3 +408,18 @@ def test_split3_producers(ops):
     out = ops.selective_scan_tm(*args)
     outs = ops.selective_scan_tm(*args, split=True)
     assert torch.equal(outs.planes.float().sum(0).view(B, L, D), out)
+
+
+@pytest.mark.parametrize("B,N,npoint,kind", [(2, 1024, 128, "surface"), (1, 8192, 300, "ball"), (3, 700, 64, "dup")])
+def test_fps_pointnet2_vs_oracle(ops, B, N, npoint, kind):
+    """Data-prep FPS (pointnet2_ops semantics): indices bit-exact vs the CPU restatement, incl. points
+    near the origin (never visited) and duplicated points (upstream thread-order tie rule)."""
+    xyz = tokenizer.synthetic_clouds(B, N, 77 + N, "surface" if kind != "ball" else "ball")
+    xyz[:, 5] = 0.0           # |p|^2 <= 1e-3: skipped by the upstream kernel
+    xyz[:, 9] = 0.01
+    if kind == "dup":
+        xyz[:, N // 2:] = xyz[:, :N - N // 2]  # exact duplicates -> ties at every step
+    ref = tokenizer.fps_pointnet2(xyz, npoint)
+    out, idx = ops.fps_pointnet2(dev(xyz), npoint, return_idx=True)
+    assert torch.equal(idx.cpu().long(), ref)
+    assert torch.equal(out.cpu(), torch.gather(xyz, 1, ref[..., None].expand(-1, -1, 3)))

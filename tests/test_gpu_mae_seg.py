@@ -162,3 +162,24 @@ def test_mae_index_maps_and_row_kernels(B, k, G, m):
     assert torch.equal(x_full, xf2)
     assert torch.allclose(tokens.grad, t2.grad, rtol=1e-5, atol=1e-5)
     assert torch.allclose(mtok.grad, m2.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("R,P,Q", [(4864, 32, 32), (5, 7, 50), (1, 256, 33)])
+def test_chamfer_l2_vs_oracle(R, P, Q):
+    """sim_chamfer_l2 forward and backward vs the torch restatement of pytorch3d's chamfer_distance (oracle/mae.py)."""
+    from si_mamba_b200 import ops
+    g = torch.Generator().manual_seed(R + P)
+    x = torch.randn(R, P, 3, generator=g)
+    y = torch.randn(R, Q, 3, generator=g)
+    if R > 2:
+        y[1, :min(P, Q)] = x[1, :min(P, Q)]  # exact zeros and ties
+    xr, yr = x.clone().requires_grad_(), y.clone().requires_grad_()
+    ref = omae.chamfer_l2(xr, yr)
+    w = torch.randn(R, generator=g)
+    (ref * w).sum().backward()
+    xc, yc = x.cuda().requires_grad_(), y.cuda().requires_grad_()
+    got = ops.chamfer_l2(xc, yc)
+    (got * w.cuda()).sum().backward()
+    assert torch.allclose(got.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(yc.grad.cpu(), yr.grad, rtol=1e-4, atol=1e-6)
