@@ -8,9 +8,11 @@
 // No (B, D, L, N) state tensor is stored: the training forward keeps only the state at the start of every
 // kScanTile-step tile (ScanParams::ckpt, one fp32 tensor the size of an activation).  Per tile, walking the
 // sequence backwards, this kernel (1) recomputes h_t forward from the checkpoint into shared memory and y_t on the
-// fly, (2) runs the adjoint recurrence dh_{t-1} = a_t dh_t in reverse.  Thread = one channel x all 16 states, so
-// every reduction over states is thread-local; dB / dC (reductions over channels) go through a transposed warp
-// butterfly (32 values over 32 lanes) and one shared + one global fp32 atomic per (t, n) per CTA.
+// fly, (2) runs the adjoint recurrence dh_{t-1} = a_t dh_t in reverse.  Thread = one channel x 8 of the 16 states
+// (two lanes per channel: reductions over states are thread-local plus one shuffle); dB / dC (reductions over
+// channels) go through a transposed warp butterfly (16 values over the warp's 16 channels) and one shared + one
+// global fp32 atomic per (t, n) per CTA.  (r01 first version: one thread per channel x 16 states, one warp per
+// CTA, 5 warps per SM: 1742 us at the C2 layer shape.)
 // Operand tiles arrive by TMA tensor copies exactly as in the forward kernel.
 //
 // Roofline class: SM issue (about 25 instructions per state update); HBM algorithmic bytes are
@@ -43,27 +45,40 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
                      __uint_as_float(r.y & 0xffff0000u));
 }
 
+// Thread = (channel, 8 of the 16 states): two lanes per channel (LPC = 2), 16 channels per warp.
+//
+// State history without a (step x state) buffer.  The first cut kept every h_t of a 16-step tile in shared memory
+// (32 KB per two warps): 6 warps per SM, ncu: 1.3 warps per scheduler, issue 30 %, 1.29 ms at the C2 layer shape.  Now a
+// tile is walked as four 4-step sub-tiles, back to front: a forward sweep over steps 0..11 leaves the sub-tile start
+// states h_4, h_8, h_12 in shared memory (96 B per thread), then each sub-tile is recomputed into REGISTERS (4 x 8
+// states) and its adjoint steps run straight from them.  2.5 instead of 2 exps per state-step, no history traffic,
+// and the CTA's shared memory drops to the operand tiles, so 3x more warps are resident.
+constexpr int SUB = 4;  // steps per sub-tile
+
 template <typename T, int CH_>
 struct BwdCfg {
   static constexpr int CH = CH_;
-  static constexpr int NT = CH_;  // one thread per channel
+  static constexpr int S = 8;          // states per thread
+  static constexpr int NT = 2 * CH_;   // threads per CTA
+  static constexpr int NW = NT / 32;
   static constexpr int NS = 2;
   static constexpr int RAW_MAIN = TT * CH_ * (int)sizeof(T);
   static constexpr int RAW_BC = TT * kN * (int)sizeof(T);
   static constexpr int RAW_STAGE = 4 * RAW_MAIN + 2 * RAW_BC;  // u, delta, z, dout, B, C
   static constexpr int OUT = 3 * RAW_MAIN;                      // du, ddelta, dz
-  static constexpr int WORK = 7 * TT * CH_ * 4                  // dt, u, sg, dy, dzc, y, (spare)
+  static constexpr int WORK = 6 * TT * CH_ * 4                  // dt, u, sg, dy, dzc, y
                               + 2 * TT * kN * 4                 // B, C fp32
-                              + 2 * TT * kN * 4;                // dB, dC tile accumulators
-  static constexpr int HBUF = TT * CH_ * kN * 4;
-  static constexpr int SMEM = NS * RAW_STAGE + OUT + WORK + HBUF + NS * 8 + 64;
+                              + NW * TT * 2 * kN * 4;           // per-warp dB | dC tile sums
+  static constexpr int SCK = (TT / SUB - 1) * 2 * NT * 16;      // sub-tile start states, float4 planes
+  static constexpr int SMEM = NS * RAW_STAGE + OUT + WORK + SCK + NS * 8 + 64;
   static_assert(RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0, "TMA tiles must stay 128-B aligned");
+  static_assert(TT % SUB == 0, "whole sub-tiles");
 };
 
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __grid_constant__ BwdTmaps tm,
                                                                      const ScanBwdParams p) {
-  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS;
+  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* raw = smem;
   T* __restrict__ o_du = reinterpret_cast<T*>(smem + NS * Cfg::RAW_STAGE);
@@ -75,19 +90,18 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   float* __restrict__ w_dy = w_sg + TT * CH;
   float* __restrict__ w_dzc = w_dy + TT * CH;
   float* __restrict__ w_y = w_dzc + TT * CH;
-  float* __restrict__ w_sp = w_y + TT * CH;
-  float* __restrict__ w_B = w_sp + TT * CH;
+  float* __restrict__ w_B = w_y + TT * CH;
   float* __restrict__ w_C = w_B + TT * kN;
-  float* __restrict__ a_dB = w_C + TT * kN;
-  float* __restrict__ a_dC = a_dB + TT * kN;
-  float* __restrict__ hbuf = a_dC + TT * kN;  // [t][c][n]
-  uint64_t* full = reinterpret_cast<uint64_t*>(hbuf + TT * CH * kN);
+  float* __restrict__ a_dBC = w_C + TT * kN;                                  // [warp][t][dB(16) | dC(16)]
+  float4* __restrict__ sck = reinterpret_cast<float4*>(a_dBC + NW * TT * 2 * kN);  // [sub-1][half][thread]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sck + (TT / SUB - 1) * 2 * NT);
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunk = p.D / CH;
   const int b = blockIdx.x / nchunk;
   const int c0 = (blockIdx.x % nchunk) * CH;
-  const int c = tid;
+  const int sub = tid & 1;   // which half of the 16 states
+  const int c = tid >> 1;    // channel within the CTA
   const int ntiles = (p.L + TT - 1) / TT;
   const bool has_z = p.z != nullptr;
 
@@ -113,17 +127,44 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     for (int k = 0; k < NS && k < ntiles; ++k) issue_tile(k);
   }
 
-  float A[kN], A2[kN], dA[kN], dh[kN];
+  float A[S], A2[S], dA[S], dh[S];
 #pragma unroll
-  for (int n = 0; n < kN; ++n) {
-    A[n] = p.A[(long)(c0 + c) * kN + n];
+  for (int n = 0; n < S; ++n) {
+    A[n] = p.A[(long)(c0 + c) * kN + sub * S + n];
     A2[n] = A[n] * kLog2e;
     dA[n] = 0.f;
     dh[n] = 0.f;
   }
   const float Dc = p.Dv ? p.Dv[c0 + c] : 0.f;
-  const float bias_c = p.dbias ? p.dbias[c0 + c] : 0.f;
   float dD = 0.f, dbias = 0.f;
+  // lane (sub, channel-in-warp cw) ends the dB / dC butterfly with the total of value v = cw:
+  // v < 8 -> dB of state sub*8 + v, else dC of state sub*8 + v - 8
+  const int vfin = lane >> 1;
+  float* my_acc = a_dBC + warp * TT * 2 * kN + (vfin < S ? sub * S + vfin : kN + sub * S + vfin - S);
+
+  // one forward step of this thread's 8 states: hn = a * hp + dt*u*B; returns the thread's share of <h, C>
+  auto fwd_step = [&](int r, const float (&hp)[S], float (&hn)[S]) -> float {
+    const float dtv = w_dt[r * CH + c];
+    const float dtu = dtv * w_u[r * CH + c];
+    float2 y2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < S / 4; ++q) {
+      const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + sub * S + 4 * q);
+      const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + sub * S + 4 * q);
+      const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        const int n = 4 * q + i;
+        const float2 x = __fmul2_rn(make_float2(dtv, dtv), make_float2(A2[n], A2[n + 1]));
+        const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+        const float2 bu = __fmul2_rn(make_float2(dtu, dtu), make_float2(Bv[i], Bv[i + 1]));
+        const float2 h2 = __ffma2_rn(a, make_float2(hp[n], hp[n + 1]), bu);
+        hn[n] = h2.x, hn[n + 1] = h2.y;
+        y2 = __ffma2_rn(h2, make_float2(Cv[i], Cv[i + 1]), y2);
+      }
+    }
+    return y2.x + y2.y;
+  };
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % NS;
@@ -139,22 +180,23 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     const T* sC = reinterpret_cast<const T*>(st + 4 * Cfg::RAW_MAIN + Cfg::RAW_BC);
 
     // state at the start of this tile (from the training forward)
-    float h[kN];
+    float h0[S];
     {
-      const float4* cp = reinterpret_cast<const float4*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + c) * kN);
+      const float4* cp =
+          reinterpret_cast<const float4*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + c) * kN + sub * S);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < S / 4; ++q) {
         const float4 v = cp[q];
-        h[4 * q] = v.x, h[4 * q + 1] = v.y, h[4 * q + 2] = v.z, h[4 * q + 3] = v.w;
+        h0[4 * q] = v.x, h0[4 * q + 1] = v.y, h0[4 * q + 2] = v.z, h0[4 * q + 3] = v.w;
       }
     }
 
     mbar_wait(&full[s], (k / NS) & 1);
 
-    // ---- pre-pass (each thread its own channel column): activations and their derivatives
-    for (int r = 0; r < TT; ++r) {
-      const int e = r * CH + c;
-      const float x = to_f32<T>(sd[e]) + bias_c;
+    // ---- pre-pass (elementwise over the tile): activations and their derivatives
+    for (int e = tid; e < TT * CH; e += NT) {
+      const int cc = e % CH;
+      const float x = to_f32<T>(sd[e]) + (p.dbias ? p.dbias[c0 + cc] : 0.f);
       w_dt[e] = p.softplus ? softplus_f(x) : x;
       w_sg[e] = p.softplus ? ((x > 20.f) ? 1.f : sigmoid_f(x)) : 1.f;  // d softplus / dx
       w_u[e] = to_f32<T>(su[e]);
@@ -172,106 +214,109 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     for (int e = tid; e < TT * kN; e += NT) {
       w_B[e] = to_f32<T>(sB[e]);
       w_C[e] = to_f32<T>(sC[e]);
-      a_dB[e] = 0.f;
-      a_dC[e] = 0.f;
     }
+    for (int e = tid; e < NW * TT * 2 * kN; e += NT) a_dBC[e] = 0.f;
     if (tid == 0) bulk_wait_read0();  // previous tile's stores have finished reading the output tiles
     __syncthreads();
     if (tid == 0 && k + NS < ntiles) issue_tile(k + NS);  // raw stage s is free again
 
-    // ---- (1) forward recompute inside the tile: h_t -> hbuf, y_t -> w_y
-    for (int r = 0; r < rows; ++r) {
-      const float dtv = w_dt[r * CH + c], uv = w_u[r * CH + c];
-      const float dtu = dtv * uv;
-      float y = Dc * uv;
-      float* hb = hbuf + ((long)r * CH + c) * kN;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + 4 * q);
-        const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + 4 * q);
-        const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
-        float hv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * q + i;
-          const float a = ex2_approx(dtv * A2[n]);
-          h[n] = fmaf(a, h[n], dtu * Bv[i]);
-          y = fmaf(h[n], Cv[i], y);
-          hv[i] = h[n];
-        }
-        *reinterpret_cast<float4*>(hb + 4 * q) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      }
-      w_y[r * CH + c] = y;
-    }
-    // h[] now holds the state at the END of the tile; reload the start state for the t == first step below
-    float h0[kN];
+    // ---- (1) forward sweep over steps 0 .. TT-SUB-1: leaves the start state of sub-tiles 1 .. 3 in shared memory
     {
-      const float4* cp = reinterpret_cast<const float4*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + c) * kN);
+      float h[S];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = cp[q];
-        h0[4 * q] = v.x, h0[4 * q + 1] = v.y, h0[4 * q + 2] = v.z, h0[4 * q + 3] = v.w;
+      for (int n = 0; n < S; ++n) h[n] = h0[n];
+#pragma unroll 1
+      for (int q = 0; q < TT / SUB - 1; ++q) {
+        if (SUB * (q + 1) >= rows) break;  // the sub-tiles after this one are past the end of the sequence
+#pragma unroll
+        for (int i = 0; i < SUB; ++i) fwd_step(SUB * q + i, h, h);
+        sck[(q * 2 + 0) * NT + tid] = make_float4(h[0], h[1], h[2], h[3]);
+        sck[(q * 2 + 1) * NT + tid] = make_float4(h[4], h[5], h[6], h[7]);
       }
     }
 
-    // ---- (2) adjoint recurrence, backwards in time
-    for (int r = rows - 1; r >= 0; --r) {
-      const int e = r * CH + c;
-      const float dtv = w_dt[e], uv = w_u[e], dy = w_dy[e];
-      const float dtu = dtv * uv;
-      float ddt = 0.f, du = dy * Dc;
-      float red[2 * kN];  // [0,16): dB partials, [16,32): dC partials of this channel
-      const float* hb = hbuf + ((long)r * CH + c) * kN;
-      const float* hp = hbuf + ((long)(r - 1) * CH + c) * kN;
+    // ---- (2) sub-tiles back to front: recompute 4 states into registers, then their adjoint steps
+#pragma unroll 1
+    for (int sb = TT / SUB - 1; sb >= 0; --sb) {
+      const int rb = SUB * sb;
+      if (rb >= rows) continue;
+      float hs[S], hq[SUB][S];
+      if (sb == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + 4 * q);
-        const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + 4 * q);
-        const float4 hq = *reinterpret_cast<const float4*>(hb + 4 * q);
-        float4 pq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r > 0) pq = *reinterpret_cast<const float4*>(hp + 4 * q);
-        const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
-        const float hv[4] = {hq.x, hq.y, hq.z, hq.w};
-        const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * q + i;
-          const float hprev = (r > 0) ? pv[i] : h0[n];
-          const float dhn = fmaf(dy, Cv[i], dh[n]);  // dL/dh_t
-          const float a = ex2_approx(dtv * A2[n]);
-          red[kN + n] = dy * hv[i];
-          red[n] = dhn * dtu;
-          const float tmp = dhn * hprev * a;          // dL/da * a
-          ddt = fmaf(dhn * Bv[i], uv, fmaf(tmp, A[n], ddt));
-          du = fmaf(dhn * dtv, Bv[i], du);
-          dA[n] = fmaf(tmp, dtv, dA[n]);
-          dh[n] = a * dhn;
-        }
+        for (int n = 0; n < S; ++n) hs[n] = h0[n];
+      } else {
+        const float4 p0 = sck[((sb - 1) * 2 + 0) * NT + tid], p1 = sck[((sb - 1) * 2 + 1) * NT + tid];
+        hs[0] = p0.x, hs[1] = p0.y, hs[2] = p0.z, hs[3] = p0.w, hs[4] = p1.x, hs[5] = p1.y, hs[6] = p1.z, hs[7] = p1.w;
       }
-      const float dd = ddt * w_sg[e];
-      dbias += dd;
-      dD = fmaf(dy, uv, dD);
-      o_du[e] = from_f32<T>(du);
-      o_dd[e] = from_f32<T>(dd);
-      o_dz[e] = from_f32<T>(w_dzc[e] * w_y[e]);
-      // reduce the 32 per-channel partials over the warp's 32 channels: lane l ends with the sum of red[l]
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-          const float send = up ? red[i] : red[i + o];
-          const float keep = up ? red[i + o] : red[i];
-          red[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
+      for (int i = 0; i < SUB; ++i) {
+        const int r = rb + i;
+        float y = (i == 0) ? fwd_step(r, hs, hq[0]) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i]);
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        if (sub == 0) w_y[r * CH + c] = fmaf(Dc, w_u[r * CH + c], y);
       }
-      float* acc = (lane < kN) ? (a_dB + r * kN + lane) : (a_dC + r * kN + lane - kN);
-      if (NT == 32)
-        *acc += red[0];  // single warp per CTA: plain read-modify-write
-      else
-        atomicAdd(acc, red[0]);
+#pragma unroll
+      for (int i = SUB - 1; i >= 0; --i) {
+        const int r = rb + i;
+        if (r >= rows) continue;
+        const int e = r * CH + c;
+        const float dtv = w_dt[e], uv = w_u[e], dy = w_dy[e];
+        const float dtu = dtv * uv;
+        // packed f32x2 over state pairs.  s1 = sum_n dh_n B_n feeds both ddt (x u) and du (x dt); s2 = sum_n tmp_n A_n
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+        float red[2 * S];  // [0,8): dB partials, [8,16): dC partials of this (channel, state half)
+        const float2 dy2 = make_float2(dy, dy), dt2 = make_float2(dtv, dtv), dtu2 = make_float2(dtu, dtu);
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) {
+          const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + sub * S + 4 * q);
+          const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + sub * S + 4 * q);
+          const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            const int n = 4 * q + j;
+            const float2 hprev = (i == 0) ? make_float2(hs[n], hs[n + 1]) : make_float2(hq[i > 0 ? i - 1 : 0][n], hq[i > 0 ? i - 1 : 0][n + 1]);
+            const float2 dhn = __ffma2_rn(dy2, make_float2(Cv[j], Cv[j + 1]), make_float2(dh[n], dh[n + 1]));  // dL/dh_t
+            const float2 x = __fmul2_rn(dt2, make_float2(A2[n], A2[n + 1]));
+            const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            const float2 rc = __fmul2_rn(dy2, make_float2(hq[i][n], hq[i][n + 1]));
+            const float2 rb2 = __fmul2_rn(dhn, dtu2);
+            red[S + n] = rc.x, red[S + n + 1] = rc.y;
+            red[n] = rb2.x, red[n + 1] = rb2.y;
+            const float2 tmp = __fmul2_rn(__fmul2_rn(dhn, hprev), a);  // dL/da * a
+            s1 = __ffma2_rn(dhn, make_float2(Bv[j], Bv[j + 1]), s1);
+            s2 = __ffma2_rn(tmp, make_float2(A[n], A[n + 1]), s2);
+            const float2 dAn = __ffma2_rn(tmp, dt2, make_float2(dA[n], dA[n + 1]));
+            dA[n] = dAn.x, dA[n + 1] = dAn.y;
+            const float2 dhp = __fmul2_rn(a, dhn);
+            dh[n] = dhp.x, dh[n + 1] = dhp.y;
+          }
+        }
+        float s1s = s1.x + s1.y, s2s = s2.x + s2.y;
+        s1s += __shfl_xor_sync(0xffffffffu, s1s, 1);
+        s2s += __shfl_xor_sync(0xffffffffu, s2s, 1);
+        if (sub == 0) {
+          const float dd = fmaf(uv, s1s, s2s) * w_sg[e];
+          dbias += dd;
+          dD = fmaf(dy, uv, dD);
+          o_du[e] = from_f32<T>(fmaf(dy, Dc, dtv * s1s));
+          o_dd[e] = from_f32<T>(dd);
+          o_dz[e] = from_f32<T>(w_dzc[e] * w_y[e]);
+        }
+        // reduce the 16 partials over the warp's 16 channels (lane bits 1..4): transposed butterfly
+#pragma unroll
+        for (int ov = S, ol = 16; ov >= 1; ov >>= 1, ol >>= 1) {
+          const bool up = (lane & ol) != 0;
+#pragma unroll
+          for (int v = 0; v < ov; ++v) {
+            const float send = up ? red[v] : red[v + ov];
+            const float keep = up ? red[v + ov] : red[v];
+            red[v] = keep + __shfl_xor_sync(0xffffffffu, send, ol);
+          }
+        }
+        my_acc[r * 2 * kN] = red[0];  // this warp's own accumulator row: no atomics
+      }
     }
-
+    // rows past the end of the sequence: keep the output tiles defined (the TMA store clips them anyway)
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -280,17 +325,23 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
       if (has_z) tma_store_3d(&tm.dz, c0, t0, b, o_dz);
       bulk_commit();
     }
-    for (int e = tid; e < rows * kN; e += NT) {
-      atomicAdd(p.dB + ((long)b * p.L + t0) * kN + e, a_dB[e]);
-      atomicAdd(p.dC + ((long)b * p.L + t0) * kN + e, a_dC[e]);
+    for (int e = tid; e < rows * 2 * kN; e += NT) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v += a_dBC[w * TT * 2 * kN + e];
+      const int r = e / (2 * kN), n = e % (2 * kN);
+      float* dst = (n < kN ? p.dB : p.dC) + ((long)b * p.L + t0 + r) * kN + (n & (kN - 1));
+      atomicAdd(dst, v);
     }
-    __syncthreads();  // a_dB / a_dC / work arrays are rewritten by the next tile's pre-pass
+    __syncthreads();  // accumulators / work arrays are rewritten by the next tile's pre-pass
   }
   if (tid == 0) bulk_wait0();
 #pragma unroll
-  for (int n = 0; n < kN; ++n) atomicAdd(p.dA + (long)(c0 + c) * kN + n, dA[n]);
-  if (p.dD) atomicAdd(p.dD + c0 + c, dD);
-  if (p.ddbias) atomicAdd(p.ddbias + c0 + c, dbias);
+  for (int n = 0; n < S; ++n) atomicAdd(p.dA + (long)(c0 + c) * kN + sub * S + n, dA[n]);
+  if (sub == 0) {
+    if (p.dD) atomicAdd(p.dD + c0 + c, dD);
+    if (p.ddbias) atomicAdd(p.ddbias + c0 + c, dbias);
+  }
 }
 
 template <typename T, int CH>

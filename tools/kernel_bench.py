@@ -93,6 +93,34 @@ def main():
                 report("selective_scan_fwd", t, alg, B=B, L=L, D=D, dtype=str(dtype).split(".")[-1], variant=variant)
                 del fns
                 torch.cuda.empty_cache()
+    # scan backward (training configs): C1 layer shape fp32, C2 layer shape (L = 1024) bf16
+    for (B, L, D, dtype) in (((32, 512, 768, torch.float32), (32, 1024, 768, torch.bfloat16)) if want("scanbwd") else []):
+        fns, alg = scan_case(B, L, D, dtype, 0, 2)
+        es = 4 if dtype == torch.float32 else 2
+        sets = []
+        for i in range(2):
+            g = torch.Generator(device="cuda").manual_seed(10 + i)
+            r = lambda *s: torch.randn(*s, generator=g, device="cuda")
+            xz, u, delta, xdbl = r(B, L, 2 * D).to(dtype), r(B, L, D).to(dtype), (0.5 * r(B, L, D)).to(dtype), r(B, L, 56).to(dtype)
+            dout = r(B, L, D).to(dtype)
+            ck = torch.empty(ops.scan_checkpoint_shape(B, L, D), dtype=torch.float32, device="cuda")
+            sets.append((u, delta, xdbl[..., 24:40], xdbl[..., 40:], xz[..., D:], dout, ck))
+        A = -torch.arange(1, 17, device="cuda", dtype=torch.float32).repeat(D, 1)
+        Dv, bias = torch.ones(D, device="cuda"), torch.full((D,), -4.0, device="cuda")
+        for s_ in sets:
+            ops.selective_scan_tm(s_[0], s_[1], A, s_[2], s_[3], Dv, s_[4], bias, True, checkpoints=s_[6])
+        bfn = [(lambda s_=s_: ops.selective_scan_bwd_tm(s_[0], s_[1], A, s_[2], s_[3], Dv, s_[4], bias, s_[5], s_[6], True))
+               for s_ in sets]
+        E, S = B * L * D, B * L * 16
+        alg_b = 7 * E * es + 2 * S * es + 2 * S * 4
+        report("selective_scan_bwd", time_fn(bfn), alg_b, B=B, L=L, D=D, dtype=str(dtype).split(".")[-1],
+               note="includes the zero-fills of dB / dC / dA and the output allocations")
+        ffn = [(lambda s_=s_: ops.selective_scan_tm(s_[0], s_[1], A, s_[2], s_[3], Dv, s_[4], bias, True, checkpoints=s_[6]))
+               for s_ in sets]
+        report("selective_scan_fwd+ckpt", time_fn(ffn), 4 * E * es + 2 * S * es + E * 4, B=B, L=L, D=D,
+               dtype=str(dtype).split(".")[-1])
+        del sets, bfn, ffn
+        torch.cuda.empty_cache()
     # conv
     for (B, L, D) in (shapes[:2] if want("conv") else []):
         for dtype in (torch.float32, torch.bfloat16):

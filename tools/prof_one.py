@@ -43,6 +43,15 @@ def main():
         for i in range(a.iters):
             s = sets[i % 3]
             ops.selective_scan_tm(s[0], s[1], A, s[2], s[3], Dv, s[4], bias, True, out=s[5], variant=a.variant)
+    elif a.kernel == "scanbwd":
+        xz, u, dl, xd = r(B, L, 2 * D).to(dt), r(B, L, D).to(dt), (0.5 * r(B, L, D)).to(dt), r(B, L, 56).to(dt)
+        dout = r(B, L, D).to(dt)
+        A = -torch.arange(1, 17, device=dev, dtype=torch.float32).repeat(D, 1)
+        Dv, bias = torch.ones(D, device=dev), torch.full((D,), -4.0, device=dev)
+        ck = torch.empty(ops.scan_checkpoint_shape(B, L, D), dtype=torch.float32, device=dev)
+        ops.selective_scan_tm(u, dl, A, xd[..., 24:40], xd[..., 40:], Dv, xz[..., D:], bias, True, checkpoints=ck)
+        for i in range(a.iters):
+            ops.selective_scan_bwd_tm(u, dl, A, xd[..., 24:40], xd[..., 40:], Dv, xz[..., D:], bias, dout, ck, True)
     elif a.kernel in ("fps", "knn", "spectral"):
         N = 1024 if a.G <= 64 else 2048
         xyz = torch.rand(B, N, 3, generator=g, device=dev)
