@@ -200,6 +200,12 @@ int sim_chamfer_l2_bwd(const float* x, const float* y, const int32_t* idx_x, con
  * elements, row stride ldo); the weights are split once per model, activations by their producer.
  * sim_gemm_bf16x3: Y[M,N] = sum of the six leading plane products X_i . W_j^T, fp32 accumulation in tensor memory.
  * ldx / ldw / plane strides multiples of 8 elements, ldd and N multiples of 4. */
+/* a-9 backward (training configs): res (rows,C) = the fp32 residual stream sim_add_layernorm wrote, dy = gradient of
+ * its normalised output (dtype_y), dres_out = gradient arriving in the residual stream from later layers (fp32, may be
+ * NULL).  dres (fp32) = gradient of both inputs of the add; dgamma / dbeta (fp32, C) are accumulated into. */
+int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, const float* gamma, float* dres,
+                          float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, sim_stream_t stream);
+
 /* Producers that emit the split operand directly (fp32 activations), so no separate split pass is needed:
  * LayerNorm output -> in_proj, conv output (fp32 u for the scan AND planes for x_proj), scan output -> out_proj. */
 int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,

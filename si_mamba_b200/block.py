@@ -41,10 +41,12 @@ def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor
     needed; plain torch ops (so autograd works) when training."""
     needs_grad = torch.is_grad_enabled() and (hidden.requires_grad or (residual is not None and residual.requires_grad)
                                               or norm.weight.requires_grad)
-    if needs_grad or not isinstance(norm, nn.LayerNorm):
+    if not isinstance(norm, nn.LayerNorm) or not hidden.is_cuda or norm.weight is None or norm.bias is None:
         res = hidden + residual if residual is not None else hidden
         res = res.float() if res.dtype != torch.float32 else res
         return norm(res.to(dtype=norm.weight.dtype)), res
+    if needs_grad:  # training: same forward kernel, backward through sim_add_layernorm_bwd
+        return ops.AddLayerNorm.apply(hidden, residual, norm.weight, norm.bias, norm.eps, _amp_dtype(hidden))
     out_dtype = _amp_dtype(hidden)
     return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=out_dtype,
                              want_residual=want_residual, split=split and out_dtype == torch.float32)

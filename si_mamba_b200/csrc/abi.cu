@@ -247,6 +247,12 @@ int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, 
   return sim::fps(xyz, B, N, npoint, idx, sampled, static_cast<cudaStream_t>(stream), 1);
 }
 
+int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, const float* gamma, float* dres,
+                          float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, sim_stream_t stream) {
+  return sim::add_layernorm_bwd(res, dy, dres_out, gamma, dres, dgamma, dbeta, rows, C, eps, dtype_y,
+                                static_cast<cudaStream_t>(stream));
+}
+
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
   return sim::split3_bf16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
 }

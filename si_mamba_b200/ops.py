@@ -382,6 +382,39 @@ def linear_f32_tc(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Ten
     return out
 
 
+class AddLayerNorm(torch.autograd.Function):
+    """(y, res) = (LayerNorm(x + residual), x + residual) with the residual stream in fp32: sim_add_layernorm forward,
+    sim_add_layernorm_bwd backward (statistics recomputed from ``res``, which autograd keeps alive anyway)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps, out_dtype):
+        y, res = add_layernorm(x, residual, weight, bias, eps, out_dtype=out_dtype, want_residual=True)
+        ctx.save_for_backward(res, weight)
+        ctx.eps = eps
+        ctx.x_dtype = x.dtype
+        ctx.res_dtype = None if residual is None else residual.dtype
+        ctx.wdtype = weight.dtype
+        ctx.mark_non_differentiable()
+        return y, res
+
+    @staticmethod
+    def backward(ctx, dy, dres_out):
+        res, weight = ctx.saved_tensors
+        C = res.shape[-1]
+        rows = res.numel() // C
+        dy = dy.contiguous()
+        if dres_out is not None:
+            dres_out = dres_out.float().contiguous()
+        dres = torch.empty_like(res)
+        dg = torch.zeros(C, dtype=torch.float32, device=res.device)
+        db = torch.zeros(C, dtype=torch.float32, device=res.device)
+        _lib.call("sim_add_layernorm_bwd", _p(res), _p(dy), _p(dres_out), _p(_f32c(weight)), _p(dres), _p(dg), _p(db),
+                  rows, C, float(ctx.eps), _dt(dy), _stream())
+        dx = dres if ctx.x_dtype == torch.float32 else dres.to(ctx.x_dtype)
+        dr = None if ctx.res_dtype is None else (dres if ctx.res_dtype == torch.float32 else dres.to(ctx.res_dtype))
+        return dx, dr, dg.to(ctx.wdtype), db.to(ctx.wdtype), None, None
+
+
 class Split3:
     """An fp32 activation (..., K) carried as three bf16 planes (3, rows, K): the operand format of the tcgen05
     projection GEMM (csrc/gemm_split3.cu).  Produced by add_layernorm / causal_conv1d_tm / selective_scan_tm with

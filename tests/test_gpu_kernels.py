@@ -423,3 +423,25 @@ def test_fps_pointnet2_vs_oracle(ops, B, N, npoint, kind):
     out, idx = ops.fps_pointnet2(dev(xyz), npoint, return_idx=True)
     assert torch.equal(idx.cpu().long(), ref)
     assert torch.equal(out.cpu(), torch.gather(xyz, 1, ref[..., None].expand(-1, -1, 3)))
+
+
+@pytest.mark.parametrize("rows,C,ydt", [(1000, 384, torch.float32), (4099, 384, torch.bfloat16), (33, 512, torch.float32),
+                                        (7, 64, torch.float32)])
+def test_add_layernorm_backward(ops, rows, C, ydt):
+    """sim_add_layernorm_bwd (through ops.AddLayerNorm) vs autograd of torch's add + layer_norm in fp64."""
+    g = torch.Generator().manual_seed(rows)
+    x, r = torch.randn(rows, C, generator=g), torch.randn(rows, C, generator=g)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    gy, gres = torch.randn(rows, C, generator=g), torch.randn(rows, C, generator=g)
+    if ydt == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    ref_in = [t.double().requires_grad_() for t in (x, r, w, b)]
+    res = ref_in[0] + ref_in[1]
+    y = torch.nn.functional.layer_norm(res, (C,), ref_in[2], ref_in[3], 1e-5)
+    ((y * gy.double()).sum() + (res * gres.double()).sum()).backward()
+    ins = [dev(t).requires_grad_() for t in (x, r, w, b)]
+    yk, resk = ops.AddLayerNorm.apply(ins[0], ins[1], ins[2], ins[3], 1e-5, ydt)
+    ((yk.float() * dev(gy)).sum() + (resk * dev(gres)).sum()).backward()
+    for got, ref in zip(ins, ref_in):
+        assert rel_err(got.grad.cpu().double(), ref.grad) < (2e-5 if ydt == torch.float32 else 2e-2)
+    assert torch.equal(ins[0].grad, ins[1].grad)
