@@ -18,6 +18,8 @@
 // Roofline class: SM issue (about 25 instructions per state update); HBM algorithmic bytes are
 // (5 reads + 3 writes) * E * s + checkpoint E * 4 + O(S).  First version - correctness first.
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tma.cuh"
 
@@ -55,53 +57,55 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
 // and the CTA's shared memory drops to the operand tiles, so 3x more warps are resident.
 constexpr int SUB = 4;  // steps per sub-tile
 
-template <typename T, int CH_>
+template <typename T, int CH_, int LPC_>
 struct BwdCfg {
   static constexpr int CH = CH_;
-  static constexpr int S = 8;          // states per thread
-  static constexpr int NT = 2 * CH_;   // threads per CTA
+  static constexpr int LPC = LPC_;       // lanes per channel
+  static constexpr int S = kN / LPC_;    // states per thread
+  static constexpr int NT = LPC_ * CH_;  // threads per CTA
   static constexpr int NW = NT / 32;
   static constexpr int NS = 2;
   static constexpr int RAW_MAIN = TT * CH_ * (int)sizeof(T);
   static constexpr int RAW_BC = TT * kN * (int)sizeof(T);
-  static constexpr int RAW_STAGE = 4 * RAW_MAIN + 2 * RAW_BC;  // u, delta, z, dout, B, C
+  static constexpr int RAW_CK = CH_ * kN * 4;                   // tile-start states of the CTA's channels (fp32)
+  static constexpr int RAW_STAGE = 4 * RAW_MAIN + 2 * RAW_BC + RAW_CK;  // u, delta, z, dout, B, C, checkpoint
   static constexpr int OUT = 3 * RAW_MAIN;                      // du, ddelta, dz
-  static constexpr int WORK = 6 * TT * CH_ * 4                  // dt, u, sg, dy, dzc, y
+  static constexpr int WORK = 9 * TT * CH_ * 4                  // (dt, u, dy, dt*u) packed, sg, dzc, y, s1, s2
                               + 2 * TT * kN * 4                 // B, C fp32
                               + NW * TT * 2 * kN * 4;           // per-warp dB | dC tile sums
-  static constexpr int SCK = (TT / SUB - 1) * 2 * NT * 16;      // sub-tile start states, float4 planes
+  static constexpr int SCK = (TT / SUB - 1) * (S / 4) * NT * 16;  // sub-tile start states, float4 planes
   static constexpr int SMEM = NS * RAW_STAGE + OUT + WORK + SCK + NS * 8 + 64;
-  static_assert(RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0, "TMA tiles must stay 128-B aligned");
-  static_assert(TT % SUB == 0, "whole sub-tiles");
+  static_assert(RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && RAW_CK % 128 == 0, "TMA tiles must stay 128-B aligned");
+  static_assert(TT % SUB == 0 && NT % CH_ == 0, "whole sub-tiles; a thread's elementwise channel is fixed");
 };
 
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __grid_constant__ BwdTmaps tm,
                                                                      const ScanBwdParams p) {
-  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW;
+  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW, LPC = Cfg::LPC, SQ = Cfg::S / 4;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* raw = smem;
   T* __restrict__ o_du = reinterpret_cast<T*>(smem + NS * Cfg::RAW_STAGE);
   T* __restrict__ o_dd = o_du + TT * CH;
   T* __restrict__ o_dz = o_dd + TT * CH;
-  float* __restrict__ w_dt = reinterpret_cast<float*>(smem + NS * Cfg::RAW_STAGE + Cfg::OUT);
-  float* __restrict__ w_u = w_dt + TT * CH;
-  float* __restrict__ w_sg = w_u + TT * CH;
-  float* __restrict__ w_dy = w_sg + TT * CH;
-  float* __restrict__ w_dzc = w_dy + TT * CH;
+  float4* __restrict__ w4 = reinterpret_cast<float4*>(smem + NS * Cfg::RAW_STAGE + Cfg::OUT);  // (dt, u, dy, dt*u)
+  float* __restrict__ w_sg = reinterpret_cast<float*>(w4 + TT * CH);
+  float* __restrict__ w_dzc = w_sg + TT * CH;
   float* __restrict__ w_y = w_dzc + TT * CH;
-  float* __restrict__ w_B = w_y + TT * CH;
+  float* __restrict__ w_s1 = w_y + TT * CH;
+  float* __restrict__ w_s2 = w_s1 + TT * CH;
+  float* __restrict__ w_B = w_s2 + TT * CH;
   float* __restrict__ w_C = w_B + TT * kN;
   float* __restrict__ a_dBC = w_C + TT * kN;                                  // [warp][t][dB(16) | dC(16)]
   float4* __restrict__ sck = reinterpret_cast<float4*>(a_dBC + NW * TT * 2 * kN);  // [sub-1][half][thread]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sck + (TT / SUB - 1) * 2 * NT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sck + (TT / SUB - 1) * SQ * NT);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunk = p.D / CH;
   const int b = blockIdx.x / nchunk;
   const int c0 = (blockIdx.x % nchunk) * CH;
-  const int sub = tid & 1;   // which half of the 16 states
-  const int c = tid >> 1;    // channel within the CTA
+  const int sub = tid % LPC;  // which slice of the 16 states
+  const int c = tid / LPC;    // channel within the CTA
   const int ntiles = (p.L + TT - 1) / TT;
   const bool has_z = p.z != nullptr;
 
@@ -115,7 +119,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     const int s = k % NS;
     const int t0 = (ntiles - 1 - k) * TT;
     unsigned char* st = raw + s * Cfg::RAW_STAGE;
-    mbar_arrive_expect_tx(&full[s], (has_z ? 4u : 3u) * Cfg::RAW_MAIN + 2u * Cfg::RAW_BC);
+    mbar_arrive_expect_tx(&full[s], (has_z ? 4u : 3u) * Cfg::RAW_MAIN + 2u * Cfg::RAW_BC + Cfg::RAW_CK);
+    bulk_g2s(st + 4 * Cfg::RAW_MAIN + 2 * Cfg::RAW_BC, p.ckpt + (((long)b * ntiles + (ntiles - 1 - k)) * p.D + c0) * kN,
+             Cfg::RAW_CK, &full[s]);
     tma_load_3d(st, &tm.u, c0, t0, b, &full[s]);
     tma_load_3d(st + Cfg::RAW_MAIN, &tm.delta, c0, t0, b, &full[s]);
     if (has_z) tma_load_3d(st + 2 * Cfg::RAW_MAIN, &tm.z, c0, t0, b, &full[s]);
@@ -136,16 +142,24 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     dh[n] = 0.f;
   }
   const float Dc = p.Dv ? p.Dv[c0 + c] : 0.f;
+  const int ce = tid % CH;  // channel of this thread's elements in the elementwise passes (NT % CH == 0)
+  const float De = p.Dv ? p.Dv[c0 + ce] : 0.f;
+  const float bias_e = p.dbias ? p.dbias[c0 + ce] : 0.f;
   float dD = 0.f, dbias = 0.f;
-  // lane (sub, channel-in-warp cw) ends the dB / dC butterfly with the total of value v = cw:
-  // v < 8 -> dB of state sub*8 + v, else dC of state sub*8 + v - 8
-  const int vfin = lane >> 1;
+  // lane (sub, channel-in-warp cw) ends the dB / dC butterfly with the total of value v = cw (the warp has 32 / LPC
+  // channels and every thread 2 S = 32 / LPC values): v < S -> dB of state sub*S + v, else dC of state sub*S + v - S
+  const int vfin = lane / LPC;
+  auto sum_subs = [&](float v) {  // total over the LPC lanes of a channel
+#pragma unroll
+    for (int o = 1; o < LPC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
   float* my_acc = a_dBC + warp * TT * 2 * kN + (vfin < S ? sub * S + vfin : kN + sub * S + vfin - S);
 
   // one forward step of this thread's 8 states: hn = a * hp + dt*u*B; returns the thread's share of <h, C>
   auto fwd_step = [&](int r, const float (&hp)[S], float (&hn)[S]) -> float {
-    const float dtv = w_dt[r * CH + c];
-    const float dtu = dtv * w_u[r * CH + c];
+    const float4 w = w4[r * CH + c];
+    const float dtv = w.x, dtu = w.w;
     float2 y2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < S / 4; ++q) {
@@ -179,43 +193,40 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     const T* sB = reinterpret_cast<const T*>(st + 4 * Cfg::RAW_MAIN);
     const T* sC = reinterpret_cast<const T*>(st + 4 * Cfg::RAW_MAIN + Cfg::RAW_BC);
 
-    // state at the start of this tile (from the training forward)
-    float h0[S];
-    {
-      const float4* cp =
-          reinterpret_cast<const float4*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + c) * kN + sub * S);
-#pragma unroll
-      for (int q = 0; q < S / 4; ++q) {
-        const float4 v = cp[q];
-        h0[4 * q] = v.x, h0[4 * q + 1] = v.y, h0[4 * q + 2] = v.z, h0[4 * q + 3] = v.w;
-      }
-    }
+    const float* sck0 = reinterpret_cast<const float*>(st + 4 * Cfg::RAW_MAIN + 2 * Cfg::RAW_BC);  // [channel][16]
 
     mbar_wait(&full[s], (k / NS) & 1);
 
-    // ---- pre-pass (elementwise over the tile): activations and their derivatives
+    // ---- pre-pass (elementwise over the tile): activations and their derivatives.  Rows past the end of the sequence
+    // were zero-filled by the TMA unit: their dout is 0, so every gradient they produce is 0 and no step needs a guard.
     for (int e = tid; e < TT * CH; e += NT) {
-      const int cc = e % CH;
-      const float x = to_f32<T>(sd[e]) + (p.dbias ? p.dbias[c0 + cc] : 0.f);
-      w_dt[e] = p.softplus ? softplus_f(x) : x;
+      const float x = to_f32<T>(sd[e]) + bias_e;
+      const float dtv = p.softplus ? softplus_f(x) : x;
       w_sg[e] = p.softplus ? ((x > 20.f) ? 1.f : sigmoid_f(x)) : 1.f;  // d softplus / dx
-      w_u[e] = to_f32<T>(su[e]);
+      const float uv = to_f32<T>(su[e]);
       const float go = to_f32<T>(so[e]);
+      float dy = go;
       if (has_z) {
         const float zv = to_f32<T>(sz[e]);
         const float sg = sigmoid_f(zv);
-        w_dy[e] = go * zv * sg;                               // dL/dy = dout * silu(z)
+        dy = go * zv * sg;                                    // dL/dy = dout * silu(z)
         w_dzc[e] = go * sg * (1.f + zv * (1.f - sg));         // dout * silu'(z); dz = this * y
       } else {
-        w_dy[e] = go;
         w_dzc[e] = 0.f;
       }
+      w4[e] = make_float4(dtv, uv, dy, dtv * uv);
     }
     for (int e = tid; e < TT * kN; e += NT) {
       w_B[e] = to_f32<T>(sB[e]);
       w_C[e] = to_f32<T>(sC[e]);
     }
-    for (int e = tid; e < NW * TT * 2 * kN; e += NT) a_dBC[e] = 0.f;
+    // state at the start of this tile (from the training forward; arrived with the operand tiles)
+    float h0[S];
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(sck0 + c * kN + sub * S + 4 * q);
+      h0[4 * q] = v.x, h0[4 * q + 1] = v.y, h0[4 * q + 2] = v.z, h0[4 * q + 3] = v.w;
+    }
     if (tid == 0) bulk_wait_read0();  // previous tile's stores have finished reading the output tiles
     __syncthreads();
     if (tid == 0 && k + NS < ntiles) issue_tile(k + NS);  // raw stage s is free again
@@ -227,11 +238,10 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
       for (int n = 0; n < S; ++n) h[n] = h0[n];
 #pragma unroll 1
       for (int q = 0; q < TT / SUB - 1; ++q) {
-        if (SUB * (q + 1) >= rows) break;  // the sub-tiles after this one are past the end of the sequence
 #pragma unroll
         for (int i = 0; i < SUB; ++i) fwd_step(SUB * q + i, h, h);
-        sck[(q * 2 + 0) * NT + tid] = make_float4(h[0], h[1], h[2], h[3]);
-        sck[(q * 2 + 1) * NT + tid] = make_float4(h[4], h[5], h[6], h[7]);
+#pragma unroll
+        for (int j = 0; j < SQ; ++j) sck[(q * SQ + j) * NT + tid] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
       }
     }
 
@@ -239,32 +249,32 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
 #pragma unroll 1
     for (int sb = TT / SUB - 1; sb >= 0; --sb) {
       const int rb = SUB * sb;
-      if (rb >= rows) continue;
       float hs[S], hq[SUB][S];
       if (sb == 0) {
 #pragma unroll
         for (int n = 0; n < S; ++n) hs[n] = h0[n];
       } else {
-        const float4 p0 = sck[((sb - 1) * 2 + 0) * NT + tid], p1 = sck[((sb - 1) * 2 + 1) * NT + tid];
-        hs[0] = p0.x, hs[1] = p0.y, hs[2] = p0.z, hs[3] = p0.w, hs[4] = p1.x, hs[5] = p1.y, hs[6] = p1.z, hs[7] = p1.w;
+#pragma unroll
+        for (int j = 0; j < SQ; ++j) {
+          const float4 pj = sck[((sb - 1) * SQ + j) * NT + tid];
+          hs[4 * j] = pj.x, hs[4 * j + 1] = pj.y, hs[4 * j + 2] = pj.z, hs[4 * j + 3] = pj.w;
+        }
       }
 #pragma unroll
       for (int i = 0; i < SUB; ++i) {
         const int r = rb + i;
         float y = (i == 0) ? fwd_step(r, hs, hq[0]) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i]);
-        y += __shfl_xor_sync(0xffffffffu, y, 1);
-        if (sub == 0) w_y[r * CH + c] = fmaf(Dc, w_u[r * CH + c], y);
+        y = sum_subs(y);
+        if (sub == 0) w_y[r * CH + c] = y;  // <h, C>; D u is added in the epilogue
       }
 #pragma unroll
       for (int i = SUB - 1; i >= 0; --i) {
         const int r = rb + i;
-        if (r >= rows) continue;
-        const int e = r * CH + c;
-        const float dtv = w_dt[e], uv = w_u[e], dy = w_dy[e];
-        const float dtu = dtv * uv;
+        const float4 w = w4[r * CH + c];
+        const float dtv = w.x, dy = w.z, dtu = w.w;
         // packed f32x2 over state pairs.  s1 = sum_n dh_n B_n feeds both ddt (x u) and du (x dt); s2 = sum_n tmp_n A_n
         float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-        float red[2 * S];  // [0,8): dB partials, [8,16): dC partials of this (channel, state half)
+        float red[2 * S];  // [0,S): dB partials, [S,2S): dC partials of this (channel, state slice)
         const float2 dy2 = make_float2(dy, dy), dt2 = make_float2(dtv, dtv), dtu2 = make_float2(dtu, dtu);
 #pragma unroll
         for (int q = 0; q < S / 4; ++q) {
@@ -291,18 +301,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
             dh[n] = dhp.x, dh[n + 1] = dhp.y;
           }
         }
-        float s1s = s1.x + s1.y, s2s = s2.x + s2.y;
-        s1s += __shfl_xor_sync(0xffffffffu, s1s, 1);
-        s2s += __shfl_xor_sync(0xffffffffu, s2s, 1);
-        if (sub == 0) {
-          const float dd = fmaf(uv, s1s, s2s) * w_sg[e];
-          dbias += dd;
-          dD = fmaf(dy, uv, dD);
-          o_du[e] = from_f32<T>(fmaf(dy, Dc, dtv * s1s));
-          o_dd[e] = from_f32<T>(dd);
-          o_dz[e] = from_f32<T>(w_dzc[e] * w_y[e]);
-        }
-        // reduce the 16 partials over the warp's 16 channels (lane bits 1..4): transposed butterfly
+        const float s1s = sum_subs(s1.x + s1.y), s2s = sum_subs(s2.x + s2.y);
+        if (sub == 0) w_s1[r * CH + c] = s1s, w_s2[r * CH + c] = s2s;
+        // reduce the 2 S partials over the warp's 32 / LPC channels: transposed butterfly over the channel lane bits
 #pragma unroll
         for (int ov = S, ol = 16; ov >= 1; ov >>= 1, ol >>= 1) {
           const bool up = (lane & ol) != 0;
@@ -316,7 +317,19 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
         my_acc[r * 2 * kN] = red[0];  // this warp's own accumulator row: no atomics
       }
     }
-    // rows past the end of the sequence: keep the output tiles defined (the TMA store clips them anyway)
+    __syncthreads();
+
+    // ---- epilogue (elementwise, every lane busy): ddelta = (u s1 + s2) softplus', du = dy D + dt s1, dz = dzc (y + D u)
+    for (int e = tid; e < TT * CH; e += NT) {
+      const float4 w = w4[e];
+      const float s1v = w_s1[e];
+      const float dd = fmaf(w.y, s1v, w_s2[e]) * w_sg[e];
+      dbias += dd;
+      dD = fmaf(w.z, w.y, dD);
+      o_du[e] = from_f32<T>(fmaf(w.z, De, w.x * s1v));
+      o_dd[e] = from_f32<T>(dd);
+      o_dz[e] = from_f32<T>(w_dzc[e] * fmaf(De, w.y, w_y[e]));
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -338,15 +351,13 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   if (tid == 0) bulk_wait0();
 #pragma unroll
   for (int n = 0; n < S; ++n) atomicAdd(p.dA + (long)(c0 + c) * kN + sub * S + n, dA[n]);
-  if (sub == 0) {
-    if (p.dD) atomicAdd(p.dD + c0 + c, dD);
-    if (p.ddbias) atomicAdd(p.ddbias + c0 + c, dbias);
-  }
+  if (p.dD) atomicAdd(p.dD + c0 + ce, dD);
+  if (p.ddbias) atomicAdd(p.ddbias + c0 + ce, dbias);
 }
 
-template <typename T, int CH>
+template <typename T, int CH, int LPC>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = BwdCfg<T, CH>;
+  using Cfg = BwdCfg<T, CH, LPC>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
@@ -387,7 +398,10 @@ int selective_scan_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
     SIM_REQUIRE(aligned16(ptrs[i]) && (lds[i] * es) % 16 == 0, SIM_ERR_ALIGN,
                 "selective_scan_bwd: tensor %d needs a 16-byte aligned base and row stride (TMA tensor maps)", i);
   }
-  return dtype == 0 ? launch_bwd<float, 32>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32>(p, dtype, stream);
+  static const int lpc = [] { const char* e = getenv("SIM_SCAN_BWD_LPC"); return e ? atoi(e) : 4; }();  // bench override
+  if (lpc == 4)
+    return dtype == 0 ? launch_bwd<float, 32, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4>(p, dtype, stream);
+  return dtype == 0 ? launch_bwd<float, 32, 2>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 2>(p, dtype, stream);
 }
 
 }  // namespace sim
