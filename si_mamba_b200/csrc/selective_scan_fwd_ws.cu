@@ -28,8 +28,9 @@ namespace sim {
 
 namespace {
 
-template <typename T, int S_, int CH_, int NS_, int POLY_, int EP_ = 0, int NE_ = 128>
+template <typename T, int S_, int CH_, int NS_, int POLY_, int EP_ = 0, int NOBF_ = 0, int NE_ = 128>
 struct ScanWsCfg {
+  static constexpr int NOBF = NOBF_;       // 1: recurrence lanes store their partial <h, C> sums, the elementwise warps add them
   static constexpr int MINB = (CH_ * (kNState / S_) + NE_) * 3 <= 1152 ? 3 : 1;  // aim at 3 resident CTAs per SM
   static constexpr int EP = EP_;           // 1: the exps of softplus / silu in the elementwise warps run on the FMA pipe too
   static constexpr int S = S_;
@@ -50,7 +51,8 @@ struct ScanWsCfg {
   static constexpr int WORK_DT = TT * CH_ * 8;
   static constexpr int WORK_BC = TT * kNState * 4;
   static constexpr int WORK = WORK_DT + 2 * WORK_BC;
-  static constexpr int YBUF = TT * CH_ * 6;  // fp32 <h, C> sums (4 B) / results in place, or three bf16 result planes (6 B)
+  // fp32 <h, C> sums (4 B, or 4 B per lane of a channel without the butterfly) / results in place, or three bf16 planes
+  static constexpr int YBUF = NOBF_ ? (TT * CH_ * 4 * (kNState / S_) > TT * CH_ * 6 ? TT * CH_ * 4 * (kNState / S_) : TT * CH_ * 6) : TT * CH_ * 6;
   static constexpr int SMEM = NS_ * RAW_STAGE + 2 * WORK + 2 * YBUF + (NS_ + 4) * 8 + 16;
   static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && WORK % 128 == 0 && YBUF % 128 == 0,
                 "TMA tiles must stay 128-B aligned");
@@ -246,12 +248,25 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
           const int r = r0 + i * RPP;
-          const float4 y = *reinterpret_cast<const float4*>(yb + r * CH + cc);
+          float4 y;
+          if constexpr (Cfg::NOBF) {
+            const float* yp = yb + (r * CH + cc) * LPC;  // LPC partial sums per channel, channel-major
+            float acc4[4];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              acc4[c4] = 0.f;
+#pragma unroll
+              for (int l = 0; l < LPC; ++l) acc4[c4] += yp[c4 * LPC + l];
+            }
+            y = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
+          } else {
+            y = *reinterpret_cast<const float4*>(yb + r * CH + cc);
+          }
           o[i] = make_float4((y.x + du[q][i].x) * gate[q][i].x, (y.y + du[q][i].y) * gate[q][i].y,
                              (y.z + du[q][i].z) * gate[q][i].z, (y.w + du[q][i].w) * gate[q][i].w);
         }
         const bool split = p.out_planes != nullptr;
-        if (sizeof(T) != 4 || split) bar_sync(2, NE);  // narrower outputs overlap other threads' fp32 sums
+        if (sizeof(T) != 4 || split || Cfg::NOBF) bar_sync(2, NE);  // the outputs overlap other threads' fp32 sums
         if (split) {
           // out_proj operand: three bf16 planes, each a dense (TT, CH) tile
 #pragma unroll
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
       const float2* w_dt = reinterpret_cast<const float2*>(wk) + ch;
       const float* w_B = reinterpret_cast<const float*>(wk + Cfg::WORK_DT) + sub * S;
       const float* w_C = w_B + TT * kNState;
-      float* yb = reinterpret_cast<float*>(ybuf + par * Cfg::YBUF) + ch;
+      float* yb = reinterpret_cast<float*>(ybuf + par * Cfg::YBUF) + (Cfg::NOBF ? ch * LPC + sub : ch);
       mbar_wait(&ready[par], (k / 2) & 1);
       float part[LPC];
 #pragma unroll
@@ -321,7 +336,12 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
           h[j] = __ffma2_rn(a, h[j], bu);
           acc[j & 1] = __ffma2_rn(h[j], make_float2(Cv[2 * j], Cv[2 * j + 1]), acc[j & 1]);
         }
-        part[t % LPC] = (acc[0].x + acc[1].x) + (acc[0].y + acc[1].y);
+        const float2 acc01 = __fadd2_rn(acc[0], acc[1]);
+        if constexpr (Cfg::NOBF) {
+          yb[t * CH * LPC] = acc01.x + acc01.y;
+          continue;
+        }
+        part[t % LPC] = acc01.x + acc01.y;
         if ((t + 1) % LPC == 0) {
           // transposed butterfly: lane `sub` ends with the full sum of step t + 1 - LPC + sub, and stores it
 #pragma unroll
@@ -343,9 +363,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
   }
 }
 
-template <typename T, int S, int CH, int NS, int POLY, int EP = 0>
+template <typename T, int S, int CH, int NS, int POLY, int EP = 0, int NOBF = 0>
 int launch_scan_ws(const ScanParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = ScanWsCfg<T, S, CH, NS, POLY, EP>;
+  using Cfg = ScanWsCfg<T, S, CH, NS, POLY, EP, NOBF>;
   constexpr int TT = Cfg::TT;
   auto kern = selective_scan_fwd_ws_kernel<Cfg, T>;
   static SmemAttrCache attr;
@@ -393,6 +413,9 @@ int dispatch_ws(const ScanParams& p, int dtype, int variant, cudaStream_t stream
     case 5104: return launch_scan_ws<T, 4, 64, 3, 1>(p, dtype, stream);
     case 5116: return launch_scan_ws<T, 16, 64, 3, 1>(p, dtype, stream);
     case 5216: return launch_scan_ws<T, 16, 64, 3, 2>(p, dtype, stream);
+    case 5508: return launch_scan_ws<T, 8, 64, 2, 0>(p, dtype, stream);
+    case 8008: return launch_scan_ws<T, 8, 64, 2, 0, 0, 1>(p, dtype, stream);
+    case 8004: return launch_scan_ws<T, 4, 64, 2, 0, 0, 1>(p, dtype, stream);
     case 7008: return launch_scan_ws<T, 8, 64, 3, 0, 1>(p, dtype, stream);
     case 7108: return launch_scan_ws<T, 8, 64, 3, 1, 1>(p, dtype, stream);
     case 7208: return launch_scan_ws<T, 8, 64, 3, 2, 1>(p, dtype, stream);

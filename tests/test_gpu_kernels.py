@@ -232,7 +232,7 @@ def test_scan_conv_golden(ops, golden, case):
 
 @pytest.mark.parametrize("variant", [0, 102, 104, 108, 116, 202, 204, 208, 216, 402, 404, 408,
                                      1002, 1004, 1008, 1016, 1104, 1108,
-                                     5004, 5008, 5016, 5104, 5108, 5208, 5116, 5216, 6008, 6108])
+                                     5004, 5008, 5016, 5104, 5108, 5208, 5116, 5216, 6008, 6108, 5508, 8008, 8004])
 @pytest.mark.parametrize("B,D,L", [(2, 768, 512), (1, 128, 1), (3, 64, 37), (1, 192, 1024)])
 def test_scan_vs_oracle_fp32(ops, variant, B, D, L):
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 10 * L + D)
@@ -264,7 +264,7 @@ def test_scan_optional_args_and_slices(ops):
     assert rel_err(out.cpu().transpose(1, 2), ref) < 1e-4
 
 
-@pytest.mark.parametrize("variant", [0, 108, 1008, 5008, 5108, 6008])
+@pytest.mark.parametrize("variant", [0, 108, 1008, 5008, 5108, 6008, 8008])
 def test_scan_bf16(ops, variant):
     B, D, L = 2, 256, 300
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 5)
