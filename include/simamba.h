@@ -218,6 +218,16 @@ int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, l
                                   const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec,
                                   const void* z, long ld_z, const float* delta_bias, void* out_planes, long ld_planes,
                                   long plane, int batch, int L, int D, int N, int delta_softplus, sim_stream_t stream);
+/* a-10 + a-11 fused: the selective scan with dt_proj computed in-kernel.  x_dbl = the x_proj output rows
+ * (dt_low[dt_rank = 24] | B[16] | C[16], row stride ld_x); wdt_planes = dt_proj.weight as bf16 planes, K zero-padded to 32:
+ * (3, D, 32) from sim_split3_bf16 for fp32 activations, (1, D, 32) for bf16.  delta = dt_low . W_dt^T never touches HBM
+ * (mma.sync in the kernel's elementwise warps; 3 x bf16 split with fp32 accumulation for fp32 activations).  Exactly one of
+ * out / out_planes is written (out_planes: fp32 activations only, see sim_selective_scan_fwd_split3).  Inference only. */
+int sim_selective_scan_fwd_fused_dt(const void* u, long ld_u, const void* x_dbl, long ld_x, int dt_rank,
+                                    const void* wdt_planes, const float* A, const float* Dvec, const void* z, long ld_z,
+                                    const float* delta_bias, void* out, long ld_out, void* out_planes, long ld_planes,
+                                    long plane, int batch, int L, int D, int N, int delta_softplus, int dtype,
+                                    sim_stream_t stream);
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
                     int M, int N, int K, sim_stream_t stream);

@@ -139,6 +139,26 @@ int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, l
   return sim::selective_scan_fwd(p, 0, 0, static_cast<cudaStream_t>(stream));
 }
 
+int sim_selective_scan_fwd_fused_dt(const void* u, long ld_u, const void* x_dbl, long ld_x, int dt_rank,
+                                    const void* wdt_planes, const float* A, const float* Dvec, const void* z, long ld_z,
+                                    const float* delta_bias, void* out, long ld_out, void* out_planes, long ld_planes,
+                                    long plane, int batch, int L, int D, int N, int delta_softplus, int dtype,
+                                    sim_stream_t stream) {
+  if (N != 16 || dt_rank != 24) {
+    sim::set_error("sim_selective_scan_fwd_fused_dt: built for d_state 16 and dt_rank 24 (got %d, %d)", N, dt_rank);
+    return SIM_ERR_INVALID;
+  }
+  sim::ScanParams p;
+  p.u = u, p.delta = x_dbl, p.z = z, p.Bm = nullptr, p.Cm = nullptr, p.out = out;
+  p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
+  p.ld_u = ld_u, p.ld_delta = ld_x, p.ld_z = ld_z, p.ld_B = 0, p.ld_C = 0, p.ld_out = ld_out;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  p.ckpt = nullptr;
+  p.out_planes = out_planes, p.ld_planes = ld_planes, p.plane = plane;
+  p.wdt = wdt_planes;
+  return sim::selective_scan_fwd(p, dtype, 0, static_cast<cudaStream_t>(stream));
+}
+
 int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
                              float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
                              sim_stream_t stream) {

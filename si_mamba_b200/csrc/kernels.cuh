@@ -35,6 +35,10 @@ struct ScanParams {
   // (operand format of gemm_split3.cu: out_proj consumes it directly); plane q at out_planes + q * plane elements
   void* out_planes = nullptr;
   long ld_planes = 0, plane = 0;
+  // optional (warp-specialised kernel): fused dt_proj.  `delta` then points at the x_proj output rows
+  // (dt_low[24] | B[16] | C[16], row stride ld_delta; Bm / Cm unused) and wdt at the bf16 planes of dt_proj.weight,
+  // (3, D, 32) for fp32 activations / (1, D, 32) for bf16, K zero-padded from 24 to 32
+  const void* wdt = nullptr;
 };
 constexpr int kScanTile = 16;  // time steps per tile of the scan kernels == checkpoint interval
 int selective_scan_fwd(const ScanParams&, int, int, cudaStream_t);

@@ -532,8 +532,11 @@ int selective_scan_fwd(const ScanParams& p, int dtype, int variant, cudaStream_t
   const int es = dtype == 0 ? 4 : 2;
   SIM_REQUIRE(dtype == 0 || dtype == 1, SIM_ERR_INVALID, "selective_scan_fwd: dtype must be 0 (fp32) or 1 (bf16)");
   SIM_REQUIRE(p.batch > 0 && p.L > 0 && p.D > 0, SIM_ERR_INVALID, "selective_scan_fwd: empty problem");
-  SIM_REQUIRE(p.u && p.delta && p.Bm && p.Cm && (p.out || p.out_planes) && p.A, SIM_ERR_INVALID,
+  SIM_REQUIRE(p.u && p.delta && (p.wdt || (p.Bm && p.Cm)) && (p.out || p.out_planes) && p.A, SIM_ERR_INVALID,
               "selective_scan_fwd: null tensor");
+  SIM_REQUIRE(!p.wdt || (p.D % 64 == 0 && aligned16(p.wdt) && !p.ckpt), SIM_ERR_INVALID,
+              "selective_scan_fwd: fused dt_proj needs D %% 64 == 0, 16-byte aligned weight planes and no checkpoints");
+  if (p.wdt) variant = 5900;
   SIM_REQUIRE(!p.out_planes || (dtype == 0 && p.D % 64 == 0 && (variant == 0 || variant >= 5000) && aligned16(p.out_planes) &&
                                 p.ld_planes % 8 == 0 && p.plane % 8 == 0),
               SIM_ERR_INVALID, "selective_scan_fwd: split-plane output needs fp32 activations, D %% 64 == 0 and 16-byte aligned planes");

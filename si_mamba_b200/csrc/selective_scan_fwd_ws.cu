@@ -28,8 +28,19 @@ namespace sim {
 
 namespace {
 
-template <typename T, int S_, int CH_, int NS_, int POLY_, int EP_ = 0, int NOBF_ = 0, int NE_ = 128>
+constexpr int kDtK = 24;  // dt_rank of the x_proj output row the fused kernel consumes (d_model 384 -> dt_rank 24)
+
+// D (16x8 fp32) += A (16x16 bf16, row) . B (16x8 bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <typename T, int S_, int CH_, int NS_, int POLY_, int EP_ = 0, int NOBF_ = 0, int FUSE_ = 0, int NE_ = 128>
 struct ScanWsCfg {
+  static constexpr int FUSE = FUSE_;       // 1: delta = W_dt . x_dbl[:, :dt_rank] is computed in the elementwise warps (mma.sync)
   static constexpr int NOBF = NOBF_;       // 1: recurrence lanes store their partial <h, C> sums, the elementwise warps add them
   static constexpr int MINB = (CH_ * (kNState / S_) + NE_) * 3 <= 1152 ? 3 : 1;  // aim at 3 resident CTAs per SM
   static constexpr int EP = EP_;           // 1: the exps of softplus / silu in the elementwise warps run on the FMA pipe too
@@ -47,15 +58,22 @@ struct ScanWsCfg {
   static constexpr int GPT = TT / RPP;     // float4 groups per elementwise thread and tile
   static constexpr int RAW_MAIN = TT * CH_ * (int)sizeof(T);
   static constexpr int RAW_BC = TT * kNState * (int)sizeof(T);
-  static constexpr int RAW_STAGE = 3 * RAW_MAIN + 2 * RAW_BC;
+  static constexpr int XW = kDtK + 2 * kNState;                    // columns of the x_proj output row: dt_low | B | C
+  static constexpr int RAW_X = TT * XW * (int)sizeof(T);            // fused: one tile of x_dbl rows instead of delta, B, C
+  static constexpr int RAW_STAGE = FUSE_ ? 2 * RAW_MAIN + RAW_X : 3 * RAW_MAIN + 2 * RAW_BC;
+  static constexpr int NPL = sizeof(T) == 4 ? 3 : 1;                // bf16 planes of an operand (fp32 -> 3, bf16 -> 1)
+  static constexpr int XS_LD = 40;                                  // padded row (bf16 elements) of the A-operand planes
+  static constexpr int FUSE_SMEM = FUSE_ ? NPL * TT * XS_LD * 2 + TT * CH_ * 4 : 0;  // A planes + fp32 delta tile
   static constexpr int WORK_DT = TT * CH_ * 8;
   static constexpr int WORK_BC = TT * kNState * 4;
   static constexpr int WORK = WORK_DT + 2 * WORK_BC;
   // fp32 <h, C> sums (4 B, or 4 B per lane of a channel without the butterfly) / results in place, or three bf16 planes
   static constexpr int YBUF = NOBF_ ? (TT * CH_ * 4 * (kNState / S_) > TT * CH_ * 6 ? TT * CH_ * 4 * (kNState / S_) : TT * CH_ * 6) : TT * CH_ * 6;
-  static constexpr int SMEM = NS_ * RAW_STAGE + 2 * WORK + 2 * YBUF + (NS_ + 4) * 8 + 16;
-  static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && WORK % 128 == 0 && YBUF % 128 == 0,
+  static constexpr int SMEM = NS_ * RAW_STAGE + 2 * WORK + 2 * YBUF + FUSE_SMEM + (NS_ + 4) * 8 + 16;
+  static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && WORK % 128 == 0 && YBUF % 128 == 0 &&
+                    RAW_X % 128 == 0 && FUSE_SMEM % 128 == 0,
                 "TMA tiles must stay 128-B aligned");
+  static_assert(!FUSE_ || (CH_ == 64 && NE_ == 128 && TT == 16), "fused dt_proj: 4 elementwise warps x 2 n-blocks of 8 channels");
   static_assert(NR % 32 == 0 && NE_ % 32 == 0 && NE_ % CQ == 0 && TT % RPP == 0 && GPT >= 1, "role split");
   static_assert(2 * TT * kNState / 4 <= NE_ * 4, "B / C widening loop");
   static_assert(POLY_ <= S_ / 2, "at most S/2 packed pairs");
@@ -138,7 +156,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
   unsigned char* raw = smem;
   unsigned char* work = smem + NS * Cfg::RAW_STAGE;
   unsigned char* ybuf = work + 2 * Cfg::WORK;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ybuf + 2 * Cfg::YBUF);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ybuf + 2 * Cfg::YBUF);               // [plane][TT][XS_LD]
+  float* sdt = reinterpret_cast<float*>(ybuf + 2 * Cfg::YBUF + Cfg::NPL * TT * Cfg::XS_LD * 2);  // [TT][CH] fp32 delta
+  uint64_t* full = reinterpret_cast<uint64_t*>(ybuf + 2 * Cfg::YBUF + Cfg::FUSE_SMEM);
   uint64_t* ready = full + NS;  // [2] work arrays of tile k are complete (NE arrivals)
   uint64_t* done = ready + 2;   // [2] <h, C> sums of tile k are in ybuf (one arrival per recurrence warp)
 
@@ -151,9 +171,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
 
   if (tid == NR) {
     tma_prefetch_desc(&tm.u);
-    tma_prefetch_desc(&tm.delta);
-    tma_prefetch_desc(&tm.B);
-    tma_prefetch_desc(&tm.C);
+    tma_prefetch_desc(&tm.delta);  // fused: the map of the x_dbl rows
+    if constexpr (!Cfg::FUSE) {
+      tma_prefetch_desc(&tm.B);
+      tma_prefetch_desc(&tm.C);
+    }
     if (p.out_planes) {
       for (int q = 0; q < 3; ++q) tma_prefetch_desc(&ptm.p[q]);
     } else {
@@ -176,12 +198,19 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
       const int s = tile % NS;
       const int t0 = tile * TT;
       unsigned char* st = raw + s * Cfg::RAW_STAGE;
-      mbar_arrive_expect_tx(&full[s], (has_z ? 3u : 2u) * Cfg::RAW_MAIN + 2u * Cfg::RAW_BC);
-      tma_load_3d(st, &tm.u, c0, t0, b, &full[s]);
-      tma_load_3d(st + Cfg::RAW_MAIN, &tm.delta, c0, t0, b, &full[s]);
-      if (has_z) tma_load_3d(st + 2 * Cfg::RAW_MAIN, &tm.z, c0, t0, b, &full[s]);
-      tma_load_3d(st + 3 * Cfg::RAW_MAIN, &tm.B, 0, t0, b, &full[s]);
-      tma_load_3d(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC, &tm.C, 0, t0, b, &full[s]);
+      if constexpr (Cfg::FUSE) {
+        mbar_arrive_expect_tx(&full[s], (has_z ? 2u : 1u) * Cfg::RAW_MAIN + Cfg::RAW_X);
+        tma_load_3d(st, &tm.u, c0, t0, b, &full[s]);
+        if (has_z) tma_load_3d(st + Cfg::RAW_MAIN, &tm.z, c0, t0, b, &full[s]);
+        tma_load_3d(st + 2 * Cfg::RAW_MAIN, &tm.delta, 0, t0, b, &full[s]);  // (dt_low | B | C) rows of x_dbl
+      } else {
+        mbar_arrive_expect_tx(&full[s], (has_z ? 3u : 2u) * Cfg::RAW_MAIN + 2u * Cfg::RAW_BC);
+        tma_load_3d(st, &tm.u, c0, t0, b, &full[s]);
+        tma_load_3d(st + Cfg::RAW_MAIN, &tm.delta, c0, t0, b, &full[s]);
+        if (has_z) tma_load_3d(st + 2 * Cfg::RAW_MAIN, &tm.z, c0, t0, b, &full[s]);
+        tma_load_3d(st + 3 * Cfg::RAW_MAIN, &tm.B, 0, t0, b, &full[s]);
+        tma_load_3d(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC, &tm.C, 0, t0, b, &full[s]);
+      }
     };
     if (te == 0) {
       for (int k = 0; k < NS && k < ntiles; ++k) issue_tile(k);
@@ -192,6 +221,74 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
     if (p.dbias) bias4 = *reinterpret_cast<const float4*>(p.dbias + c0 + cc);
     if (p.Dv) D4 = *reinterpret_cast<const float4*>(p.Dv + c0 + cc);
     float4 gate[2][GPT], du[2][GPT];
+    // fused dt_proj: warp `we` owns n-blocks 2 we, 2 we + 1 (8 channels each); its B fragments (W_dt rows of those
+    // channels, K padded to 32, NPL bf16 planes) stay in registers for the whole kernel
+    const int we = te >> 5, lg = (te & 31) >> 2, lt = te & 3;
+    uint32_t bw[2][Cfg::NPL][2][2];
+    if constexpr (Cfg::FUSE) {
+      const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(p.wdt);
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int pl = 0; pl < Cfg::NPL; ++pl)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const __nv_bfloat16* row = wp + ((long)pl * p.D + c0 + (2 * we + nb) * 8 + lg) * 32 + ks * 16 + 2 * lt;
+            bw[nb][pl][ks][0] = *reinterpret_cast<const uint32_t*>(row);
+            bw[nb][pl][ks][1] = *reinterpret_cast<const uint32_t*>(row + 8);
+          }
+    }
+
+    // delta tile of `tile` = dt_low . W_dt^T -> sdt (fused dt_proj).  Runs one tile AHEAD of the pre-pass that consumes it
+    // (after `ready` of the current tile has been signalled), so it never delays the recurrence warps.
+    auto compute_delta = [&](int tile) {
+      if constexpr (Cfg::FUSE) {
+          const int s_ = tile % NS;
+          mbar_wait(&full[s_], (tile / NS) & 1);
+          const T* sx = reinterpret_cast<const T*>(raw + s_ * Cfg::RAW_STAGE + 2 * Cfg::RAW_MAIN);
+          constexpr int XW = Cfg::XW, XL = Cfg::XS_LD;
+          // (a) A operand: the dt_low columns of the 16 rows as NPL bf16 planes [16][32] (K padded with zeros)
+          {
+            const int row = te >> 3, k0 = (te & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 < kDtK) v = lds4<T>(sx + row * XW + k0);
+            if constexpr (sizeof(T) == 4) {
+              split3_store4(xs + row * XL + k0, TT * XL, v);
+            } else {
+              sts_out4<__nv_bfloat16>(xs + row * XL + k0, v);
+            }
+          }
+          bar_sync(2, NE);
+          // (b) delta tile = x_low . W_dt^T on the tensor cores (mma.sync, fp32 accumulate); the six partial products
+          // of the 3 x bf16 split, smallest first (same scheme as gemm_split3.cu)
+          float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          constexpr int NPROD = Cfg::NPL == 3 ? 6 : 1;
+          constexpr int PA[6] = {0, 2, 1, 0, 1, 0}, PB[6] = {2, 0, 1, 1, 0, 0};
+#pragma unroll
+          for (int q = 0; q < NPROD; ++q) {
+            const int pa = Cfg::NPL == 3 ? PA[q] : 0, pb = Cfg::NPL == 3 ? PB[q] : 0;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const __nv_bfloat16* ap = xs + pa * TT * XL + ks * 16 + 2 * lt;
+              uint32_t a[4];
+              a[0] = *reinterpret_cast<const uint32_t*>(ap + lg * XL);
+              a[1] = *reinterpret_cast<const uint32_t*>(ap + (lg + 8) * XL);
+              a[2] = *reinterpret_cast<const uint32_t*>(ap + lg * XL + 8);
+              a[3] = *reinterpret_cast<const uint32_t*>(ap + (lg + 8) * XL + 8);
+              mma_bf16_16816(acc[0], a, bw[0][pb][ks]);
+              mma_bf16_16816(acc[1], a, bw[1][pb][ks]);
+            }
+          }
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            const int col = (2 * we + nb) * 8 + 2 * lt;
+            *reinterpret_cast<float2*>(sdt + lg * CH + col) = make_float2(acc[nb][0], acc[nb][1]);
+            *reinterpret_cast<float2*>(sdt + (lg + 8) * CH + col) = make_float2(acc[nb][2], acc[nb][3]);
+          }
+          bar_sync(2, NE);
+      }
+    };
+    if constexpr (Cfg::FUSE) compute_delta(0);
 
     auto body = [&](auto PAR, int k) {
       constexpr int par = decltype(PAR)::value;
@@ -200,8 +297,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
         unsigned char* st = raw + s * Cfg::RAW_STAGE;
         const T* su = reinterpret_cast<const T*>(st);
         const T* sd = reinterpret_cast<const T*>(st + Cfg::RAW_MAIN);
-        const T* sz = reinterpret_cast<const T*>(st + 2 * Cfg::RAW_MAIN);
+        const T* sz = reinterpret_cast<const T*>(st + (Cfg::FUSE ? 1 : 2) * Cfg::RAW_MAIN);
         const T* sB = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN);
+        const T* sx = reinterpret_cast<const T*>(st + 2 * Cfg::RAW_MAIN);  // fused: [TT][XW] rows of x_dbl
         unsigned char* wk = work + par * Cfg::WORK;
         float* w_dt = reinterpret_cast<float*>(wk);
         float* w_BC = reinterpret_cast<float*>(wk + Cfg::WORK_DT);
@@ -211,7 +309,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
           const int r = r0 + i * RPP;
-          float4 dv = lds4<T>(sd + r * CH + cc);
+          float4 dv = Cfg::FUSE ? *reinterpret_cast<const float4*>(sdt + r * CH + cc) : lds4<T>(sd + r * CH + cc);
           dv.x += bias4.x, dv.y += bias4.y, dv.z += bias4.z, dv.w += bias4.w;
           if (p.softplus) {
             if constexpr (Cfg::EP) dv = softplus4_poly(dv);
@@ -231,13 +329,23 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
           gate[par][i] = gv;
         }
         // B and C are adjacent in the raw stage and in the work arrays: widen both with one loop
-        for (int g = te; g < 2 * TT * kNState / 4; g += NE)
-          *reinterpret_cast<float4*>(w_BC + 4 * g) = lds4<T>(sB + 4 * g);
+        if constexpr (Cfg::FUSE) {
+          for (int g = te; g < 2 * TT * kNState / 4; g += NE) {  // B then C, [TT][16] each, from the x_dbl rows
+            const int which = g / (TT * kNState / 4), rr = (g % (TT * kNState / 4)) / (kNState / 4), c4 = (g % (kNState / 4)) * 4;
+            *reinterpret_cast<float4*>(w_BC + 4 * g) = lds4<T>(sx + rr * Cfg::XW + kDtK + which * kNState + c4);
+          }
+        } else {
+          for (int g = te; g < 2 * TT * kNState / 4; g += NE)
+            *reinterpret_cast<float4*>(w_BC + 4 * g) = lds4<T>(sB + 4 * g);
+        }
         // ybuf[par] is rewritten by the recurrence of tile k: the TMA store of tile k-2 must have read it
         if (te == 0) bulk_wait_read0();
         mbar_arrive(&ready[par]);
         bar_sync(1, NE);  // every elementwise thread has left raw stage s
         if (te == 0 && k + NS < ntiles) issue_tile(k + NS);
+        if constexpr (Cfg::FUSE) {
+          if (k + 1 < ntiles) compute_delta(k + 1);
+        }
       }
       if (k >= 1) {
         constexpr int q = par ^ 1;  // parity of tile j = k - 1
@@ -363,9 +471,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
   }
 }
 
-template <typename T, int S, int CH, int NS, int POLY, int EP = 0, int NOBF = 0>
+template <typename T, int S, int CH, int NS, int POLY, int EP = 0, int NOBF = 0, int FUSE = 0>
 int launch_scan_ws(const ScanParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = ScanWsCfg<T, S, CH, NS, POLY, EP, NOBF>;
+  using Cfg = ScanWsCfg<T, S, CH, NS, POLY, EP, NOBF, FUSE>;
   constexpr int TT = Cfg::TT;
   auto kern = selective_scan_fwd_ws_kernel<Cfg, T>;
   static SmemAttrCache attr;
@@ -373,14 +481,20 @@ int launch_scan_ws(const ScanParams& p, int dtype, cudaStream_t stream) {
   ScanTmaps tm;
   int rc;
   if ((rc = make_tmap_tokens(&tm.u, p.u, dtype, p.D, p.L, p.batch, p.ld_u, CH, TT))) return rc;
-  if ((rc = make_tmap_tokens(&tm.delta, p.delta, dtype, p.D, p.L, p.batch, p.ld_delta, CH, TT))) return rc;
   if (p.z) {
     if ((rc = make_tmap_tokens(&tm.z, p.z, dtype, p.D, p.L, p.batch, p.ld_z, CH, TT))) return rc;
   } else {
     tm.z = tm.u;
   }
-  if ((rc = make_tmap_tokens(&tm.B, p.Bm, dtype, kNState, p.L, p.batch, p.ld_B, kNState, TT))) return rc;
-  if ((rc = make_tmap_tokens(&tm.C, p.Cm, dtype, kNState, p.L, p.batch, p.ld_C, kNState, TT))) return rc;
+  if constexpr (FUSE) {
+    // `delta` is the x_proj output (rows of dt_low | B | C): one box of all its columns per tile
+    if ((rc = make_tmap_tokens(&tm.delta, p.delta, dtype, Cfg::XW, p.L, p.batch, p.ld_delta, Cfg::XW, TT))) return rc;
+    tm.B = tm.C = tm.delta;
+  } else {
+    if ((rc = make_tmap_tokens(&tm.delta, p.delta, dtype, p.D, p.L, p.batch, p.ld_delta, CH, TT))) return rc;
+    if ((rc = make_tmap_tokens(&tm.B, p.Bm, dtype, kNState, p.L, p.batch, p.ld_B, kNState, TT))) return rc;
+    if ((rc = make_tmap_tokens(&tm.C, p.Cm, dtype, kNState, p.L, p.batch, p.ld_C, kNState, TT))) return rc;
+  }
   PlaneTmaps ptm;
   if (p.out_planes) {
     if (dtype != 0) {
@@ -413,6 +527,7 @@ int dispatch_ws(const ScanParams& p, int dtype, int variant, cudaStream_t stream
     case 5104: return launch_scan_ws<T, 4, 64, 3, 1>(p, dtype, stream);
     case 5116: return launch_scan_ws<T, 16, 64, 3, 1>(p, dtype, stream);
     case 5216: return launch_scan_ws<T, 16, 64, 3, 2>(p, dtype, stream);
+    case 5900: return launch_scan_ws<T, 8, 64, 3, 0, 0, 0, 1>(p, dtype, stream);  // fused dt_proj
     case 5508: return launch_scan_ws<T, 8, 64, 2, 0>(p, dtype, stream);
     case 8008: return launch_scan_ws<T, 8, 64, 2, 0, 0, 1>(p, dtype, stream);
     case 8004: return launch_scan_ws<T, 4, 64, 2, 0, 0, 1>(p, dtype, stream);

@@ -567,6 +567,41 @@ def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delt
     return out
 
 
+def dt_proj_planes(w_dt: torch.Tensor, act_dtype: torch.dtype) -> torch.Tensor:
+    """dt_proj.weight (D, 24) -> the bf16 planes the fused scan consumes: (3, D, 32) for fp32 activations (3 x bf16 split),
+    (1, D, 32) for bf16; K zero-padded to 32."""
+    D, R = w_dt.shape
+    assert R <= 32
+    w32 = torch.zeros(D, 32, dtype=torch.float32, device=w_dt.device)
+    w32[:, :R] = w_dt.float()
+    if act_dtype == torch.float32:
+        return split3(w32)
+    return w32.to(torch.bfloat16).unsqueeze(0).contiguous()
+
+
+def selective_scan_fused_dt_tm(u, x_dbl, dt_rank: int, wdt_planes, A, D=None, z=None, delta_bias=None,
+                               delta_softplus=True, split: bool = False):
+    """Token-major selective scan with dt_proj fused in (inference): x_dbl (B,L,dt_rank+32) = x_proj output rows
+    (dt_low | B | C), wdt_planes from dt_proj_planes().  delta never touches HBM.  Returns out (B,L,D) or, with
+    ``split`` (fp32), the result as a Split3."""
+    _cuda(u, x_dbl, wdt_planes, A, D, z, delta_bias)
+    B, L, Dm = u.shape
+    N = A.shape[1]
+    assert x_dbl.shape[-1] == dt_rank + 2 * N and x_dbl.dtype == u.dtype and (z is None or z.dtype == u.dtype)
+    u, x_dbl, z = (_bulk_ok(t) for t in (u, x_dbl, z))
+    out = planes = None
+    if split:
+        assert u.dtype == torch.float32
+        planes = torch.empty(3, B * L, Dm, dtype=torch.bfloat16, device=u.device)
+    else:
+        out = torch.empty(B, L, Dm, dtype=u.dtype, device=u.device)
+    _lib.call("sim_selective_scan_fwd_fused_dt", _p(u), _tm(u), _p(x_dbl), _tm(x_dbl), int(dt_rank), _p(wdt_planes),
+              _p(_f32c(A)), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(out),
+              0 if out is None else _tm(out), _p(planes), 0 if planes is None else planes.stride(1),
+              0 if planes is None else planes.stride(0), B, L, Dm, N, int(delta_softplus), _dt(u), _stream())
+    return Split3(planes, (B, L, Dm)) if split else out
+
+
 def scan_checkpoint_shape(B: int, L: int, D: int):
     return (B, (L + 15) // 16, D, 16)
 

@@ -445,3 +445,25 @@ def test_add_layernorm_backward(ops, rows, C, ydt):
     for got, ref in zip(ins, ref_in):
         assert rel_err(got.grad.cpu().double(), ref.grad) < (2e-5 if ydt == torch.float32 else 2e-2)
     assert torch.equal(ins[0].grad, ins[1].grad)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,D,L", [(2, 768, 512), (3, 64, 37), (1, 128, 1)])
+def test_scan_fused_dt_proj(ops, dtype, tol, B, D, L):
+    """Scan with dt_proj computed in-kernel (mma.sync, 3 x bf16 split for fp32) vs GEMM-then-scan on the same inputs."""
+    g = torch.Generator().manual_seed(L + D)
+    u, z = torch.randn(B, L, D, generator=g), torch.randn(B, L, D, generator=g)
+    x_dbl = torch.randn(B, L, 56, generator=g)
+    w_dt = torch.randn(D, 24, generator=g) * 24 ** -0.5
+    A = -torch.arange(1, 17, dtype=torch.float32).repeat(D, 1) * (1 + 0.1 * torch.rand(D, 16, generator=g))
+    Dv, bias = torch.randn(D, generator=g), torch.randn(D, generator=g) - 4.0
+    cast = lambda t: dev(t.to(dtype))
+    uc, zc, xc = cast(u), cast(z), cast(x_dbl)
+    delta = (xc[..., :24].double() @ dev(w_dt).to(dtype).double().t()).to(dtype)   # exact dt_proj in the activation dtype
+    ref = ops.selective_scan_tm(uc, delta, dev(A), xc[..., 24:40], xc[..., 40:], dev(Dv), zc, dev(bias), True)
+    planes = ops.dt_proj_planes(dev(w_dt), dtype)
+    out = ops.selective_scan_fused_dt_tm(uc, xc, 24, planes, dev(A), dev(Dv), zc, dev(bias), True)
+    assert rel_err(out.float(), ref.float()) < tol
+    if dtype == torch.float32:
+        sp = ops.selective_scan_fused_dt_tm(uc, xc, 24, planes, dev(A), dev(Dv), zc, dev(bias), True, split=True)
+        assert torch.equal(sp.planes.float().sum(0).view(B, L, D), out)

@@ -43,6 +43,16 @@ def main():
         for i in range(a.iters):
             s = sets[i % 3]
             ops.selective_scan_tm(s[0], s[1], A, s[2], s[3], Dv, s[4], bias, True, out=s[5], variant=a.variant)
+    elif a.kernel == "scanfused":
+        sets = []
+        for _ in range(3):
+            sets.append((r(B, L, D).to(dt), r(B, L, 2 * D).to(dt)[..., D:], (0.3 * r(B, L, 56)).to(dt)))
+        A = -torch.arange(1, 17, device=dev, dtype=torch.float32).repeat(D, 1)
+        Dv, bias = torch.ones(D, device=dev), torch.full((D,), -4.0, device=dev)
+        planes = ops.dt_proj_planes(torch.randn(D, 24, device=dev) * 0.2, dt)
+        for i in range(a.iters):
+            s = sets[i % 3]
+            ops.selective_scan_fused_dt_tm(s[0], s[2], 24, planes, A, Dv, s[1], bias, True)
     elif a.kernel == "scanbwd":
         xz, u, dl, xd = r(B, L, 2 * D).to(dt), r(B, L, D).to(dt), (0.5 * r(B, L, D)).to(dt), r(B, L, 56).to(dt)
         dout = r(B, L, D).to(dt)
