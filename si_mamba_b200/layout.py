@@ -46,7 +46,18 @@ def mae_index_maps_torch(perm: torch.Tensor, mask: torch.Tensor):
                 perm_full=perm_full.int())
 
 
+_HLT_SLOTS = {}
+
+
 def hlt_slots(G: int, k: int, reverse: bool, device) -> torch.Tensor:
+    """Cached per (G, k, reverse, device): a constant of the layout (also keeps the forward CUDA-graph capturable)."""
+    key = (G, k, bool(reverse), str(device))
+    if key not in _HLT_SLOTS:
+        _HLT_SLOTS[key] = _hlt_slots(G, k, reverse, device)
+    return _HLT_SLOTS[key]
+
+
+def _hlt_slots(G: int, k: int, reverse: bool, device) -> torch.Tensor:
     """Rank (in the bucket-sorted order) shown at each of the 2G output slots, -1 = zero token.  The reference loop
     writes chunk i (c = 2^k tokens) at [(i+1)c, (i+2)c) for i >= 1 - over the previous chunk's reverse - and its
     reverse right after, so the net layout is [F0, R0, F1, F2, ..., F_last, R_last, zeros]."""

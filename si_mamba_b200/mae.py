@@ -29,6 +29,19 @@ def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return d.min(dim=2).values.mean(dim=1) + d.min(dim=1).values.mean(dim=1)
 
 
+def rand_mask_host(B: int, G: int, mask_ratio: float) -> torch.Tensor:
+    """models/point_mamba.py:2232-2255 ``_mask_center_rand``: per cloud a numpy shuffle of G-m zeros and m ones,
+    m = int(ratio * G).  Host tensor (B, G) bool; callers that capture the step in a CUDA graph copy it into a static
+    device tensor and pass it as ``bool_masked_pos``."""
+    m = int(mask_ratio * G)
+    out = np.zeros([B, G])
+    for i in range(B):
+        mask = np.hstack([np.zeros(G - m), np.ones(m)])
+        np.random.shuffle(mask)
+        out[i, :] = mask
+    return torch.from_numpy(out).to(torch.bool)
+
+
 def _init_trunc_normal(m):
     if isinstance(m, nn.Linear):
         nn.init.trunc_normal_(m.weight, std=.02)
@@ -78,7 +91,7 @@ class MaskMamba_2(nn.Module):
             overall_mask[i, :] = mask
         return torch.from_numpy(overall_mask).to(torch.bool).to(center.device)
 
-    def forward(self, neighborhood, center, perm, reverse=True, noaug=False, bool_masked_pos=None):
+    def forward(self, neighborhood, center, perm, reverse=True, noaug=False, bool_masked_pos=None, n_vis=None):
         """-> (x_vis (B, 2k*n_vis, C), maps) with ``maps`` the index maps of layout.mae_index_maps."""
         if not reverse:
             raise NotImplementedError("the MAE path is only defined for reverse=True (point_mamba.py:2778-2796)")
@@ -91,7 +104,7 @@ class MaskMamba_2(nn.Module):
         pos = self.pos_embed(center)
         G = center.shape[1]
         if user_mask:
-            n_vis = None  # counted from the caller's mask (host sync + validation)
+            pass  # the caller's n_vis, or None = counted from the mask (host sync + validation)
         elif noaug or self.mask_ratio == 0:
             n_vis = G
         else:
@@ -170,13 +183,13 @@ class Point_MAE_Mamba(nn.Module):
 
     def forward(self, pts, noaug=False, vis=False, tau=None, use_wavelets: bool = False, use_diff_sort: bool = False,
                 ret_policy: bool = False, ret_only_policy: bool = False, save_pts_dir: str = None, epoch: int = None,
-                bool_masked_pos=None, **kwargs):
+                bool_masked_pos=None, n_vis=None, **kwargs):
         """pts (B,N,3) -> scalar Chamfer-L2 loss (x_vis when ``noaug``)."""
         if use_wavelets or use_diff_sort or ret_only_policy:
             raise NotImplementedError("wavelet / learned-ordering branches are out of the hot-path scope")
         neighborhood, center, neighborhood_org = self.group_divider(pts)
         perm = self.spectral_order(center)["perm"]
-        x_vis, maps = self.MAE_encoder(neighborhood, center, perm, self.reverse, noaug, bool_masked_pos)
+        x_vis, maps = self.MAE_encoder(neighborhood, center, perm, self.reverse, noaug, bool_masked_pos, n_vis)
         if noaug:
             return x_vis
         B, _, C = x_vis.shape

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--configs", default="C2,C3,C4")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="capture forward + backward + optimizer of C3 in one CUDA graph "
+                    "(single GPU; the host-side random mask becomes a graph input)")
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     torch.cuda.set_device(local)
@@ -91,7 +93,23 @@ def main():
                 loss.backward()
                 torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
 
-            report("C2 scan-hardest finetune fwd+bwd bf16 (2048 pts, L=1024)", timed(step), B, dtype="bf16 autocast")
+            tag = ""
+            if args.graph and not ddp:
+                from si_mamba_b200.train import GraphedStep
+
+                def train_step():
+                    model.zero_grad(set_to_none=False)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        logits = model(pts)
+                    loss = torch.nn.functional.cross_entropy(logits.float(), label)
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+                    return loss
+
+                gs = GraphedStep(train_step)
+                step = gs.replay  # noqa: F811
+                tag = ", CUDA graph"
+            report("C2 scan-hardest finetune fwd+bwd bf16 (2048 pts, L=1024" + tag + ")", timed(step), B, dtype="bf16 autocast")
         elif name == "C3":
             cfg = sm.pretrain()
             B, N = 16, 1024
@@ -106,7 +124,33 @@ def main():
                 loss.backward()
                 opt.step()
 
-            report("C3 MAE pretrain step bf16 (1024 pts, mask 0.6, 12+4 layers, AdamW" + (", DDP" if ddp else "") + ")",
+            tag = ""
+            if args.graph and not ddp:
+                # the step at batch 16 is launch-bound in eager mode (11 ms of GPU work in a 23 ms step): capture it.
+                # The per-cloud random mask is drawn on the host exactly as the reference does (numpy shuffle) and
+                # copied into a static tensor before every replay.
+                from si_mamba_b200.mae import rand_mask_host
+                from si_mamba_b200.train import GraphedStep
+                opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, capturable=True)
+                G, ratio = cfg.num_group, cfg.transformer_config.mask_ratio
+                static_mask = rand_mask_host(B, G, ratio).to(dev)
+
+                def train_step():
+                    opt.zero_grad(set_to_none=False)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        loss = model(pts, bool_masked_pos=static_mask, n_vis=G - int(ratio * G))
+                    loss.backward()
+                    opt.step()
+                    return loss
+
+                gs = GraphedStep(train_step)
+
+                def step():  # noqa: F811
+                    static_mask.copy_(rand_mask_host(B, G, ratio), non_blocking=True)
+                    gs.replay()
+
+                tag = ", CUDA graph"
+            report("C3 MAE pretrain step bf16 (1024 pts, mask 0.6, 12+4 layers, AdamW" + (", DDP" if ddp else "") + tag + ")",
                    timed(step), B, dtype="bf16 autocast")
         elif name == "C4":
             for method in ("HLT", "SAST"):
@@ -124,7 +168,28 @@ def main():
                     loss = torch.nn.functional.nll_loss(out.reshape(-1, 50), target.reshape(-1))
                     loss.backward()
 
-                report(f"C4 part segmentation fwd+bwd fp32 (2048 pts, 128 patches, {method})", timed(step), B,
+                tag = ""
+                if args.graph and not ddp and os.environ.get("SIM_GRAPH_C4") == "1":  # off: see note below
+                    # torch 2.11 + cuDNN pick a 144 GiB workspace for the head's Conv1d backward under stream capture
+                    # (the same step needs 2 GiB eagerly), so C4 stays eager by default
+                    from si_mamba_b200.train import GraphedStep
+                    noise = torch.rand(B, 128, device=dev)  # HLT tie-break noise: a graph input
+
+                    def train_step(model=model, pts=pts, cls=cls, target=target, noise=noise):
+                        model.zero_grad(set_to_none=False)
+                        out = model(pts, cls, hlt_noise=noise)
+                        loss = torch.nn.functional.nll_loss(out.reshape(-1, 50), target.reshape(-1))
+                        loss.backward()
+                        return loss
+
+                    gs = GraphedStep(train_step)
+
+                    def step(gs=gs, noise=noise):  # noqa: F811
+                        noise.copy_(torch.rand(noise.shape), non_blocking=True)
+                        gs.replay()
+
+                    tag = ", CUDA graph"
+                report(f"C4 part segmentation fwd+bwd fp32 (2048 pts, 128 patches, {method}{tag})", timed(step), B,
                        dtype="fp32")
         else:
             raise SystemExit(f"unknown config {name}")
