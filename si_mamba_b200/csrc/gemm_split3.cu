@@ -39,7 +39,7 @@ struct GemmCfg {
   static constexpr int B_TILE = BN * kBK * 2;
   static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
-  static constexpr int MINB = (NSTAGE_ * STAGE + 2304) * 2 <= 232448 && 4 * BN <= 512 ? 2 : 1;  // CTAs per SM
+  static constexpr int MINB = (NSTAGE_ * STAGE + 2304) * 2 <= 232448 && 4 * BN <= 512 && BN != 192 ? 2 : 1;  // CTAs per SM
   static constexpr int STG_LD = 36;  // padded row stride (floats) of the epilogue staging tile: 16-B aligned, conflict-free
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
   static_assert(4 * 32 * STG_LD * 4 <= STAGE, "epilogue staging reuses pipeline stage 0");
@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
     mbar_init(accum_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);  // columns [0, BN): x0.w0, [BN, 2 BN): the five corrections
+  constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);  // power of two >= 2 BN
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);  // columns [0, BN): x0.w0, [BN, 2 BN): the five corrections
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, 2 * BN);
+    tmem_dealloc(tmem_d, kTmemCols);
   }
 }
 
@@ -292,11 +293,22 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
   SIM_REQUIRE(aligned16(Xs) && aligned16(Ws) && aligned16(Y) && ldx % 8 == 0 && ldw % 8 == 0 && xplane % 8 == 0 &&
                   wplane % 8 == 0 && ldd % 4 == 0 && N % 4 == 0,
               SIM_ERR_ALIGN, "gemm_bf16x3: TMA needs 16-byte aligned bases / strides, the epilogue N and ldd multiples of 4");
-  // widest tile that still gives every SM work; the two operand tiles of a stage share one tensor copy each
+  // tile width: the kernel time is (rounds of tiles over the SMs) x (tile cost), tile cost ~ bn + a fixed prologue /
+  // epilogue share (measured ~40 columns' worth); e.g. in_proj (128 x 1536 outputs per row block): bn 256 -> 6 rounds,
+  // 192 -> 7 rounds of 3/4 the cost, 128 -> 11 rounds
   const int m_tiles = (M + kBM - 1) / kBM;
-  int bn = N <= 64 ? 64 : ((N % 256 == 0 && (long)m_tiles * (N / 256) >= 2 * 148) ? 256 : 128);
+  int bn = 64;
+  if (N > 64) {
+    long best = -1;
+    for (int cand : {256, 192, 128}) {
+      const long tiles = (long)m_tiles * ((N + cand - 1) / cand);
+      const long cost = ((tiles + 147) / 148) * (cand + 40);
+      if (best < 0 || cost < best) best = cost, bn = cand;
+    }
+  }
   static const int force = [] { const char* e = getenv("SIM_GEMM_CFG"); return e ? atoi(e) : 0; }();  // bench-only override
   if (force == 128 || force == 1282) bn = N <= 64 ? 64 : 128;
+  if (force == 256 || force == 192 || force == 96) bn = N <= 64 ? 64 : force;
   // one or two k-blocks (dt_proj, K = 24): the tile is all prologue + epilogue, so prefer two co-resident CTAs per SM
   // that overlap each other's phases (measured 21.3 vs 27.3 us)
   const bool shallow = K <= 2 * kBK && N > 64;
@@ -309,6 +321,8 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
     case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream);
     case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream)
                                    : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream);
+    case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream);
+    case 192: return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream);
     default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream);
   }
 }

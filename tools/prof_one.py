@@ -43,6 +43,13 @@ def main():
         for i in range(a.iters):
             s = sets[i % 3]
             ops.selective_scan_tm(s[0], s[1], A, s[2], s[3], Dv, s[4], bias, True, out=s[5], variant=a.variant)
+    elif a.kernel == "gemm":
+        M, N, K = B * L, 1536, 384
+        xs = [ops.split3(r(M, K)) for _ in range(3)]
+        ws = ops.split3(r(N, K) * K ** -0.5)
+        outs = [torch.empty(M, N, device=dev) for _ in range(3)]
+        for i in range(a.iters):
+            ops.linear_split3(xs[i % 3], ws, K, out=outs[i % 3])
     elif a.kernel == "scanfused":
         sets = []
         for _ in range(3):
