@@ -46,6 +46,10 @@ struct GemmCfg {
   static_assert(A_TILE % 1024 == 0 && B_TILE % 512 == 0, "swizzle-64B tiles need 512-byte aligned bases");
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- PTX wrappers (tcgen05 / TMEM)
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -218,6 +222,163 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (large problems).  ncu on the one-tile-per-CTA kernel above: tensor pipe busy 65 % of the active
+// time and SMs active 82 % of the kernel - every tile pays barrier init, TMEM allocation, the first TMA round trip and
+// a TMEM -> registers -> staging -> global epilogue that nothing overlaps, because a 200 KB CTA has no co-resident CTA.
+// Here one CTA per SM walks tiles j, j + gridDim.x, ...: the smem pipeline keeps rolling across tiles, and EIGHT
+// epilogue warps (two per TMEM lane quadrant, half of the tile's columns each) first drain both accumulators into
+// registers (BN / 2 fp32 values per thread), release the accumulators to the MMA warp, and only then do the slow part
+// (staging + global stores) while the next tile's MMAs are already running.
+template <int BN, int NSTAGE_>
+struct GemmPCfg {
+  static constexpr int A_TILE = kBM * kBK * 2;
+  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int NEPI = 8;                      // epilogue warps
+  static constexpr int NT = 64 + 32 * NEPI;
+  static constexpr int STG_LD = 36;
+  static constexpr int STG = NEPI * 32 * STG_LD * 4;  // one 32 x 32 (padded) staging tile per epilogue warp
+  static constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
+  static constexpr int CW = BN / 2;                   // columns per epilogue warp
+  static_assert(CW % 32 == 0 && 2 * BN <= 512, "two column halves of whole 32-column chunks; both accumulators in TMEM");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int BN, int NSTAGE_>
+__global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
+    gemm_split3_persistent_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y, long ldd, int M, int N, int K,
+                                  int n_tiles, int total_tiles) {
+  using Cfg = GemmPCfg<BN, NSTAGE_>;
+  constexpr int NSTAGE = Cfg::NSTAGE, CW = Cfg::CW;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
+  float* stg_base = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE + Cfg::STG);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* acc_full = empty + NSTAGE;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = (K + kBK - 1) / kBK;
+  constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.x);
+    tma_prefetch_desc(&tm.w);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, Cfg::NEPI);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
+          unsigned char* st = smem + s * Cfg::STAGE;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+          tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
+          tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
+      constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+        if (i >= 1) {  // the epilogue warps have drained the previous tile's accumulators
+          mbar_wait(acc_empty, (i - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(&full[s], (it / NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
+          const uint32_t b0 = a0 + 3 * Cfg::A_TILE;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+#pragma unroll
+            for (int k = 0; k < kBK / kUK; ++k) {
+              const uint64_t da = umma_desc_sw64(a0 + PA[q] * Cfg::A_TILE + k * kUK * 2);
+              const uint64_t db = umma_desc_sw64(b0 + PB[q] * Cfg::B_TILE + k * kUK * 2);
+              umma_bf16(tmem_d + (q == 5 ? 0 : BN), da, db, idesc, q == 5 ? (kb | k) != 0 : (kb | q | k) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // epilogue warp ew: TMEM lanes [32 (warp % 4), +32), columns [half * CW, +CW)
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    float* stg = stg_base + ew * 32 * Cfg::STG_LD;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+      mbar_wait(acc_full, i & 1);
+      tc_fence_after();
+      float v[CW / 32][32];
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) {
+        float sm[32];
+        const uint32_t col = half * CW + c * 32;
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + col, v[c]);
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + BN + col, sm);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[c][e] += sm[e];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);  // the MMA warp may overwrite the accumulators: the rest overlaps its work
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) {
+        const int nc = n0 + half * CW + c * 32;
+        if (nc >= N) break;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          *reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + 4 * e) =
+              make_float4(v[c][4 * e], v[c][4 * e + 1], v[c][4 * e + 2], v[c][4 * e + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
+          const int gm = m0 + quad * 32 + row, gn = nc + col;
+          if (gm < M && gn < N)
+            *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, kTmemCols);
+  }
+}
+
 // 3-D map over the three bf16 planes of a row-major (rows, K) operand: dims (K, rows, 3), 64-byte swizzle.
 int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows) {
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
@@ -249,6 +410,23 @@ int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cu
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
   kern<<<m_tiles * n_tiles, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles);
   return check_launch("gemm_split3");
+}
+
+template <int BN, int NSTAGE>
+int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream) {
+  using Cfg = GemmPCfg<BN, NSTAGE>;
+  auto kern = gemm_split3_persistent_kernel<BN, NSTAGE>;
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 persistent attr");
+  static int sm_count[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < sm_count[dev & 63] ? total : sm_count[dev & 63];
+  kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total);
+  return check_launch("gemm_split3 persistent");
 }
 
 // x = x0 + x1 + x2 with every residual formed exactly in fp32 (the differences are representable)
@@ -322,7 +500,11 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
     case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream)
                                    : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream);
     case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream);
-    case 192: return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream);
+    case 192: {
+      static const int persist = [] { const char* e = getenv("SIM_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
+      if (persist && (long)m_tiles * ((N + 191) / 192) > 148) return launch_gemm_persistent<192, 3>(tm, Y, ldd, M, N, K, stream);
+      return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream);
+    }
     default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream);
   }
 }
