@@ -489,8 +489,10 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
   if (force == 256 || force == 192 || force == 96) bn = N <= 64 ? 64 : force;
   // one or two k-blocks (dt_proj, K = 24): the tile is all prologue + epilogue, so prefer two co-resident CTAs per SM
   // that overlap each other's phases (measured 21.3 vs 27.3 us)
-  const bool shallow = K <= 2 * kBK && N > 64;
+  static const int shallow_mode = [] { const char* e = getenv("SIM_GEMM_SHALLOW"); return e ? atoi(e) : 0; }();
+  const bool shallow = K <= 2 * kBK && N > 64 && shallow_mode == 0;
   if (shallow) bn = 128;
+  if (K <= 2 * kBK && N > 64 && shallow_mode == 1) bn = 192;
   GemmTmaps tm;
   int rc;
   if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
