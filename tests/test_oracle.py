@@ -174,3 +174,56 @@ def test_mae_restore_roundtrip(golden):
     assert torch.equal(full[~mfull], seq[~mfull])
     assert torch.equal(full[mfull], g["mask_token"].expand(int(mfull.sum()), -1))
     assert mae.gather_masked(full, mfull).shape[1] == 2 * perm.shape[1] * int(mask[0].sum())
+
+
+def test_fps_pointnet2_semantics():
+    """Restated pointnet2_ops furthest_point_sample: start index 0, points with |p|^2 <= 1e-3 are never
+    picked, selected indices are distinct while enough visitable points remain, and on exact duplicates the lower
+    upstream thread wins (index mod block size, then index)."""
+    xyz = tokenizer.synthetic_clouds(2, 300, 3, "ball")
+    xyz[:, 7] = 0.0
+    xyz[:, 8] = 0.01   # |p|^2 = 3e-4 <= 1e-3
+    idx = tokenizer.fps_pointnet2(xyz, 40)
+    assert idx.shape == (2, 40) and (idx[:, 0] == 0).all()
+    for b in range(2):
+        sel = idx[b].tolist()
+        assert len(set(sel)) == 40 and 7 not in sel and 8 not in sel
+    # brute-force re-check of every step in fp64 (well separated random points: no near-ties)
+    p = xyz[0].double()
+    ok = (p * p).sum(-1) > 1e-3
+    md = torch.full((300,), 1e10, dtype=torch.float64)
+    last = 0
+    for j in range(1, 40):
+        d = ((p - p[last]) ** 2).sum(-1)
+        md = torch.where(ok, torch.minimum(md, d), md)
+        last = int(torch.where(ok, md, torch.full_like(md, -1.0)).argmax())
+        assert last == idx[0, j]
+    # tie rule: 256 points duplicated once -> block size 512; a duplicate pair (i, i + 256) maps to threads i and
+    # i + 256, so the lower index wins; with 600 points (block 512) point 520 sits in thread 8 and beats point 9
+    dup = tokenizer.synthetic_clouds(1, 600, 5, "surface")
+    dup[0, 9] = dup[0, 520]
+    sel = tokenizer.fps_pointnet2(dup, 64)[0].tolist()
+    assert not (9 in sel and 520 in sel)
+    if 9 in sel or 520 in sel:
+        assert 520 in sel
+
+
+def test_mae_index_maps_torch_consistency():
+    """The torch restatement of the MAE layout maps (the GPU kernel's parity target) against the oracle's own
+    compaction / restore (models/point_mamba.py:2734-2796, 3147-3197)."""
+    from oracle import mae as omae
+    from si_mamba_b200 import layout
+    g = torch.Generator().manual_seed(1)
+    B, k, G, C = 2, 4, 64, 8
+    perm = torch.stack([torch.stack([torch.randperm(G, generator=g) for _ in range(k)]) for _ in range(B)])
+    mask = omae.rand_mask(B, G, 0.6, 3)
+    maps = layout.mae_index_maps_torch(perm, mask)
+    x = torch.randn(B, G, C, generator=g)
+    x_vis = torch.gather(x, 1, maps["src_vis"].long()[..., None].expand(-1, -1, C))
+    assert torch.equal(x_vis, omae.compact_visible(x, perm, mask))
+    assert torch.equal(maps["mask_full"], omae.mask_full(mask, perm))
+    rs = maps["restore_src"].long()
+    assert ((rs >= 0) == ~maps["mask_full"]).all()
+    for b in range(B):
+        vis_rows = rs[b][rs[b] >= 0]
+        assert torch.equal(vis_rows, torch.arange(vis_rows.numel()))  # visible rows appear in encoder order
