@@ -186,6 +186,18 @@ int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int
  * idx (B,npoint) i32, sampled (B,npoint,3). */
 int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, float* sampled, sim_stream_t stream);
 
+/* a-2 / a-14  row passes between the Encoder's library GEMMs and in the classification tail (inference):
+ * sim_group_max       out[g,c] = max over the M rows of group g of x (rows = groups*M, C)   (torch.max(feature, dim=2),
+ *                     models/point_mamba.py:66, 71);
+ * sim_group_bias_relu x[p,c] = relu(x[p,c] + gvec[p / M, c]) in place: the conv over cat([global, local]) (:67-69) split
+ *                     into a per-point and a per-patch GEMM, recombined here;
+ * sim_layernorm_mean  out[b,c] += mean over the L tokens of LayerNorm(x[b,t,:])[c] (self.norm(x).mean(1), :1122-1123;
+ *                     fp32, out zeroed by the caller). */
+int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream);
+int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, sim_stream_t stream);
+int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
+                       sim_stream_t stream);
+
 /* a-18  Chamfer-L2 of R pairs of small point sets, x (R,P,3), y (R,Q,3) fp32, P, Q <= 256:
  * loss[r] = mean_i min_j |x_i - y_j|^2 + mean_j min_i |x_i - y_j|^2  (pytorch3d chamfer_distance(x, y,
  * batch_reduction=None)[0], models/point_mamba.py:2950, 3199-3213).  idx_x (R,P) / idx_y (R,Q) receive the arg-mins

@@ -273,6 +273,19 @@ int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_ou
                                 static_cast<cudaStream_t>(stream));
 }
 
+int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream) {
+  return sim::group_max(x, out, groups, M, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, sim_stream_t stream) {
+  return sim::group_bias_relu(x, gvec, rows, M, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
+                       sim_stream_t stream) {
+  return sim::layernorm_mean(x, gamma, beta, out, B, L, C, eps, static_cast<cudaStream_t>(stream));
+}
+
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
   return sim::split3_bf16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
 }

@@ -107,6 +107,10 @@ int chamfer_l2_bwd(const float* x, const float* y, const int* idx_x, const int* 
                    int Q, float* dx, float* dy, cudaStream_t stream);
 int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, const float* gamma, float* dres,
                       float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream);
+int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream);
+int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream);
+int layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
+                   cudaStream_t stream);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream);

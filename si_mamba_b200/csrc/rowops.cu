@@ -281,6 +281,146 @@ int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, c
   return check_launch("add_layernorm_bwd");
 }
 
+// ----------------------------------------------------------------------------- Encoder / head glue (a-2, a-14)
+// The per-patch PointNet (Encoder.forward, models/point_mamba.py:59-73) stays on library GEMMs; these are the
+// row-granular passes between them, each one read + one write instead of ATen's add -> relu and generic reductions.
+//   group_max:        out[g, c] = max_{m < M} x[g*M + m, c]                     (torch.max(feature, dim=2))
+//   group_bias_relu:  x[p, c] = relu(x[p, c] + gvec[p / M, c])   in place         (cat([global, local]) conv, split)
+//   layernorm_mean:   out[b, c] = mean_t LN(x[b, t, :])[c]                       (self.norm(x).mean(1), :1122-1123)
+template <typename T>
+__global__ void __launch_bounds__(256) group_max_kernel(const T* __restrict__ x, T* __restrict__ out, long groups, int M,
+                                                        int C) {
+  const int nv = C / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * nv) return;
+  const long g = i / nv;
+  const int q = (int)(i % nv);
+  const T* p = x + (g * M) * C + 4 * q;
+  float4 m = ld4<T>(p);
+  for (int r = 1; r < M; ++r) {
+    const float4 v = ld4<T>(p + (long)r * C);
+    m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+  }
+  st4<T>(out + g * C + 4 * q, m);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) group_bias_relu_kernel(T* __restrict__ x, const T* __restrict__ gvec, long rows,
+                                                              int M, int C) {
+  const int nv = C / 4;
+  const long n = rows * nv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nv;
+    const int q = (int)(i % nv);
+    float4 v = ld4<T>(x + r * C + 4 * q);
+    const float4 b = ld4<T>(gvec + (r / M) * C + 4 * q);
+    v.x = fmaxf(v.x + b.x, 0.f), v.y = fmaxf(v.y + b.y, 0.f), v.z = fmaxf(v.z + b.z, 0.f), v.w = fmaxf(v.w + b.w, 0.f);
+    st4<T>(x + r * C + 4 * q, v);
+  }
+}
+
+// one warp per row as in add_layernorm; a CTA (8 warps) owns 8-row strides of ONE batch element's tokens and adds its
+// rows' normalised values into that element's mean with one shared-memory reduce + one atomic per column
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_mean_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ out,
+                                                             int L, int C, float eps, int ctas_per_batch) {
+  extern __shared__ float s_acc[];  // C
+  const int b = blockIdx.x / ctas_per_batch, part = blockIdx.x % ctas_per_batch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = C / 4;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float4 acc[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = part * 8 + warp; t < L; t += ctas_per_batch * 8) {
+    const float* row = x + ((long)b * L + t) * C;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int q = lane + 32 * i;
+      v[i] = q < nv ? *reinterpret_cast<const float4*>(row + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      acc[i].x += (v[i].x - mean) * rstd, acc[i].y += (v[i].y - mean) * rstd;
+      acc[i].z += (v[i].z - mean) * rstd, acc[i].w += (v[i].w - mean) * rstd;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nv) {
+      atomicAdd(s_acc + 4 * q, acc[i].x), atomicAdd(s_acc + 4 * q + 1, acc[i].y);
+      atomicAdd(s_acc + 4 * q + 2, acc[i].z), atomicAdd(s_acc + 4 * q + 3, acc[i].w);
+    }
+  }
+  __syncthreads();
+  // mean_t (xhat gamma + beta) = gamma * mean_t(xhat) + beta: the affine part is applied once per column
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    atomicAdd(out + (long)b * C + i, s_acc[i] * gamma[i] / (float)L + (part == 0 ? beta[i] : 0.f));
+}
+
+int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(x && out && groups > 0 && M > 0 && C > 0 && C % 4 == 0, SIM_ERR_INVALID, "group_max: bad arguments");
+  SIM_REQUIRE(aligned16(x) && aligned16(out), SIM_ERR_ALIGN, "group_max: tensors must be 16-byte aligned");
+  const long n = groups * (C / 4);
+  const int grid = (int)((n + 255) / 256);
+  if (dtype == 0)
+    group_max_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(out), groups, M, C);
+  else
+    group_max_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<__nv_bfloat16*>(out), groups, M, C);
+  return check_launch("group_max");
+}
+
+int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream) {
+  SIM_REQUIRE(x && gvec && rows > 0 && M > 0 && C > 0 && C % 4 == 0 && rows % M == 0, SIM_ERR_INVALID,
+              "group_bias_relu: bad arguments");
+  SIM_REQUIRE(aligned16(x) && aligned16(gvec), SIM_ERR_ALIGN, "group_bias_relu: tensors must be 16-byte aligned");
+  const long n = rows * (C / 4);
+  const int grid = (int)((n + 255) / 256 < 148L * 32 ? (n + 255) / 256 : 148L * 32);
+  if (dtype == 0)
+    group_bias_relu_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(x), static_cast<const float*>(gvec), rows, M, C);
+  else
+    group_bias_relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(x),
+                                                                    static_cast<const __nv_bfloat16*>(gvec), rows, M, C);
+  return check_launch("group_bias_relu");
+}
+
+int layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
+                   cudaStream_t stream) {
+  SIM_REQUIRE(x && gamma && beta && out && B > 0 && L > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
+              "layernorm_mean: bad arguments (C must be a multiple of 4, <= 1024)");
+  SIM_REQUIRE(aligned16(x), SIM_ERR_ALIGN, "layernorm_mean: x must be 16-byte aligned");
+  int per = (L + 7) / 8;
+  const int want = (148 * 4 + B - 1) / B;  // enough CTAs to fill the machine at small batch
+  if (per > want) per = want;
+  if (per < 1) per = 1;
+  const size_t smem = (size_t)C * sizeof(float);
+  if (C <= 384)
+    layernorm_mean_kernel<3><<<B * per, 256, smem, stream>>>(x, gamma, beta, out, L, C, eps, per);
+  else if (C <= 512)
+    layernorm_mean_kernel<4><<<B * per, 256, smem, stream>>>(x, gamma, beta, out, L, C, eps, per);
+  else
+    layernorm_mean_kernel<8><<<B * per, 256, smem, stream>>>(x, gamma, beta, out, L, C, eps, per);
+  return check_launch("layernorm_mean");
+}
+
 // ----------------------------------------------------------------------------- SAST order gather
 // out[b, s*G + r, :] = x[b, perm[b,s,r], :] (+ x2[...]) and, if reverse, the mirrored row
 // out[b, 2kG-1-(s*G+r), :] gets the same data: each source row is read once and written twice.

@@ -217,6 +217,36 @@ def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Ten
     return out
 
 
+# ----------------------------------------------------------------------------- Encoder / head glue (a-2, a-14)
+def group_max(x: torch.Tensor, M: int) -> torch.Tensor:
+    """x (groups*M, C) -> (groups, C): max over each group's M rows (forward only)."""
+    _cuda(x)
+    x = x.contiguous()
+    P, C = x.shape
+    out = torch.empty(P // M, C, dtype=x.dtype, device=x.device)
+    _lib.call("sim_group_max", _p(x), _p(out), P // M, M, C, _dt(x), _stream())
+    return out
+
+
+def group_bias_relu_(x: torch.Tensor, gvec: torch.Tensor, M: int) -> torch.Tensor:
+    """In place x[p] = relu(x[p] + gvec[p // M]) for x (groups*M, C), gvec (groups, C) (forward only)."""
+    _cuda(x, gvec)
+    assert x.is_contiguous() and gvec.is_contiguous() and x.dtype == gvec.dtype
+    P, C = x.shape
+    _lib.call("sim_group_bias_relu", _p(x), _p(gvec), P, M, C, _dt(x), _stream())
+    return x
+
+
+def layernorm_mean(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """mean over tokens of LayerNorm(x): x (B, L, C) fp32 -> (B, C) (forward only)."""
+    _cuda(x, weight, bias)
+    x = x.float().contiguous()
+    B, L, C = x.shape
+    out = torch.zeros(B, C, dtype=torch.float32, device=x.device)
+    _lib.call("sim_layernorm_mean", _p(x), _p(_f32c(weight)), _p(_f32c(bias)), _p(out), B, L, C, float(eps), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- Chamfer-L2 (a-18)
 class ChamferL2(torch.autograd.Function):
     """(R,P,3), (R,Q,3) fp32 -> (R,) pytorch3d chamfer_distance(..., batch_reduction=None)[0] (squared L2, mean over

@@ -72,9 +72,15 @@ class Encoder(nn.Module):
             w1, b1 = self._fold_bn(self.first_conv[0], self.first_conv[1])
             h = F.relu(F.linear(x, w1, b1))
             f = F.linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)          # (P, 256)
-            fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
             w3, b3 = self._fold_bn(self.second_conv[0], self.second_conv[1])
             c_loc = f.shape[-1]
+            if x.is_cuda and f.dtype in (torch.float32, torch.bfloat16):
+                # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
+                fg = ops.group_max(f, n)                                                            # (BG, 256)
+                h2 = ops.group_bias_relu_(F.linear(f, w3[:, c_loc:]), F.linear(fg, w3[:, :c_loc], b3), n)
+                o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)    # (P, C)
+                return ops.group_max(o, n).view(bs, g, self.encoder_channel)
+            fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
             t = F.linear(f, w3[:, c_loc:]).view(BG, n, -1) + F.linear(fg, w3[:, :c_loc], b3)[:, None, :]
             h2 = F.relu(t).view(P, -1)
             o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)        # (P, C)
@@ -357,8 +363,12 @@ class PointMamba(nn.Module):
             pos = ops.order_gather(pos, perm, reverse, inv)
             x = self.drop_out(x)
             x = self.blocks(x, pos)
-        x = self.norm(x)
-        concat_f = x[:, :].mean(1)
+        if (x.is_cuda and x.dtype == torch.float32 and isinstance(self.norm, nn.LayerNorm)
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.norm.weight.requires_grad))):
+            concat_f = ops.layernorm_mean(x, self.norm.weight, self.norm.bias, self.norm.eps)  # self.norm(x).mean(1), fused
+        else:
+            x = self.norm(x)
+            concat_f = x[:, :].mean(1)
         ret = self.cls_head_finetune(concat_f)
         if gt is not None:
             policy = torch.zeros((batch_size,), device=center.device, dtype=center.dtype)

@@ -467,3 +467,22 @@ def test_scan_fused_dt_proj(ops, dtype, tol, B, D, L):
     if dtype == torch.float32:
         sp = ops.selective_scan_fused_dt_tm(uc, xc, 24, planes, dev(A), dev(Dv), zc, dev(bias), True, split=True)
         assert torch.equal(sp.planes.float().sum(0).view(B, L, D), out)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_encoder_row_passes(ops, dtype):
+    """sim_group_max / sim_group_bias_relu / sim_layernorm_mean vs the torch expressions they replace."""
+    g = torch.Generator().manual_seed(9)
+    G, M, C = 37, 32, 256
+    x = torch.randn(G * M, C, generator=g).to(dtype)
+    assert torch.equal(ops.group_max(dev(x), M).cpu(), x.view(G, M, C).max(dim=1).values)
+    gv = torch.randn(G, C, generator=g).to(dtype)
+    ref = torch.relu((x.float().view(G, M, C) + gv.float()[:, None, :])).to(dtype).view(G * M, C)
+    got = ops.group_bias_relu_(dev(x.clone()), dev(gv), M).cpu()
+    assert torch.equal(got, ref)
+    if dtype == torch.float32:
+        B, L, Cn = 3, 77, 384
+        h = torch.randn(B, L, Cn, generator=g)
+        w, b = torch.randn(Cn, generator=g), torch.randn(Cn, generator=g)
+        refm = torch.nn.functional.layer_norm(h.double(), (Cn,), w.double(), b.double(), 1e-5).mean(1)
+        assert rel_err(ops.layernorm_mean(dev(h), dev(w), dev(b)).cpu().double(), refm) < 1e-5
