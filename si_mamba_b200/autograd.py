@@ -145,7 +145,15 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         planes = _CACHE.get(dt_proj_w, ("dtp", u.dtype), lambda t: ops.dt_proj_planes(t, u.dtype))
         y = ops.selective_scan_fused_dt_tm(u, x_dbl, dt_rank, planes, A, D, z, dt_proj_b, True, split=x3)
         return linear(y, w_out)
-    dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
+    if x3 and dt_rank <= 32 and x_dbl.shape[-1] >= 32:
+        # dt_proj with K padded to 32: a 64-byte row pitch is what the TMA tensor copies like (19.5 -> 13.6 us).  The
+        # padding columns of the weight are zero, so the operand is simply the first 32 columns of x_dbl (the extra 8 are
+        # B values that meet zero weights) - no padded copy of the activations is needed.
+        wdt32 = _CACHE.get(dt_proj_w, "x3_pad32",
+                           lambda t: ops.split3(F.pad(t.float(), (0, 32 - t.shape[1])).contiguous()))
+        dt = ops.linear_split3(ops.split3(x_dbl[..., :32]), wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
+    else:
+        dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]
     Cm = x_dbl[..., dt_rank + d_state:]
     if join_z is not None:
