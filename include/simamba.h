@@ -230,6 +230,12 @@ int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, l
                                   const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec,
                                   const void* z, long ld_z, const float* delta_bias, void* out_planes, long ld_planes,
                                   long plane, int batch, int L, int D, int N, int delta_softplus, sim_stream_t stream);
+/* sim_gemm_bf16x3 for N <= 64 (x_proj) that ALSO writes the first planes_cols output columns as split bf16 planes
+ * (row stride ld_p, plane stride `plane`): the operand of the dt_proj GEMM, without a separate split pass. */
+int sim_gemm_bf16x3_split_out(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y,
+                              long ldd, int M, int N, int K, void* planes_out, int planes_cols, long ld_p, long plane,
+                              sim_stream_t stream);
+
 /* a-10 + a-11 fused: the selective scan with dt_proj computed in-kernel.  x_dbl = the x_proj output rows
  * (dt_low[dt_rank = 24] | B[16] | C[16], row stride ld_x); wdt_planes = dt_proj.weight as bf16 planes, K zero-padded to 32:
  * (3, D, 32) from sim_split3_bf16 for fp32 activations, (1, D, 32) for bf16.  delta = dt_low . W_dt^T never touches HBM

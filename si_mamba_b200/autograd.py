@@ -138,7 +138,14 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         u, u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True, split=True)
     else:
         u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
-    x_dbl = linear(u_op, w_x)  # (B, L, dt_rank + 2*d_state)
+    dt_planes = None
+    if x3 and isinstance(u_op, ops.Split3) and dt_rank <= 32 and x_proj_w.shape[0] >= 32 and x_proj_w.shape[0] <= 64:
+        # x_proj whose epilogue also writes the dt_proj operand (split planes of the first 32 output columns)
+        wxp = _CACHE.get(x_proj_w, "x3", ops.split3)
+        x_dbl, dt_planes = ops.linear_split3_planes_out(u_op.planes, wxp, x_proj_w.shape[1], 32)
+        x_dbl = x_dbl.view(*u_op.shape[:-1], x_proj_w.shape[0])
+    else:
+        x_dbl = linear(u_op, w_x)  # (B, L, dt_rank + 2*d_state)
     if join_z is None and (not need_grad and _FUSE_DT and hidden.is_cuda and dt_rank == 24 and d_state == 16 and d_inner % 64 == 0
             and u.dtype in (torch.float32, torch.bfloat16) and x_dbl.dtype == u.dtype):
         # inference: dt_proj runs inside the scan kernel (mma.sync in its elementwise warps); delta never touches HBM
@@ -151,7 +158,9 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         # B values that meet zero weights) - no padded copy of the activations is needed.
         wdt32 = _CACHE.get(dt_proj_w, "x3_pad32",
                            lambda t: ops.split3(F.pad(t.float(), (0, 32 - t.shape[1])).contiguous()))
-        dt = ops.linear_split3(ops.split3(x_dbl[..., :32]), wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
+        if dt_planes is None:
+            dt_planes = ops.split3(x_dbl[..., :32])
+        dt = ops.linear_split3(dt_planes, wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
     else:
         dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
     Bm = x_dbl[..., dt_rank:dt_rank + d_state]

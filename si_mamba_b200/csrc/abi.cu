@@ -273,6 +273,13 @@ int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_ou
                                 static_cast<cudaStream_t>(stream));
 }
 
+int sim_gemm_bf16x3_split_out(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y,
+                              long ldd, int M, int N, int K, void* planes_out, int planes_cols, long ld_p, long plane,
+                              sim_stream_t stream) {
+  return sim::gemm_bf16x3(Xs, ldx, xplane, Ws, ldw, wplane, Y, ldd, M, N, K, static_cast<cudaStream_t>(stream), planes_out,
+                          planes_cols, ld_p, plane);
+}
+
 int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream) {
   return sim::group_max(x, out, groups, M, C, dtype, static_cast<cudaStream_t>(stream));
 }

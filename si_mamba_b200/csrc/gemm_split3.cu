@@ -114,7 +114,9 @@ struct GemmTmaps {
 
 template <int BN, int NSTAGE_>
 __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
-                                                             long ldd, int M, int N, int K, int n_tiles) {
+                                                             long ldd, int M, int N, int K, int n_tiles,
+                                                             __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
+                                                             long po_plane) {
   using Cfg = GemmCfg<BN, NSTAGE_>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
@@ -208,8 +210,13 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
       for (int rr = 0; rr < 8; ++rr) {
         const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
         const int gm = m0 + quad * 32 + row, gn = n0 + c * 32 + col;
-        if (gm < M && gn < N)
-          *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
+        if (gm < M && gn < N) {
+          const float4 o = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
+          *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = o;
+          // optionally also emit the first po_cols output columns as split bf16 planes: the operand of a GEMM that
+          // consumes them (x_proj -> dt_proj), saving a separate split pass
+          if (po && gn < po_cols) split3_store4(po + (long)gm * po_ld + gn, po_plane, o);
+        }
       }
       __syncwarp();
     }
@@ -402,13 +409,15 @@ int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld,
 }
 
 template <int BN, int NSTAGE>
-int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream) {
+int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream, void* po = nullptr,
+                int po_cols = 0, long po_ld = 0, long po_plane = 0) {
   using Cfg = GemmCfg<BN, NSTAGE>;
   auto kern = gemm_split3_kernel<BN, NSTAGE>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 attr");
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
-  kern<<<m_tiles * n_tiles, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles);
+  kern<<<m_tiles * n_tiles, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, static_cast<__nv_bfloat16*>(po), po_cols,
+                                                      po_ld, po_plane);
   return check_launch("gemm_split3");
 }
 
@@ -466,7 +475,10 @@ int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, l
 }
 
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
-                int N, int K, cudaStream_t stream) {
+                int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
+  SIM_REQUIRE(!po || (N <= 64 && po_cols % 4 == 0 && po_cols <= N + 3 && po_ld % 4 == 0 && po_plane % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(po) & 7u) == 0),
+              SIM_ERR_INVALID, "gemm_bf16x3: split-plane output is built for N <= 64 (x_proj) and 8-byte aligned planes");
   SIM_REQUIRE(Xs && Ws && Y && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_bf16x3: empty problem / null tensor");
   SIM_REQUIRE(aligned16(Xs) && aligned16(Ws) && aligned16(Y) && ldx % 8 == 0 && ldw % 8 == 0 && xplane % 8 == 0 &&
                   wplane % 8 == 0 && ldd % 4 == 0 && N % 4 == 0,
@@ -498,7 +510,7 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
   if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
   if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn))) return rc;
   switch (bn) {
-    case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream);
+    case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream, po, po_cols, po_ld, po_plane);
     case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream)
                                    : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream);
     case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream);

@@ -113,6 +113,6 @@ int layernorm_mean(const float* x, const float* gamma, const float* beta, float*
                    cudaStream_t stream);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
-                int N, int K, cudaStream_t stream);
+                int N, int K, cudaStream_t stream, void* po = nullptr, int po_cols = 0, long po_ld = 0, long po_plane = 0);
 
 }  // namespace sim

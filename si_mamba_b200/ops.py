@@ -493,6 +493,18 @@ def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torc
     return out
 
 
+def linear_split3_planes_out(xs: torch.Tensor, ws: torch.Tensor, K: int, planes_cols: int):
+    """linear_split3 for N <= 64 that also returns the first ``planes_cols`` output columns as split planes
+    (3, rows, planes_cols): y, planes."""
+    _cuda(xs, ws)
+    M, N = xs.shape[1], ws.shape[1]
+    out = torch.empty(M, N, dtype=torch.float32, device=xs.device)
+    planes = torch.empty(3, M, planes_cols, dtype=torch.bfloat16, device=xs.device)
+    _lib.call("sim_gemm_bf16x3_split_out", _p(xs), xs.stride(1), xs.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out),
+              out.stride(0), M, N, K, _p(planes), planes_cols, planes.stride(1), planes.stride(0), _stream())
+    return out, planes
+
+
 def linear_f32_x3(x, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
     """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is a Split3 from its producer, or an
     fp32 tensor that is split here."""

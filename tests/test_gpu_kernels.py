@@ -486,3 +486,14 @@ def test_encoder_row_passes(ops, dtype):
         w, b = torch.randn(Cn, generator=g), torch.randn(Cn, generator=g)
         refm = torch.nn.functional.layer_norm(h.double(), (Cn,), w.double(), b.double(), 1e-5).mean(1)
         assert rel_err(ops.layernorm_mean(dev(h), dev(w), dev(b)).cpu().double(), refm) < 1e-5
+
+
+def test_gemm_split_planes_out(ops):
+    """x_proj-shaped GEMM whose epilogue also emits the first 32 output columns as split planes."""
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 1000, 56, 768
+    xs, ws = ops.split3(dev(torch.randn(M, K, generator=g))), ops.split3(dev(torch.randn(N, K, generator=g) * K ** -0.5))
+    y = ops.linear_split3(xs, ws, K)
+    y2, planes = ops.linear_split3_planes_out(xs, ws, K, 32)
+    assert torch.equal(y, y2)
+    assert torch.equal(planes.float().sum(0), y[:, :32])
