@@ -11,7 +11,10 @@
 // segment, the only re-read is the (W-1)-row halo per chunk.
 // Roofline: HBM, algorithmic bytes 2*B*L*D*s forward, 3*B*L*D*s backward.
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace sim {
 
@@ -167,6 +170,158 @@ __global__ void __launch_bounds__(256) causal_conv1d_fwd_bf16x8_kernel(const __n
   }
 }
 
+// ----------------------------------------------------------------------------- forward through TMA tiles
+// The register-window kernels above are latency-bound at the C1 / C2 batch sizes (ncu, bf16: 2.6 warps per scheduler,
+// long-scoreboard stall 7.5 per issue, 0.26 of the HBM roofline): too few loads in flight.  Here a CTA owns 64 channels
+// of one cloud and walks L in 32-step tiles that arrive - WITH their 3-row causal halo, rows before the sequence
+// zero-filled by the TMA unit - through a 3-deep ring of tensor copies; four threads per channel convolve 8 rows each
+// out of shared memory, results leave through double-buffered output tiles and TMA tensor stores (fp32 results
+// optionally also as the three split bf16 planes of the x_proj operand).
+constexpr int kCvTT = 32, kCvNS = 3;
+
+struct ConvTmaps {
+  CUtensorMap x, y, p[3];
+};
+
+template <typename T>
+struct ConvTmaCfg {
+  static constexpr int CPT = 4 / (int)sizeof(T);        // channels per thread (one 32-bit word)
+  static constexpr int COLS = sizeof(T) == 4 ? 64 : 32; // four-byte columns per CTA: 64 fp32 / 64 bf16 channels (measured)
+  static constexpr int SEGS = 256 / COLS;               // row segments per tile (threads = COLS x SEGS = 256)
+  static constexpr int CH = COLS * CPT;                 // channels per CTA
+  static constexpr int IN_TILE = (kCvTT + kConvW - 1) * COLS * 4;
+  static constexpr int IN_STAGE = (IN_TILE + 127) / 128 * 128;
+  static constexpr int OUT_TILE = kCvTT * COLS * 4;
+  static constexpr int PL_TILE = kCvTT * COLS * 2;   // fp32 only: one bf16 plane of the 64 channels
+  static constexpr int OUT_BUF = OUT_TILE + (sizeof(T) == 4 ? 3 * PL_TILE : 0);
+  static constexpr int SMEM = kCvNS * IN_STAGE + 2 * OUT_BUF + kCvNS * 8 + 16;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) causal_conv1d_fwd_tma_kernel(const __grid_constant__ ConvTmaps tm,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, int L, int D, int silu,
+                                                                     int has_planes) {
+  using Cfg = ConvTmaCfg<T>;
+  constexpr int COLS = Cfg::COLS, CPT = Cfg::CPT, CH = Cfg::CH, TT = kCvTT, NS = kCvNS, HALO = kConvW - 1, RPS = kCvTT / Cfg::SEGS;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* obuf = smem + NS * Cfg::IN_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(obuf + 2 * Cfg::OUT_BUF);
+  const int tid = threadIdx.x;
+  const int nchunk = D / CH;
+  const int b = blockIdx.x / nchunk, c0 = (blockIdx.x % nchunk) * CH;
+  const int col = tid % COLS, seg = tid / COLS;  // SEGS row segments of RPS steps per column
+  const int ntiles = (L + TT - 1) / TT;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm.x);
+    tma_prefetch_desc(&tm.y);
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile) {
+    const int s = tile % NS;
+    mbar_arrive_expect_tx(&full[s], (TT + HALO) * COLS * 4);
+    tma_load_3d(smem + s * Cfg::IN_STAGE, &tm.x, c0, tile * TT - HALO, b, &full[s]);  // rows < 0: zero-filled
+  };
+  if (tid == 0)
+    for (int k = 0; k < NS && k < ntiles; ++k) issue(k);
+
+  float wt[CPT][kConvW], bv[CPT];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long)(c0 + col * CPT + q) * kConvW);
+    wt[q][0] = wv.x, wt[q][1] = wv.y, wt[q][2] = wv.z, wt[q][3] = wv.w;
+    bv[q] = bias ? bias[c0 + col * CPT + q] : 0.f;
+  }
+  // one 32-bit word of a tile row = this thread's CPT channels
+  auto unpack = [](uint32_t word, float (&v)[CPT]) {
+    if constexpr (CPT == 1) {
+      v[0] = __uint_as_float(word);
+    } else {
+      v[0] = __uint_as_float(word << 16), v[1] = __uint_as_float(word & 0xffff0000u);
+    }
+  };
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int s = tile % NS, ob = tile & 1;
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(smem + s * Cfg::IN_STAGE);  // [TT + 3][COLS], row i <-> t0 - 3 + i
+    uint32_t* out = reinterpret_cast<uint32_t*>(obuf + ob * Cfg::OUT_BUF);
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(obuf + ob * Cfg::OUT_BUF + Cfg::OUT_TILE);
+    mbar_wait(&full[s], (tile / NS) & 1);
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // output buffer `ob` (tile - 2) was read
+    __syncthreads();
+    const int r0 = seg * RPS;
+    float x0[CPT], x1[CPT], x2[CPT], x3[CPT];
+    unpack(in[(r0 + 0) * COLS + col], x0);
+    unpack(in[(r0 + 1) * COLS + col], x1);
+    unpack(in[(r0 + 2) * COLS + col], x2);
+#pragma unroll
+    for (int j = 0; j < RPS; ++j) {
+      unpack(in[(r0 + HALO + j) * COLS + col], x3);
+      float acc[CPT];
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        acc[q] = fmaf(wt[q][3], x3[q], fmaf(wt[q][2], x2[q], fmaf(wt[q][1], x1[q], fmaf(wt[q][0], x0[q], bv[q]))));
+        if (silu) acc[q] = silu_f(acc[q]);
+        x0[q] = x1[q], x1[q] = x2[q], x2[q] = x3[q];
+      }
+      if constexpr (CPT == 1) {
+        out[(r0 + j) * COLS + col] = __float_as_uint(acc[0]);
+        if (has_planes) {
+          const __nv_bfloat16 p0 = __float2bfloat16_rn(acc[0]);
+          const float r1 = acc[0] - __bfloat162float(p0);
+          const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+          pl[(r0 + j) * COLS + col] = p0;
+          pl[TT * COLS + (r0 + j) * COLS + col] = p1;
+          pl[2 * TT * COLS + (r0 + j) * COLS + col] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+        }
+      } else {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(acc[0], acc[1]);
+        out[(r0 + j) * COLS + col] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();  // the tile is complete; input stage s is free again
+    if (tid == 0) {
+      tma_store_3d(&tm.y, c0, tile * TT, b, out);  // rows past L are clipped
+      if (CPT == 1 && has_planes) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) tma_store_3d(&tm.p[q], c0, tile * TT, b, pl + q * TT * COLS);
+      }
+      bulk_commit();
+      if (tile + NS < ntiles) issue(tile + NS);
+    }
+  }
+  if (tid == 0) bulk_wait0();
+}
+
+template <typename T>
+int launch_conv_tma(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y, int batch, int L, int D,
+                    int silu, int dtype, void* planes, long ld_p, long plane, cudaStream_t stream) {
+  using Cfg = ConvTmaCfg<T>;
+  auto kern = causal_conv1d_fwd_tma_kernel<T>;
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("causal_conv1d_fwd_tma attr");
+  ConvTmaps tm;
+  int rc;
+  if ((rc = make_tmap_tokens(&tm.x, x, dtype, D, L, batch, ld_x, Cfg::CH, kCvTT + kConvW - 1))) return rc;
+  if ((rc = make_tmap_tokens(&tm.y, y, dtype, D, L, batch, ld_y, Cfg::CH, kCvTT))) return rc;
+  for (int q = 0; q < 3; ++q) {
+    if (planes) {
+      if ((rc = make_tmap_tokens(&tm.p[q], static_cast<__nv_bfloat16*>(planes) + q * plane, 1, D, L, batch, ld_p, Cfg::CH, kCvTT)))
+        return rc;
+    } else {
+      tm.p[q] = tm.y;
+    }
+  }
+  kern<<<batch * (D / Cfg::CH), 256, Cfg::SMEM, stream>>>(tm, w, bias, L, D, silu, planes != nullptr);
+  return check_launch("causal_conv1d_fwd_tma");
+}
+
+constexpr int kTcBf16 = 32, kTcF32 = 32, kTcF32Planes = 32;  // time steps per thread (see causal_conv1d_fwd)
+
 int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bias, void* y, long ld_y, int batch,
                       int L, int D, int width, int silu, int dtype, cudaStream_t stream, void* planes, long ld_p,
                       long plane) {
@@ -182,23 +337,40 @@ int causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float* bia
               SIM_ERR_ALIGN, "causal_conv1d_fwd: x/y/w/bias need 16-byte bases and vector-aligned row strides");
   // Time chunk per thread.  Shorter chunks (more threads, 3-row halo from L1/L2) measured no faster on B200:
   // fp32 22.2 us at TC=16 vs 22.5 at TC=32; bf16 27.3 us at TC=8 vs 23.1 at TC=32.
-  constexpr int TC = 32;
+  // SIM_CONV_TC (bench-only): time steps per thread.  Default chosen from the measurements in the comment above /
+  // profiles/r01_kernel_bench_all.jsonl.
+  static const int tc_env = [] { const char* e = getenv("SIM_CONV_TC"); return e ? atoi(e) : 0; }();
+  const int es_ = dtype == 0 ? 4 : 2;
+  if (tc_env == 0 && D % 64 == 0 && aligned16(x) && aligned16(y) && (ld_x * es_) % 16 == 0 && (ld_y * es_) % 16 == 0 &&
+      (!planes || (aligned16(planes) && ld_p % 8 == 0 && plane % 8 == 0))) {
+    return dtype == 0 ? launch_conv_tma<float>(x, ld_x, w, bias, y, ld_y, batch, L, D, silu, dtype, planes, ld_p, plane, stream)
+                      : launch_conv_tma<__nv_bfloat16>(x, ld_x, w, bias, y, ld_y, batch, L, D, silu, dtype, nullptr, 0, 0, stream);
+  }
   if (dtype == 1 && D % 8 == 0 && aligned16(x) && aligned16(y) && ld_x % 8 == 0 && ld_y % 8 == 0) {
-    constexpr int TC8 = 32;
-    const long items = (long)batch * ((L + TC8 - 1) / TC8) * (D / 8);
-    causal_conv1d_fwd_bf16x8_kernel<TC8><<<(int)((items + 255) / 256), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<__nv_bfloat16*>(y), ld_y, batch, L, D, silu);
+    const int tc = tc_env ? tc_env : kTcBf16;
+    const long items = (long)batch * ((L + tc - 1) / tc) * (D / 8);
+    const int grid8 = (int)((items + 255) / 256);
+    const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+    if (tc == 8) causal_conv1d_fwd_bf16x8_kernel<8><<<grid8, 256, 0, stream>>>(xb, ld_x, w, bias, yb, ld_y, batch, L, D, silu);
+    else if (tc == 16) causal_conv1d_fwd_bf16x8_kernel<16><<<grid8, 256, 0, stream>>>(xb, ld_x, w, bias, yb, ld_y, batch, L, D, silu);
+    else causal_conv1d_fwd_bf16x8_kernel<32><<<grid8, 256, 0, stream>>>(xb, ld_x, w, bias, yb, ld_y, batch, L, D, silu);
     return check_launch("causal_conv1d_fwd");
   }
-  const long items = (long)batch * ((L + TC - 1) / TC) * (D / 4);
+  const int tc = tc_env ? tc_env : (planes ? kTcF32Planes : kTcF32);
+  const long items = (long)batch * ((L + tc - 1) / tc) * (D / 4);
   const int grid = (int)((items + 255) / 256);
-  if (dtype == 0)
-    causal_conv1d_fwd_kernel<float, TC><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld_x, w, bias,
-                                                                  static_cast<float*>(y), ld_y, batch, L, D, silu,
-                                                                  static_cast<__nv_bfloat16*>(planes), ld_p, plane);
-  else
-    causal_conv1d_fwd_kernel<__nv_bfloat16, TC><<<grid, 256, 0, stream>>>(
+  if (dtype == 0) {
+    const float* xf = static_cast<const float*>(x);
+    float* yf = static_cast<float*>(y);
+    __nv_bfloat16* pp = static_cast<__nv_bfloat16*>(planes);
+    if (tc == 8) causal_conv1d_fwd_kernel<float, 8><<<grid, 256, 0, stream>>>(xf, ld_x, w, bias, yf, ld_y, batch, L, D, silu, pp, ld_p, plane);
+    else if (tc == 16) causal_conv1d_fwd_kernel<float, 16><<<grid, 256, 0, stream>>>(xf, ld_x, w, bias, yf, ld_y, batch, L, D, silu, pp, ld_p, plane);
+    else causal_conv1d_fwd_kernel<float, 32><<<grid, 256, 0, stream>>>(xf, ld_x, w, bias, yf, ld_y, batch, L, D, silu, pp, ld_p, plane);
+  } else {
+    causal_conv1d_fwd_kernel<__nv_bfloat16, 32><<<(int)(((long)batch * ((L + 31) / 32) * (D / 4) + 255) / 256), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<__nv_bfloat16*>(y), ld_y, batch, L, D, silu, nullptr, 0, 0);
+  }
   return check_launch("causal_conv1d_fwd");
 }
 
