@@ -36,6 +36,9 @@ class RMSNorm(nn.Module):
         return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight.float()).to(x.dtype)
 
 
+_ENCODER_ROWS = __import__("os").environ.get("SIM_ENCODER_ROWS", "1") != "0"
+
+
 class Encoder(nn.Module):
     """Per-patch mini-PointNet (models/point_mamba.py:42-73); dense contractions stay on cuDNN / cuBLAS."""
 
@@ -88,10 +91,36 @@ class Encoder(nn.Module):
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
+    def _forward_rows(self, point_groups):
+        """Differentiable form of forward() on the (B*G*M, C) point matrix: the 1x1 convolutions as row-major linears
+        (cuBLAS forward / dgrad / wgrad instead of cuDNN's NCHW wgrad reduction, which was 10 % of the C2 training step),
+        BatchNorm1d on the 2-D rows (same statistics and running buffers as on (N, C, L)), and the conv over
+        cat([global, local]) split into a per-point and a per-patch linear.  Same TF32 policy as the convolutions."""
+        bs, g, n, _ = point_groups.shape
+        BG, P = bs * g, bs * g * n
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            c0, bn0, c3 = self.first_conv[0], self.first_conv[1], self.first_conv[3]
+            d0, bn1, d3 = self.second_conv[0], self.second_conv[1], self.second_conv[3]
+            h = F.relu(bn0(F.linear(point_groups.reshape(P, 3), c0.weight[:, :, 0], c0.bias)))
+            f = F.linear(h, c3.weight[:, :, 0], c3.bias)                                            # (P, 256)
+            fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
+            c_loc = f.shape[-1]
+            w3 = d0.weight[:, :, 0]
+            t = F.linear(f, w3[:, c_loc:]).view(BG, n, -1) + F.linear(fg, w3[:, :c_loc], d0.bias)[:, None, :]
+            h2 = F.relu(bn1(t.reshape(P, -1)))
+            o = F.linear(h2, d3.weight[:, :, 0], d3.bias)                                           # (P, C)
+            return o.view(BG, n, -1).max(dim=1).values.view(bs, g, self.encoder_channel)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
     def forward(self, point_groups):
         """point_groups (B, G, M, 3) -> (B, G, C)."""
         if not self.training and not torch.is_grad_enabled():
             return self._forward_eval(point_groups)
+        if point_groups.is_cuda and _ENCODER_ROWS:
+            return self._forward_rows(point_groups)
         bs, g, n, _ = point_groups.shape
         point_groups = point_groups.reshape(bs * g, n, 3)
         feature = self.first_conv(point_groups.transpose(2, 1))

@@ -93,8 +93,11 @@ class PointNetFeaturePropagation(nn.Module):
             dists, idx = square_distance(xyz1, xyz2).topk(3, dim=-1, largest=False, sorted=True)
             dist_recip = 1.0 / (dists + 1e-8)
             weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
-            gathered = torch.gather(points2[:, None].expand(-1, N, -1, -1), 2,
-                                    idx[..., None].expand(-1, -1, -1, points2.shape[-1]))
+            # index_points (pointnet2_utils.py:41-57) as ONE gather along the S axis: its backward is a scatter-add into
+            # (B, S, C).  (Gathering from an expanded (B, N, S, C) view makes autograd materialise a gradient of that
+            # shape - 144 GiB at the SAST shape.)
+            Cf = points2.shape[-1]
+            gathered = torch.gather(points2, 1, idx.reshape(B, N * 3)[..., None].expand(-1, -1, Cf)).view(B, N, 3, Cf)
             interpolated_points = torch.sum(gathered * weight.view(B, N, 3, 1), dim=2)
         if points1 is not None:
             new_points = torch.cat([points1.permute(0, 2, 1), interpolated_points], dim=-1)
