@@ -22,6 +22,17 @@ if name == "C2":
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(pts)
         torch.nn.functional.cross_entropy(logits.float(), label).backward()
+elif name == "C4":
+    cfg = sm.part_seg_config()
+    model = sm.get_model(50, cfg).to(dev).train()
+    pts = tokenizer.synthetic_clouds(16, 2048, 4000, "surface").to(dev).transpose(1, 2).contiguous()
+    cls = torch.nn.functional.one_hot(torch.randint(0, 16, (16,), device=dev), 16).float()
+    target = torch.randint(0, 50, (16, 2048), device=dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(pts, cls)
+        torch.nn.functional.nll_loss(out.reshape(-1, 50), target.reshape(-1)).backward()
 else:
     cfg = sm.pretrain()
     model = sm.Point_MAE_Mamba(cfg).to(dev).train()
