@@ -236,6 +236,12 @@ int sim_gemm_bf16x3_split_out(const void* Xs, long ldx, long xplane, const void*
                               long ldd, int M, int N, int K, void* planes_out, int planes_cols, long ld_p, long plane,
                               sim_stream_t stream);
 
+/* Narrow projection (N <= 64: x_proj) straight from the fp32 activation X (M,K) (row stride ldx): the three bf16 planes of X
+ * are formed inside the kernel by transform warps, the weight comes pre-split; bit-identical to sim_split3_bf16 +
+ * sim_gemm_bf16x3.  planes_out (optional): the first planes_cols output columns as split planes (dt_proj operand). */
+int sim_gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,
+                         int K, void* planes_out, int planes_cols, long ld_p, long plane, sim_stream_t stream);
+
 /* a-10 + a-11 fused: the selective scan with dt_proj computed in-kernel.  x_dbl = the x_proj output rows
  * (dt_low[dt_rank = 24] | B[16] | C[16], row stride ld_x); wdt_planes = dt_proj.weight as bf16 planes, K zero-padded to 32:
  * (3, D, 32) from sim_split3_bf16 for fp32 activations, (1, D, 32) for bf16.  delta = dt_low . W_dt^T never touches HBM

@@ -75,6 +75,7 @@ def _side_stream(device):
     return _SIDE[key]
 
 
+_XPROJ_F32A = __import__("os").environ.get("SIM_XPROJ_F32A", "1") != "0"  # x_proj reads fp32 u and splits it in-kernel
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
@@ -134,12 +135,18 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:
         u = u_op = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
+    elif x3 and _XPROJ_F32A and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
+        u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)  # x_proj splits u itself (gemm_f32a kernel)
     elif x3:
         u, u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True, split=True)
     else:
         u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
     dt_planes = None
-    if x3 and isinstance(u_op, ops.Split3) and dt_rank <= 32 and x_proj_w.shape[0] >= 32 and x_proj_w.shape[0] <= 64:
+    if x3 and _XPROJ_F32A and not isinstance(u_op, ops.Split3) and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
+        wxp = _CACHE.get(x_proj_w, "x3", ops.split3)
+        x_dbl, dt_planes = ops.linear_f32a_planes_out(u_op, wxp, x_proj_w.shape[1], 32)
+        x_dbl = x_dbl.view(*u_op.shape[:-1], x_proj_w.shape[0])
+    elif x3 and isinstance(u_op, ops.Split3) and dt_rank <= 32 and x_proj_w.shape[0] >= 32 and x_proj_w.shape[0] <= 64:
         # x_proj whose epilogue also writes the dt_proj operand (split planes of the first 32 output columns)
         wxp = _CACHE.get(x_proj_w, "x3", ops.split3)
         x_dbl, dt_planes = ops.linear_split3_planes_out(u_op.planes, wxp, x_proj_w.shape[1], 32)

@@ -280,6 +280,12 @@ int sim_gemm_bf16x3_split_out(const void* Xs, long ldx, long xplane, const void*
                           planes_cols, ld_p, plane);
 }
 
+int sim_gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,
+                         int K, void* planes_out, int planes_cols, long ld_p, long plane, sim_stream_t stream) {
+  return sim::gemm_f32a_bf16x3(X, ldx, Ws, ldw, wplane, Y, ldd, M, N, K, static_cast<cudaStream_t>(stream), planes_out,
+                               planes_cols, ld_p, plane);
+}
+
 int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream) {
   return sim::group_max(x, out, groups, M, C, dtype, static_cast<cudaStream_t>(stream));
 }

@@ -386,6 +386,170 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32-A variant for narrow outputs (x_proj: N <= 64).  The activation is read as fp32 and split into its three bf16
+// planes INSIDE the kernel by four transform warps (one thread per row of the 128-row tile), so its producer (the conv)
+// does not have to write 6 bytes of planes per element next to the fp32 result and this kernel reads 4 instead of 6.
+// Per 32-deep k-block: TMA brings the fp32 tile (128-byte rows, SWIZZLE_128B so the row-per-thread reads are
+// conflict-free) and the weight planes; the transform warps write the three A-operand tiles in the K-major SWIZZLE_64B
+// layout the MMA descriptors expect (16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)); one thread issues
+// the same twelve MMAs as gemm_split3_kernel, so the results are bit-identical to the pre-split path.
+template <int BN>
+struct GemmF32ACfg {
+  static constexpr int RAW = kBM * kBK * 4;          // fp32 tile, 128-byte rows
+  static constexpr int A_TILE = kBM * kBK * 2;
+  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int STAGE = RAW + 3 * A_TILE + 3 * B_TILE;
+  static constexpr int NSTAGE = 4;
+  static constexpr int STG_LD = 36;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+  static_assert(STAGE % 1024 == 0, "stage bases stay 1024-byte aligned (SWIZZLE_128B)");
+};
+
+struct GemmF32ATmaps {
+  CUtensorMap x, w;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_constant__ GemmF32ATmaps tm,
+                                                                  float* __restrict__ Y, long ldd, int M, int N, int K,
+                                                                  __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
+                                                                  long po_plane) {
+  using Cfg = GemmF32ACfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE);  // TMA landed (raw + weight planes)
+  uint64_t* tfull = full + NSTAGE;                                           // A planes written (128 arrivals)
+  uint64_t* empty = tfull + NSTAGE;                                          // MMAs of the stage done
+  uint64_t* accum_full = empty + NSTAGE;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int nk = (K + kBK - 1) / kBK;
+  constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.x);
+    tma_prefetch_desc(&tm.w);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&tfull[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
+        unsigned char* st = smem + s * Cfg::STAGE;
+        mbar_arrive_expect_tx(&full[s], Cfg::RAW + 3 * Cfg::B_TILE);
+        tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
+        tma_load_3d(st + Cfg::RAW + 3 * Cfg::A_TILE, &tm.w, kb * kBK, 0, 0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
+      constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % NSTAGE;
+        mbar_wait(&tfull[s], (kb / NSTAGE) & 1);  // implies full[s]: the transform warps waited on it
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE + Cfg::RAW);
+        const uint32_t b0 = a0 + 3 * Cfg::A_TILE;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+#pragma unroll
+          for (int k = 0; k < kBK / kUK; ++k) {
+            const uint64_t da = umma_desc_sw64(a0 + PA[q] * Cfg::A_TILE + k * kUK * 2);
+            const uint64_t db = umma_desc_sw64(b0 + PB[q] * Cfg::B_TILE + k * kUK * 2);
+            umma_bf16(tmem_d + (q == 5 ? 0 : BN), da, db, idesc, q == 5 ? (kb | k) != 0 : (kb | q | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum_full);
+    }
+  } else {
+    // ===== transform warps (then epilogue): thread r owns row r of the tile
+    const int r = threadIdx.x - 64;
+    const int quad = warp & 3;  // TMEM lane quadrant of this warp for the epilogue
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % NSTAGE;
+      unsigned char* st = smem + s * Cfg::STAGE;
+      mbar_wait(&full[s], (kb / NSTAGE) & 1);
+      const float4* rawrow = reinterpret_cast<const float4*>(st + r * 128);
+      __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(st + Cfg::RAW) + r * kBK;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {  // eight consecutive k = two fp32 chunks in, one 16-byte chunk per plane out
+        const float4 v0 = rawrow[(2 * c8) ^ (r & 7)], v1 = rawrow[(2 * c8 + 1) ^ (r & 7)];  // SWIZZLE_128B: chunk ^ (row % 8)
+        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        __nv_bfloat16 p[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p[0][j] = __float2bfloat16_rn(f[j]);
+          const float r1 = f[j] - __bfloat162float(p[0][j]);
+          p[1][j] = __float2bfloat16_rn(r1);
+          p[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][j]));
+        }
+        const int pc = c8 ^ ((r >> 1) & 3);  // SWIZZLE_64B position of chunk c8 in row r
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          *reinterpret_cast<uint4*>(arow + q * (Cfg::A_TILE / 2) + pc * 8) = *reinterpret_cast<const uint4*>(p[q]);
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&tfull[s]);
+    }
+    // ===== epilogue (as gemm_split3_kernel)
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + quad * 32 * Cfg::STG_LD;  // stage 0's raw tile is idle now
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (c * 32 >= N) break;
+      float v[32], sm[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + BN + c * 32, sm);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sm[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
+        const int gm = m0 + quad * 32 + row, gn = c * 32 + col;
+        if (gm < M && gn < N) {
+          const float4 o = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
+          *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = o;
+          if (po && gn < po_cols) split3_store4(po + (long)gm * po_ld + gn, po_plane, o);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, kTmemCols);
+  }
+}
+
 // 3-D map over the three bf16 planes of a row-major (rows, K) operand: dims (K, rows, 3), 64-byte swizzle.
 int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows) {
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
@@ -521,6 +685,45 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
     }
     default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream);
   }
+}
+
+int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,
+                     int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
+  SIM_REQUIRE(X && Ws && Y && M > 0 && N > 0 && N <= 64 && K > 0, SIM_ERR_INVALID,
+              "gemm_f32a_bf16x3: built for N <= 64 (x_proj); empty problem / null tensor");
+  SIM_REQUIRE(aligned16(X) && aligned16(Ws) && aligned16(Y) && ldx % 4 == 0 && ldw % 8 == 0 && wplane % 8 == 0 && ldd % 4 == 0 &&
+                  N % 4 == 0,
+              SIM_ERR_ALIGN, "gemm_f32a_bf16x3: TMA needs 16-byte aligned bases / strides, the epilogue N and ldd multiples of 4");
+  SIM_REQUIRE(!po || (po_cols % 4 == 0 && po_ld % 4 == 0 && po_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(po) & 7u) == 0),
+              SIM_ERR_ALIGN, "gemm_f32a_bf16x3: split-plane output needs 8-byte aligned planes");
+  PFN_tmapEncodeTiled enc = tmap_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SIM_ERR_CUDA;
+  }
+  GemmF32ATmaps tm;
+  {  // fp32 activation: dims (K, M, 1), box (32, 128, 1), 128-byte swizzle
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * 4 * (cuuint64_t)M};
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBM, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(&tm.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (fp32 A) failed with CUresult %d (K=%d M=%d ld=%ld)", (int)r, K, M, ldx);
+      return SIM_ERR_CUDA;
+    }
+  }
+  int rc;
+  if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, 64))) return rc;
+  using Cfg = GemmF32ACfg<64>;
+  auto kern = gemm_f32a_split3_kernel<64>;
+  static SmemAttrCache attr;
+  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_f32a_split3 attr");
+  kern<<<(M + kBM - 1) / kBM, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld,
+                                                         po_plane);
+  return check_launch("gemm_f32a_split3");
 }
 
 }  // namespace sim

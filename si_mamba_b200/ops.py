@@ -505,6 +505,21 @@ def linear_split3_planes_out(xs: torch.Tensor, ws: torch.Tensor, K: int, planes_
     return out, planes
 
 
+def linear_f32a_planes_out(x: torch.Tensor, ws: torch.Tensor, K: int, planes_cols: int = 0):
+    """Narrow projection (N <= 64) from the fp32 activation x (..., K) itself: the split happens in-kernel
+    (sim_gemm_f32a_bf16x3).  Returns (y (rows, N), planes (3, rows, planes_cols) or None)."""
+    _cuda(x, ws)
+    assert x.dtype == torch.float32
+    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else _as_rows(x)
+    M, N = x2.shape[0], ws.shape[1]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    planes = torch.empty(3, M, planes_cols, dtype=torch.bfloat16, device=x.device) if planes_cols else None
+    _lib.call("sim_gemm_f32a_bf16x3", _p(x2), x2.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out), out.stride(0), M, N, K,
+              _p(planes), planes_cols, 0 if planes is None else planes.stride(1), 0 if planes is None else planes.stride(0),
+              _stream())
+    return out, planes
+
+
 def linear_f32_x3(x, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
     """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is a Split3 from its producer, or an
     fp32 tensor that is split here."""

@@ -497,3 +497,17 @@ def test_gemm_split_planes_out(ops):
     y2, planes = ops.linear_split3_planes_out(xs, ws, K, 32)
     assert torch.equal(y, y2)
     assert torch.equal(planes.float().sum(0), y[:, :32])
+
+
+@pytest.mark.parametrize("M,N,K,ld", [(16384, 56, 768, 768), (1000, 56, 768, 1536), (130, 64, 96, 96), (7, 32, 32, 32)])
+def test_gemm_f32a_in_kernel_split(ops, M, N, K, ld):
+    """x_proj-shaped GEMM that splits the fp32 activation in-kernel: bit-identical to split3 + gemm on pre-split planes."""
+    g = torch.Generator().manual_seed(M + K)
+    xb = dev(torch.randn(M, ld, generator=g))
+    x = xb[:, :K]
+    ws = ops.split3(dev(torch.randn(N, K, generator=g) * K ** -0.5))
+    ref = ops.linear_split3(ops.split3(x), ws, K)
+    y, planes = ops.linear_f32a_planes_out(x, ws, K, 32 if N >= 32 else 0)
+    assert torch.equal(y, ref)
+    if planes is not None:
+        assert torch.equal(planes.float().sum(0), y[:, :32])
