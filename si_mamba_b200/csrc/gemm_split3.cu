@@ -411,7 +411,7 @@ struct GemmF32ATmaps {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_constant__ GemmF32ATmaps tm,
+__global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_constant__ GemmF32ATmaps tm,
                                                                   float* __restrict__ Y, long ldd, int M, int N, int K,
                                                                   __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
                                                                   long po_plane) {
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_c
     tma_prefetch_desc(&tm.w);
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&tfull[s], 128);
+      mbar_init(&tfull[s], 512);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum_full, 1);
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_c
       umma_commit(accum_full);
     }
   } else {
-    // ===== transform warps (then epilogue): thread r owns row r of the tile
-    const int r = threadIdx.x - 64;
+    // ===== sixteen transform warps (then epilogue): four threads per row of the tile, 8 of the 32 k each
+    const int r = (threadIdx.x - 64) & 127, kh = (threadIdx.x - 64) >> 7;
     const int quad = warp & 3;  // TMEM lane quadrant of this warp for the epilogue
     for (int kb = 0; kb < nk; ++kb) {
       const int s = kb % NSTAGE;
@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_c
       const float4* rawrow = reinterpret_cast<const float4*>(st + r * 128);
       __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(st + Cfg::RAW) + r * kBK;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {  // eight consecutive k = two fp32 chunks in, one 16-byte chunk per plane out
+      {  // eight consecutive k = two fp32 chunks in, one 16-byte chunk per plane out
+        const int c8 = kh;
         const float4 v0 = rawrow[(2 * c8) ^ (r & 7)], v1 = rawrow[(2 * c8 + 1) ^ (r & 7)];  // SWIZZLE_128B: chunk ^ (row % 8)
         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         __nv_bfloat16 p[3][8];
@@ -516,9 +517,9 @@ __global__ void __launch_bounds__(192, 1) gemm_f32a_split3_kernel(const __grid_c
     // ===== epilogue (as gemm_split3_kernel)
     mbar_wait(accum_full, 0);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + quad * 32 * Cfg::STG_LD;  // stage 0's raw tile is idle now
+    float* stg = reinterpret_cast<float*>(smem) + (quad + 4 * kh) * 32 * Cfg::STG_LD;  // stages 0.. are idle now
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = kh; c < BN / 32; c += 4) {  // the four warps of a lane quadrant take alternate 32-column chunks
       if (c * 32 >= N) break;
       float v[32], sm[32];
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
@@ -721,7 +722,7 @@ int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wp
   auto kern = gemm_f32a_split3_kernel<64>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_f32a_split3 attr");
-  kern<<<(M + kBM - 1) / kBM, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld,
+  kern<<<(M + kBM - 1) / kBM, 576, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld,
                                                          po_plane);
   return check_launch("gemm_f32a_split3");
 }
