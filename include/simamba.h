@@ -242,6 +242,13 @@ int sim_gemm_bf16x3_split_out(const void* Xs, long ldx, long xplane, const void*
 int sim_gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,
                          int K, void* planes_out, int planes_cols, long ld_p, long plane, sim_stream_t stream);
 
+/* a-12 + a-10 fused (fp32 inference): u = silu(causal_conv1d(x)) (width 4) AND x_dbl = u . W_x^T in one kernel.  x (batch*L, D)
+ * token-major fp32 with row stride ld_x (the x half of the in_proj output, in place), conv_w (D,4), conv_b (D) or NULL;
+ * u (batch*L, D) is written for the scan; Ws = split planes of x_proj.weight (N <= 64 rows); planes_out as above. */
+int sim_conv_xproj_f32(const float* x, long ld_x, const float* conv_w, const float* conv_b, float* u, long ld_u,
+                       const void* Ws, long ldw, long wplane, float* x_dbl, long ldd, int batch, int L, int D, int N,
+                       void* planes_out, int planes_cols, long ld_p, long plane, sim_stream_t stream);
+
 /* a-10 + a-11 fused: the selective scan with dt_proj computed in-kernel.  x_dbl = the x_proj output rows
  * (dt_low[dt_rank = 24] | B[16] | C[16], row stride ld_x); wdt_planes = dt_proj.weight as bf16 planes, K zero-padded to 32:
  * (3, D, 32) from sim_split3_bf16 for fp32 activations, (1, D, 32) for bf16.  delta = dt_low . W_dt^T never touches HBM

@@ -65,6 +65,7 @@ SIGNATURES = {
                                              _i, _i, _i, _i, _i, _i, _p]),
     "sim_gemm_bf16x3_split_out": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p, _i, _l, _l, _p]),
     "sim_gemm_f32a_bf16x3": (_i, [_p, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p, _i, _l, _l, _p]),
+    "sim_conv_xproj_f32": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _p, _l, _i, _i, _i, _i, _p, _i, _l, _l, _p]),
     "sim_group_max": (_i, [_p, _p, _l, _i, _i, _i, _p]),
     "sim_group_bias_relu": (_i, [_p, _p, _l, _i, _i, _i, _p]),
     "sim_layernorm_mean": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p]),

@@ -76,6 +76,7 @@ def _side_stream(device):
 
 
 _XPROJ_F32A = __import__("os").environ.get("SIM_XPROJ_F32A", "1") != "0"  # x_proj reads fp32 u and splits it in-kernel
+_CONV_XPROJ = __import__("os").environ.get("SIM_CONV_XPROJ", "0") != "0"  # causal conv fused into that x_proj kernel (measured slower: 60 us vs 17 + 19)
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
@@ -135,6 +136,12 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:
         u = u_op = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
+    elif (x3 and _XPROJ_F32A and _CONV_XPROJ and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64 and conv_w.shape[-1] == 4
+          and d_inner % 8 == 0 and d_inner <= 1024 and x.dtype == torch.float32):
+        # one kernel: conv + SiLU in the x_proj GEMM's transform warps (u written for the scan on the way)
+        wxp = _CACHE.get(x_proj_w, "x3", ops.split3)
+        u, x_dbl_f, dt_planes_f = ops.conv_xproj_f32(x, conv_w, conv_b, wxp, 32)
+        u_op = None
     elif x3 and _XPROJ_F32A and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
         u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)  # x_proj splits u itself (gemm_f32a kernel)
     elif x3:
@@ -142,7 +149,9 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     else:
         u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
     dt_planes = None
-    if x3 and _XPROJ_F32A and not isinstance(u_op, ops.Split3) and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
+    if u_op is None:
+        x_dbl, dt_planes = x_dbl_f, dt_planes_f
+    elif x3 and _XPROJ_F32A and not isinstance(u_op, ops.Split3) and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
         wxp = _CACHE.get(x_proj_w, "x3", ops.split3)
         x_dbl, dt_planes = ops.linear_f32a_planes_out(u_op, wxp, x_proj_w.shape[1], 32)
         x_dbl = x_dbl.view(*u_op.shape[:-1], x_proj_w.shape[0])

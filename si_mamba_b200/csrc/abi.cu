@@ -286,6 +286,13 @@ int sim_gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, lon
                                planes_cols, ld_p, plane);
 }
 
+int sim_conv_xproj_f32(const float* x, long ld_x, const float* conv_w, const float* conv_b, float* u, long ld_u,
+                       const void* Ws, long ldw, long wplane, float* x_dbl, long ldd, int batch, int L, int D, int N,
+                       void* planes_out, int planes_cols, long ld_p, long plane, sim_stream_t stream) {
+  return sim::gemm_f32a_bf16x3(x, ld_x, Ws, ldw, wplane, x_dbl, ldd, batch * L, N, D, static_cast<cudaStream_t>(stream),
+                               planes_out, planes_cols, ld_p, plane, conv_w, conv_b, u, ld_u, batch, L);
+}
+
 int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream) {
   return sim::group_max(x, out, groups, M, C, dtype, static_cast<cudaStream_t>(stream));
 }

@@ -394,15 +394,22 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
 // conflict-free) and the weight planes; the transform warps write the three A-operand tiles in the K-major SWIZZLE_64B
 // layout the MMA descriptors expect (16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)); one thread issues
 // the same twelve MMAs as gemm_split3_kernel, so the results are bit-identical to the pre-split path.
-template <int BN>
+constexpr int kCW = 4;  // taps of the fused causal conv (d_conv of the reference's Mamba blocks)
+
+// CONV = true fuses the causal depthwise conv1d + SiLU that precedes x_proj (Mamba.forward: x -> conv1d -> silu -> x_proj):
+// the fp32 tile then holds the PRE-conv activation with a 3-row halo (tiles are per cloud, rows before the sequence are
+// zero-filled by the TMA unit), the transform threads convolve their (row, 8 channels), write u = silu(conv(x)) to global
+// memory for the scan, and split it into the operand planes - the conv kernel and one 50 MB read of u disappear.
+template <int BN, bool CONV>
 struct GemmF32ACfg {
-  static constexpr int RAW = kBM * kBK * 4;          // fp32 tile, 128-byte rows
+  static constexpr int RAW_ROWS = kBM + (CONV ? kCW - 1 : 0);
+  static constexpr int RAW = (RAW_ROWS * kBK * 4 + 1023) / 1024 * 1024;  // fp32 tile, 128-byte rows
   static constexpr int A_TILE = kBM * kBK * 2;
   static constexpr int B_TILE = BN * kBK * 2;
   static constexpr int STAGE = RAW + 3 * A_TILE + 3 * B_TILE;
-  static constexpr int NSTAGE = 4;
+  static constexpr int NSTAGE = CONV ? 3 : 4;  // 53 KB stages + 15 KB of conv weights: three fit in 227 KB
   static constexpr int STG_LD = 36;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+  static constexpr int CONVW = CONV ? 1 : 0;  // conv weights + bias of all K channels staged once per CTA: K * 5 floats
   static_assert(STAGE % 1024 == 0, "stage bases stay 1024-byte aligned (SWIZZLE_128B)");
 };
 
@@ -410,24 +417,31 @@ struct GemmF32ATmaps {
   CUtensorMap x, w;
 };
 
-template <int BN>
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_constant__ GemmF32ATmaps tm,
                                                                   float* __restrict__ Y, long ldd, int M, int N, int K,
                                                                   __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
-                                                                  long po_plane) {
-  using Cfg = GemmF32ACfg<BN>;
-  constexpr int NSTAGE = Cfg::NSTAGE;
+                                                                  long po_plane, const float* __restrict__ cw,
+                                                                  const float* __restrict__ cb, float* __restrict__ U,
+                                                                  long ldu, int L, int tiles_per_cloud) {
+  using Cfg = GemmF32ACfg<BN, CONV>;
+  constexpr int NSTAGE = Cfg::NSTAGE, HALO = CONV ? kCW - 1 : 0;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE);  // TMA landed (raw + weight planes)
-  uint64_t* tfull = full + NSTAGE;                                           // A planes written (128 arrivals)
+  uint64_t* tfull = full + NSTAGE;                                           // A planes written (512 arrivals)
   uint64_t* empty = tfull + NSTAGE;                                          // MMAs of the stage done
   uint64_t* accum_full = empty + NSTAGE;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_full + 1);
+  float* s_cw = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // CONV: [K][4] taps then [K] bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
+  // CONV: tiles are per cloud (the halo must not reach into the previous cloud); otherwise rows are one flat M
+  const int cloud = CONV ? blockIdx.x / tiles_per_cloud : 0;
+  const int t0 = CONV ? (blockIdx.x % tiles_per_cloud) * kBM : 0;
+  const int m0 = CONV ? cloud * L + t0 : blockIdx.x * kBM;   // first output row of this tile
+  const int m_end = CONV ? cloud * L + L : M;                // rows of this tile are valid below m_end
   const int nk = (K + kBK - 1) / kBK;
   constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 
@@ -443,6 +457,10 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if constexpr (CONV) {
+    for (int i = threadIdx.x; i < K * kCW; i += blockDim.x) s_cw[i] = cw[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_cw[K * kCW + i] = cb ? cb[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -454,8 +472,9 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
         const int s = kb % NSTAGE;
         if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
         unsigned char* st = smem + s * Cfg::STAGE;
-        mbar_arrive_expect_tx(&full[s], Cfg::RAW + 3 * Cfg::B_TILE);
-        tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
+        mbar_arrive_expect_tx(&full[s], Cfg::RAW_ROWS * kBK * 4 + 3 * Cfg::B_TILE);
+        if constexpr (CONV) tma_load_3d(st, &tm.x, kb * kBK, t0 - HALO, cloud, &full[s]);  // rows < 0 / >= L: zero-filled
+        else tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
         tma_load_3d(st + Cfg::RAW + 3 * Cfg::A_TILE, &tm.w, kb * kBK, 0, 0, &full[s]);
       }
     }
@@ -491,13 +510,36 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
       const int s = kb % NSTAGE;
       unsigned char* st = smem + s * Cfg::STAGE;
       mbar_wait(&full[s], (kb / NSTAGE) & 1);
-      const float4* rawrow = reinterpret_cast<const float4*>(st + r * 128);
       __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(st + Cfg::RAW) + r * kBK;
-#pragma unroll
       {  // eight consecutive k = two fp32 chunks in, one 16-byte chunk per plane out
         const int c8 = kh;
-        const float4 v0 = rawrow[(2 * c8) ^ (r & 7)], v1 = rawrow[(2 * c8 + 1) ^ (r & 7)];  // SWIZZLE_128B: chunk ^ (row % 8)
-        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float f[8];
+        if constexpr (CONV) {
+          // raw row i <-> token t0 - 3 + i: output row r reads raw rows r .. r + 3 (SWIZZLE_128B: chunk ^ (row % 8))
+          const int ch = kb * kBK + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = s_cw[K * kCW + (ch + j < K ? ch + j : 0)];
+#pragma unroll
+          for (int tap = 0; tap < kCW; ++tap) {
+            const int i = r + tap;
+            const float4* rawrow = reinterpret_cast<const float4*>(st + i * 128);
+            const float4 v0 = rawrow[(2 * c8) ^ (i & 7)], v1 = rawrow[(2 * c8 + 1) ^ (i & 7)];
+            const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(s_cw[(ch + j < K ? ch + j : 0) * kCW + tap], xv[j], f[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+          if (m0 + r < m_end && ch < K) {  // u for the scan (token-major, row stride ldu)
+            float* up = U + (long)(m0 + r) * ldu + ch;
+            *reinterpret_cast<float4*>(up) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(up + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        } else {
+          const float4* rawrow = reinterpret_cast<const float4*>(st + r * 128);
+          const float4 v0 = rawrow[(2 * c8) ^ (r & 7)], v1 = rawrow[(2 * c8 + 1) ^ (r & 7)];  // SWIZZLE_128B: chunk ^ (row % 8)
+          f[0] = v0.x, f[1] = v0.y, f[2] = v0.z, f[3] = v0.w, f[4] = v1.x, f[5] = v1.y, f[6] = v1.z, f[7] = v1.w;
+        }
         __nv_bfloat16 p[3][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -534,7 +576,7 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
       for (int rr = 0; rr < 8; ++rr) {
         const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
         const int gm = m0 + quad * 32 + row, gn = c * 32 + col;
-        if (gm < M && gn < N) {
+        if (gm < m_end && gn < N) {
           const float4 o = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
           *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = o;
           if (po && gn < po_cols) split3_store4(po + (long)gm * po_ld + gn, po_plane, o);
@@ -689,7 +731,8 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
 }
 
 int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,
-                     int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
+                     int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane, const float* conv_w,
+                     const float* conv_b, float* U, long ldu, int batch, int L) {
   SIM_REQUIRE(X && Ws && Y && M > 0 && N > 0 && N <= 64 && K > 0, SIM_ERR_INVALID,
               "gemm_f32a_bf16x3: built for N <= 64 (x_proj); empty problem / null tensor");
   SIM_REQUIRE(aligned16(X) && aligned16(Ws) && aligned16(Y) && ldx % 4 == 0 && ldw % 8 == 0 && wplane % 8 == 0 && ldd % 4 == 0 &&
@@ -697,16 +740,20 @@ int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wp
               SIM_ERR_ALIGN, "gemm_f32a_bf16x3: TMA needs 16-byte aligned bases / strides, the epilogue N and ldd multiples of 4");
   SIM_REQUIRE(!po || (po_cols % 4 == 0 && po_ld % 4 == 0 && po_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(po) & 7u) == 0),
               SIM_ERR_ALIGN, "gemm_f32a_bf16x3: split-plane output needs 8-byte aligned planes");
+  const bool conv = conv_w != nullptr;
+  SIM_REQUIRE(!conv || (U && batch > 0 && L > 0 && (long)batch * L == M && K % 8 == 0 && ldu % 4 == 0 && aligned16(U) &&
+                        (size_t)K * 5 * 4 <= 20 * 1024),
+              SIM_ERR_INVALID, "gemm_f32a_bf16x3: fused conv needs u, batch * L == M, K %% 8 == 0 and K <= 1024");
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SIM_ERR_CUDA;
   }
   GemmF32ATmaps tm;
-  {  // fp32 activation: dims (K, M, 1), box (32, 128, 1), 128-byte swizzle
-    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
-    cuuint64_t gstr[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * 4 * (cuuint64_t)M};
-    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBM, 1u};
+  {  // fp32 activation, 128-byte swizzle: flat (K, M, 1) rows, or per cloud (K, L, batch) with the conv's 3-row halo
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)(conv ? L : M), (cuuint64_t)(conv ? batch : 1)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * 4 * (cuuint64_t)(conv ? L : M)};
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)(kBM + (conv ? kCW - 1 : 0)), 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(&tm.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -718,12 +765,23 @@ int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wp
   }
   int rc;
   if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, 64))) return rc;
-  using Cfg = GemmF32ACfg<64>;
-  auto kern = gemm_f32a_split3_kernel<64>;
-  static SmemAttrCache attr;
-  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_f32a_split3 attr");
-  kern<<<(M + kBM - 1) / kBM, 576, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld,
-                                                         po_plane);
+  static SmemAttrCache attr0, attr1;
+  if (conv) {
+    using Cfg = GemmF32ACfg<64, true>;
+    auto kern = gemm_f32a_split3_kernel<64, true>;
+    const size_t smem = Cfg::NSTAGE * Cfg::STAGE + 1024 + 256 + (size_t)K * 5 * 4;
+    if (ensure_dyn_smem(kern, smem, attr1) != cudaSuccess) return check_launch("gemm_f32a_split3 attr");
+    const int tpc = (L + kBM - 1) / kBM;
+    kern<<<batch * tpc, 576, smem, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld, po_plane,
+                                             conv_w, conv_b, U, ldu, L, tpc);
+  } else {
+    using Cfg = GemmF32ACfg<64, false>;
+    auto kern = gemm_f32a_split3_kernel<64, false>;
+    const size_t smem = Cfg::NSTAGE * Cfg::STAGE + 1024 + 256;
+    if (ensure_dyn_smem(kern, smem, attr0) != cudaSuccess) return check_launch("gemm_f32a_split3 attr");
+    kern<<<(M + kBM - 1) / kBM, 576, smem, stream>>>(tm, Y, ldd, M, N, K, static_cast<__nv_bfloat16*>(po), po_cols, po_ld,
+                                                     po_plane, nullptr, nullptr, nullptr, 0, 0, 1);
+  }
   return check_launch("gemm_f32a_split3");
 }
 

@@ -520,6 +520,24 @@ def linear_f32a_planes_out(x: torch.Tensor, ws: torch.Tensor, K: int, planes_col
     return out, planes
 
 
+def conv_xproj_f32(x: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], ws: torch.Tensor,
+                   planes_cols: int = 0):
+    """Fused causal conv1d(width 4) + SiLU + x_proj (fp32 inference, sim_conv_xproj_f32): x (B, L, D) token-major fp32
+    (any uniform row stride) -> u (B, L, D), x_dbl (B, L, N), planes (3, B*L, planes_cols) of x_dbl's first columns."""
+    _cuda(x, conv_w, conv_b, ws)
+    B, L, D = x.shape
+    N = ws.shape[1]
+    w = _f32c(conv_w.reshape(D, -1))
+    assert x.dtype == torch.float32 and w.shape[1] == 4
+    u = torch.empty(B, L, D, dtype=torch.float32, device=x.device)
+    x_dbl = torch.empty(B, L, N, dtype=torch.float32, device=x.device)
+    planes = torch.empty(3, B * L, planes_cols, dtype=torch.bfloat16, device=x.device) if planes_cols else None
+    _lib.call("sim_conv_xproj_f32", _p(x), _tm(x), _p(w), _p(_f32c(conv_b)), _p(u), D, _p(ws), ws.stride(1), ws.stride(0),
+              _p(x_dbl), N, B, L, D, N, _p(planes), planes_cols, 0 if planes is None else planes.stride(1),
+              0 if planes is None else planes.stride(0), _stream())
+    return u, x_dbl, planes
+
+
 def linear_f32_x3(x, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
     """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is a Split3 from its producer, or an
     fp32 tensor that is split here."""

@@ -511,3 +511,30 @@ def test_gemm_f32a_in_kernel_split(ops, M, N, K, ld):
     assert torch.equal(y, ref)
     if planes is not None:
         assert torch.equal(planes.float().sum(0), y[:, :32])
+
+
+@pytest.mark.parametrize("B,L,D,N,ld", [(3, 512, 768, 56, 1536), (2, 128, 768, 56, 768), (5, 100, 64, 40, 128),
+                                        (1, 1, 32, 56, 32), (2, 131, 256, 64, 512), (4, 37, 1024, 32, 1024)])
+def test_conv_xproj_fused(ops, B, L, D, N, ld):
+    """Causal conv1d + SiLU fused into the x_proj GEMM (sim_conv_xproj_f32): u against the conv kernel and the float64
+    formula, x_dbl against the unfused pair (Mamba.forward, mamba_simple.py conv1d -> act -> x_proj)."""
+    g = torch.Generator().manual_seed(B * L + D)
+    xb = dev(torch.randn(B, L, ld, generator=g))
+    x = xb[..., :D]
+    cw = dev(torch.randn(D, 1, 4, generator=g) * 0.5)
+    cb = dev(torch.randn(D, generator=g) * 0.1)
+    ws = ops.split3(dev(torch.randn(N, D, generator=g) * D ** -0.5))
+    u_ref = ops.causal_conv1d_tm(x, cw, cb, silu=True)
+    y_ref, p_ref = ops.linear_f32a_planes_out(u_ref, ws, D, 32)
+    u, y, planes = ops.conv_xproj_f32(x, cw, cb, ws, 32)
+    xd = torch.nn.functional.pad(x.double().transpose(1, 2), (3, 0))
+    u64 = torch.nn.functional.silu(torch.nn.functional.conv1d(xd, cw.double(), cb.double(), groups=D)).transpose(1, 2)
+    assert (u.double() - u64).abs().max().item() < 2e-6
+    assert (u - u_ref).abs().max().item() < 2e-6
+    y2, _ = ops.linear_f32a_planes_out(u, ws, D, 32)  # same u -> the GEMM part is bit-identical
+    assert torch.equal(y.view(-1, N), y2)
+    assert (y.view(-1, N) - y_ref).abs().max().item() < 2e-5
+    assert torch.equal(planes.float().sum(0), y.view(-1, N)[:, :32])
+    u0, y0, _ = ops.conv_xproj_f32(x, cw, None, ws, 0)  # no bias, no planes
+    u64 = torch.nn.functional.silu(torch.nn.functional.conv1d(xd, cw.double(), None, groups=D)).transpose(1, 2)
+    assert (u0.double() - u64).abs().max().item() < 2e-6
