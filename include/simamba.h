@@ -198,6 +198,17 @@ int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int 
 int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
                        sim_stream_t stream);
 
+/* a-19: 3-nearest-centre inverse-squared-distance interpolation (PointNetFeaturePropagation.forward,
+ * part_segmentation/models/pointnet2_utils.py:273-311; replaces square_distance + full sort + index_points gathers).
+ * xyz1 (B,N,3) query points, xyz2 (B,S,3) centres (3 <= S <= 2048), points2 (B,S,C) feature rows, all fp32 contiguous.
+ * idx (B,N,3) = the three nearest centres in ascending (distance, index) order, weight (B,N,3) = normalised
+ * 1/(dist + 1e-8); out (B,N,C) = sum_k weight_k * points2[idx_k] (points2 and out may both be NULL: indices only).
+ * sim_three_interp_bwd: dpoints2 (B,S,C) = scatter-add of weight_k * dout (zeroed by the call; fp32 atomics). */
+int sim_three_nn_interp_fwd(const float* xyz1, const float* xyz2, const float* points2, int B, int N, int S, int C,
+                            float* out, int32_t* idx, float* weight, sim_stream_t stream);
+int sim_three_interp_bwd(const float* dout, const int32_t* idx, const float* weight, int B, int N, int S, int C,
+                         float* dpoints2, sim_stream_t stream);
+
 /* a-18  Chamfer-L2 of R pairs of small point sets, x (R,P,3), y (R,Q,3) fp32, P, Q <= 256:
  * loss[r] = mean_i min_j |x_i - y_j|^2 + mean_j min_i |x_i - y_j|^2  (pytorch3d chamfer_distance(x, y,
  * batch_reduction=None)[0], models/point_mamba.py:2950, 3199-3213).  idx_x (R,P) / idx_y (R,Q) receive the arg-mins

@@ -57,6 +57,8 @@ SIGNATURES = {
     "sim_mae_restore_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sim_gather_sum_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sim_spectral_perm": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
+    "sim_three_nn_interp_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "sim_three_interp_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "sim_chamfer_l2_fwd": (_i, [_p, _p, _l, _i, _i, _p, _p, _p, _p]),
     "sim_chamfer_l2_bwd": (_i, [_p, _p, _p, _p, _p, _l, _i, _i, _p, _p, _p]),
     "sim_fps_pointnet2": (_i, [_p, _i, _i, _i, _p, _p, _p]),

@@ -253,6 +253,16 @@ int sim_spectral_perm(const float* keys, long ld, long es, int rows, int n, int3
   return sim::argsort_rows(keys, ld, es, rows, n, perm, inv_perm, static_cast<cudaStream_t>(stream));
 }
 
+int sim_three_nn_interp_fwd(const float* xyz1, const float* xyz2, const float* points2, int B, int N, int S, int C,
+                            float* out, int32_t* idx, float* weight, sim_stream_t stream) {
+  return sim::three_nn_interp_fwd(xyz1, xyz2, points2, B, N, S, C, out, idx, weight, static_cast<cudaStream_t>(stream));
+}
+
+int sim_three_interp_bwd(const float* dout, const int32_t* idx, const float* weight, int B, int N, int S, int C,
+                         float* dpoints2, sim_stream_t stream) {
+  return sim::three_interp_bwd(dout, idx, weight, B, N, S, C, dpoints2, static_cast<cudaStream_t>(stream));
+}
+
 int sim_chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* loss, int32_t* idx_x,
                        int32_t* idx_y, sim_stream_t stream) {
   return sim::chamfer_l2_fwd(x, y, R, P, Q, loss, idx_x, idx_y, static_cast<cudaStream_t>(stream));

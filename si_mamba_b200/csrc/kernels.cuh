@@ -101,6 +101,10 @@ int mae_index_maps(const int* perm, const unsigned char* mask, int B, int k, int
 int gather_sum_rows(const void* x, const int* idx, void* out, int B, int R_in, int R_out, int J, int C, int dtype,
                     cudaStream_t stream);
 int masked_colsum(const void* x, const int* sel, long rows, int C, float* dfill, int dtype, cudaStream_t stream);
+int three_nn_interp_fwd(const float* xyz1, const float* xyz2, const float* points2, int B, int N, int S, int C, float* out,
+                        int* idx, float* weight, cudaStream_t stream);
+int three_interp_bwd(const float* dout, const int* idx, const float* weight, int B, int N, int S, int C, float* dpoints2,
+                     cudaStream_t stream);
 int chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* loss, int* idx_x, int* idx_y,
                    cudaStream_t stream);
 int chamfer_l2_bwd(const float* x, const float* y, const int* idx_x, const int* idx_y, const float* gloss, long R, int P,

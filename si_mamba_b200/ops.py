@@ -283,6 +283,51 @@ def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return ChamferL2.apply(x, y)
 
 
+# ----------------------------------------------------------------------------- 3-NN interpolation (a-19)
+class ThreeNNInterpolate(torch.autograd.Function):
+    """xyz1 (B,N,3), xyz2 (B,S,3), points2 (B,S,C) -> (B,N,C): inverse-squared-distance interpolation from the three
+    nearest centres (PointNetFeaturePropagation.forward, pointnet2_utils.py:273-311); gradient to points2 only, as in
+    the reference (the coordinates are inputs).  sim_three_nn_interp_fwd / sim_three_interp_bwd."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, points2):
+        _cuda(xyz1, xyz2, points2)
+        xyz1, xyz2, p2 = _f32c(xyz1), _f32c(xyz2), points2.detach().float().contiguous()
+        B, N, _ = xyz1.shape
+        S, C = p2.shape[1], p2.shape[2]
+        out = torch.empty(B, N, C, dtype=torch.float32, device=p2.device)
+        idx = torch.empty(B, N, 3, dtype=torch.int32, device=p2.device)
+        w = torch.empty(B, N, 3, dtype=torch.float32, device=p2.device)
+        _lib.call("sim_three_nn_interp_fwd", _p(xyz1), _p(xyz2), _p(p2), B, N, S, C, _p(out), _p(idx), _p(w), _stream())
+        ctx.save_for_backward(idx, w)
+        ctx.shape = (B, N, S, C)
+        ctx.in_dtype = points2.dtype
+        return out.to(points2.dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, w = ctx.saved_tensors
+        B, N, S, C = ctx.shape
+        dp2 = torch.empty(B, S, C, dtype=torch.float32, device=dout.device)
+        _lib.call("sim_three_interp_bwd", _p(dout.float().contiguous()), _p(idx), _p(w), B, N, S, C, _p(dp2), _stream())
+        return None, None, dp2.to(ctx.in_dtype)
+
+
+def three_nn_interpolate(xyz1: torch.Tensor, xyz2: torch.Tensor, points2: torch.Tensor) -> torch.Tensor:
+    return ThreeNNInterpolate.apply(xyz1, xyz2, points2)
+
+
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """Indices (B,N,3) int32 and normalised weights (B,N,3) of the three nearest centres (no interpolation)."""
+    _cuda(xyz1, xyz2)
+    xyz1, xyz2 = _f32c(xyz1), _f32c(xyz2)
+    B, N, _ = xyz1.shape
+    idx = torch.empty(B, N, 3, dtype=torch.int32, device=xyz1.device)
+    w = torch.empty(B, N, 3, dtype=torch.float32, device=xyz1.device)
+    _lib.call("sim_three_nn_interp_fwd", _p(xyz1), _p(xyz2), None, B, N, xyz2.shape[1], 0, None, _p(idx), _p(w), _stream())
+    return idx, w
+
+
 # ----------------------------------------------------------------------------- MAE layout (a-16 / a-17)
 def mae_index_maps(perm: torch.Tensor, mask: torch.Tensor, n_vis: int, check: bool = False) -> dict:
     """perm (B,k,G) int32, mask (B,G) bool with G - n_vis masked patches per cloud -> the index maps of the masked

@@ -68,6 +68,9 @@ def square_distance(src, dst):
     return dist
 
 
+_THREE_NN_KERNEL = __import__("os").environ.get("SIM_THREE_NN", "1") != "0"  # 0: the torch topk + gather formulation
+
+
 class PointNetFeaturePropagation(nn.Module):
     """pointnet2_utils.py:262-311 (3-NN inverse-squared-distance interpolation + shared MLP)."""
 
@@ -89,6 +92,9 @@ class PointNetFeaturePropagation(nn.Module):
         _, S, _ = xyz2.shape
         if S == 1:
             interpolated_points = points2.repeat(1, N, 1)
+        elif xyz1.is_cuda and 3 <= S <= 2048 and _THREE_NN_KERNEL:
+            # one kernel: centres staged in shared memory, warp-level top-3, weighted row gather (sim_three_nn_interp_fwd)
+            interpolated_points = ops.three_nn_interpolate(xyz1, xyz2, points2)
         else:
             dists, idx = square_distance(xyz1, xyz2).topk(3, dim=-1, largest=False, sorted=True)
             dist_recip = 1.0 / (dists + 1e-8)

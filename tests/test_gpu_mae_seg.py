@@ -183,3 +183,57 @@ def test_chamfer_l2_vs_oracle(R, P, Q):
     assert torch.allclose(got.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
     assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-6)
     assert torch.allclose(yc.grad.cpu(), yr.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,S,C,kind", [(2, 2048, 256, 1152, "hlt"), (3, 500, 128, 384, "ball"), (1, 33, 3, 7, "ball"),
+                                          (2, 64, 40, 16, "dup")])
+def test_three_nn_interpolate_vs_oracle(lib, B, N, S, C, kind):
+    """a-19: 3-NN inverse-squared-distance interpolation (pointnet2_utils.py:273-311) against the oracle's
+    square_distance + full sort + gather, forward and gradient."""
+    from si_mamba_b200 import ops
+    g = torch.Generator().manual_seed(B * N + S)
+    xyz1 = tokenizer.synthetic_clouds(B, N, 11 + S, "ball" if kind != "hlt" else "surface")
+    xyz2 = xyz1[:, torch.randperm(N, generator=g)[:S]].clone()        # centres are a subset of the points (FPS)
+    if kind == "hlt":
+        xyz2[:, S - 96:] = 0.0                                         # HLT layout: 96 zero tokens at the origin
+    if kind == "dup":
+        xyz2[:, 1::2] = xyz2[:, 0::2]                                  # exact duplicates: ties -> lowest index
+    p2 = torch.randn(B, S, C, generator=g)
+    # oracle (CPU, the reference's formulation)
+    d = oseg.square_distance(xyz1, xyz2)
+    ds, di = torch.sort(d, dim=-1, stable=True)
+    recip = 1.0 / (ds[..., :3] + 1e-8)
+    w_ref = recip / recip.sum(-1, keepdim=True)
+    idx, w = ops.three_nn(xyz1.cuda(), xyz2.cuda())
+    idx, w = idx.cpu().long(), w.cpu()
+    # the selection is exact wherever the four best distances are separated by more than fp32 cancellation noise
+    m = 4 if S > 3 else 3
+    gap_ok = (ds[..., 1:m] - ds[..., :m - 1]) > 1e-5
+    if kind == "dup":  # an exact duplicate pair (2i, 2i+1) ties in any arithmetic and is ordered by index: also fine
+        gap_ok |= (di[..., 1:m] // 2 == di[..., :m - 1] // 2) & (di[..., 1:m] > di[..., :m - 1])
+    clear = gap_ok.all(-1)
+    assert clear.float().mean() > 0.9
+    assert torch.equal(idx[clear], di[..., :3][clear])
+    # everywhere: the kernel's choice is a valid 3-nearest set of the oracle's distances up to that noise
+    chosen = torch.gather(d, 2, idx)
+    assert (chosen - ds[..., :3]).abs().max() < 1e-5
+    if kind == "dup":  # duplicates are exact ties in any arithmetic: the lower index must win
+        assert (idx[..., 0] % 2 == 0).all() and torch.equal(idx[..., 1], idx[..., 0] + 1)
+    far = ds[..., 0] > 1e-4  # queries that coincide with a centre have weights dominated by cancellation noise
+    assert torch.allclose(w[clear & far], w_ref[clear & far], rtol=2e-3, atol=1e-6)
+    # interpolation + gradient against the gather formulation on the kernel's own (idx, weight)
+    p2g = p2.cuda().requires_grad_(True)
+    out = ops.three_nn_interpolate(xyz1.cuda(), xyz2.cuda(), p2g)
+    p2r = p2.cuda().requires_grad_(True)
+    gathered = torch.gather(p2r, 1, idx.cuda().reshape(B, N * 3, 1).expand(-1, -1, C)).view(B, N, 3, C)
+    ref = (gathered * w.cuda()[..., None]).sum(2)
+    assert torch.equal(out, ref) or (out - ref).abs().max() < 1e-6
+    dout = torch.randn(B, N, C, generator=g).cuda()
+    out.backward(dout)
+    ref.backward(dout)
+    assert torch.allclose(p2g.grad, p2r.grad, rtol=1e-4, atol=1e-4)
+    # and the full oracle interpolation where the selection is unambiguous
+    gat = torch.gather(p2[:, None].expand(-1, N, -1, -1), 2, di[..., :3, None].expand(-1, -1, -1, C))
+    interp_ref = (gat * w_ref[..., None]).sum(2)
+    sel = clear & far
+    assert torch.allclose(out.detach().cpu()[sel], interp_ref[sel], rtol=1e-3, atol=1e-4)
