@@ -77,6 +77,10 @@ def _side_stream(device):
 
 _XPROJ_F32A = __import__("os").environ.get("SIM_XPROJ_F32A", "1") != "0"  # x_proj reads fp32 u and splits it in-kernel
 _CONV_XPROJ = __import__("os").environ.get("SIM_CONV_XPROJ", "0") != "0"  # causal conv fused into that x_proj kernel (measured slower: 60 us vs 17 + 19)
+# fp32 TRAINING projections on the split GEMM: opt-in.  Measured on C4 (fp32, 16 clouds): HLT 25.9 -> 28.8 ms (slower: the
+# per-step operand splits and transposes outweigh the GEMM time at 4096 rows), SAST 50.5 -> 49.5 ms; and dW, whose
+# contraction runs over all B*L rows, shows the tensor core's truncating fp32 accumulation (1.9e-5 at 16384 rows).
+_TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "0") != "0"
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
@@ -116,6 +120,9 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
 
             def linear(x, w):
                 return ops.linear_f32_x3(x, _CACHE.get(w, "x3", ops.split3), w.shape[1])
+    if (need_grad and _TRAIN_X3 and act == torch.float32 and hidden.is_cuda and in_proj_w.dtype == torch.float32
+            and _FP32_GEMM not in ("cublas", "tc") and d_inner % 8 == 0 and hidden.shape[-1] % 8 == 0 and dt_rank % 4 == 0):
+        linear = ops.linear_x3_train  # fp32 training: forward, dX and dW GEMMs on the split-plane tensor-core kernel
     join_z = None
     if x3 and _OVERLAP_Z:
         # in_proj as two GEMMs: the x half on this stream, the z half (only needed by the scan) on a side stream where it

@@ -538,6 +538,39 @@ def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torc
     return out
 
 
+class LinearX3(torch.autograd.Function):
+    """y = x @ w.T for fp32 TRAINING on the tcgen05 split-plane GEMM (the reference's fp32 runs do all three GEMMs of a
+    Linear as SIMT SGEMMs): forward, dX = dY @ W and dW = dY^T @ X each split their two operands into bf16 planes
+    (sim_split3_bf16) and run sim_gemm_bf16x3; accuracy is that of an fp32 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        K = w.shape[1]
+        ctx.save_for_backward(x, w)
+        y = linear_split3(split3(x), split3(w), K)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_split3(split3(dy2), split3(w.t().contiguous()), N).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            x2 = x.reshape(-1, K)
+            M = x2.shape[0]
+            dw = linear_split3(split3(dy2.t().contiguous()), split3(x2.t().contiguous()), M)
+        return dx, dw
+
+
+def linear_x3_train(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    return LinearX3.apply(x, w)
+
+
 def linear_split3_planes_out(xs: torch.Tensor, ws: torch.Tensor, K: int, planes_cols: int):
     """linear_split3 for N <= 64 that also returns the first ``planes_cols`` output columns as split planes
     (3, rows, planes_cols): y, planes."""

@@ -538,3 +538,26 @@ def test_conv_xproj_fused(ops, B, L, D, N, ld):
     u0, y0, _ = ops.conv_xproj_f32(x, cw, None, ws, 0)  # no bias, no planes
     u64 = torch.nn.functional.silu(torch.nn.functional.conv1d(xd, cw.double(), None, groups=D)).transpose(1, 2)
     assert (u0.double() - u64).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 1536, 384), (16384, 56, 768), (4096, 768, 24), (1000, 384, 768)])
+def test_linear_x3_training(ops, M, N, K):
+    """fp32 training Linear on the split-plane GEMM (opt-in, SIM_TRAIN_X3=1): y, dX and dW against float64.  y and dX are
+    at fp32-GEMM accuracy; dW contracts over all M rows, where the tensor core's truncating accumulation shows
+    (1.9e-5 at M = 16384) - one reason the path is not the default."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = dev(torch.randn(M, K, generator=g)).requires_grad_(True)
+    w = dev(torch.randn(N, K, generator=g) * K ** -0.5).requires_grad_(True)
+    dy = dev(torch.randn(M, N, generator=g))
+    y = ops.linear_x3_train(x, w)
+    y.backward(dy)
+    xd, wd, dyd = x.detach().double(), w.detach().double(), dy.double()
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+
+    e_y, e_dx, e_dw = rel(y, xd @ wd.t()), rel(x.grad, dyd @ wd), rel(w.grad, dyd.t() @ xd)
+    # the same three GEMMs as cuBLAS SGEMM (what the reference runs) for scale
+    s_y, s_dx, s_dw = rel(x.detach() @ w.detach().t(), xd @ wd.t()), rel(dy @ w.detach(), dyd @ wd), rel(dy.t() @ x.detach(), dyd.t() @ xd)
+    print(f"M={M} N={N} K={K}: x3 {e_y:.2e} {e_dx:.2e} {e_dw:.2e} | sgemm {s_y:.2e} {s_dx:.2e} {s_dw:.2e}")
+    assert e_y < 3e-6 and e_dx < 3e-6 and e_dw < 4e-5
