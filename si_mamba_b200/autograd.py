@@ -77,10 +77,10 @@ def _side_stream(device):
 
 _XPROJ_F32A = __import__("os").environ.get("SIM_XPROJ_F32A", "1") != "0"  # x_proj reads fp32 u and splits it in-kernel
 _CONV_XPROJ = __import__("os").environ.get("SIM_CONV_XPROJ", "0") != "0"  # causal conv fused into that x_proj kernel (measured slower: 60 us vs 17 + 19)
-# fp32 TRAINING projections on the split GEMM: opt-in.  Measured on C4 (fp32, 16 clouds): HLT 25.9 -> 28.8 ms (slower: the
-# per-step operand splits and transposes outweigh the GEMM time at 4096 rows), SAST 50.5 -> 49.5 ms; and dW, whose
-# contraction runs over all B*L rows, shows the tensor core's truncating fp32 accumulation (1.9e-5 at 16384 rows).
-_TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "0") != "0"
+# fp32 TRAINING projections (forward, dX, dW) on the split GEMM.  Measured on C4 (fp32, 16 clouds, whole step in a CUDA
+# graph): HLT 21.8 -> 19.4 ms, SAST 48.0 -> 37.0 ms.  dW contracts over all B*L rows with few output tiles: the kernel's
+# split-K both fills the SMs and keeps each tensor-core accumulation chain short (6e-7 against fp64, cuBLAS SGEMM 8e-7).
+_TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "1") != "0"
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 

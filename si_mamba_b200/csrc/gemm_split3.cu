@@ -22,6 +22,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "tma.cuh"
 
@@ -116,7 +118,7 @@ template <int BN, int NSTAGE_>
 __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
                                                              long ldd, int M, int N, int K, int n_tiles,
                                                              __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
-                                                             long po_plane) {
+                                                             long po_plane, int kb_per_split) {
   using Cfg = GemmCfg<BN, NSTAGE_>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
@@ -131,7 +133,13 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (blockIdx.x / n_tiles) * kBM;
   const int n0 = (blockIdx.x % n_tiles) * BN;
-  const int nk = (K + kBK - 1) / kBK;
+  // split-K (gridDim.y > 1; long contractions with few output tiles, e.g. a weight gradient): CTA y contracts k-blocks
+  // [kb0, kb0 + nk) and ADDS its partial tile to the zero-initialised output with 16-byte vector atomics.  Besides
+  // filling the SMs this bounds the length of one tensor-core accumulation chain (its fp32 adds truncate).
+  const int nk_all = (K + kBK - 1) / kBK;
+  const int kb0 = blockIdx.y * kb_per_split;
+  const int nk = gridDim.y > 1 ? min(kb_per_split, nk_all - kb0) : nk_all;
+  const bool accumulate_out = gridDim.y > 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm.x);
@@ -158,8 +166,8 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
         if (kb >= NSTAGE) mbar_wait(&empty[s], ((kb / NSTAGE) - 1) & 1);
         unsigned char* st = smem + s * Cfg::STAGE;
         mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
-        tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
-        tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+        tma_load_3d(st, &tm.x, (kb0 + kb) * kBK, m0, 0, &full[s]);
+        tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, (kb0 + kb) * kBK, n0, 0, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -212,7 +220,8 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
         const int gm = m0 + quad * 32 + row, gn = n0 + c * 32 + col;
         if (gm < M && gn < N) {
           const float4 o = *reinterpret_cast<const float4*>(stg + row * Cfg::STG_LD + col);
-          *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = o;
+          if (accumulate_out) atomicAdd(reinterpret_cast<float4*>(Y + (long)gm * ldd + gn), o);
+          else *reinterpret_cast<float4*>(Y + (long)gm * ldd + gn) = o;
           // optionally also emit the first po_cols output columns as split bf16 planes: the operand of a GEMM that
           // consumes them (x_proj -> dt_proj), saving a separate split pass
           if (po && gn < po_cols) split3_store4(po + (long)gm * po_ld + gn, po_plane, o);
@@ -623,8 +632,20 @@ int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cu
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 attr");
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
-  kern<<<m_tiles * n_tiles, 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, static_cast<__nv_bfloat16*>(po), po_cols,
-                                                      po_ld, po_plane);
+  // split-K when the output tiles cannot fill the SMs and the contraction is long (>= 32 k-blocks = 1024): chunks of at
+  // least 8 k-blocks, enough of them to give every SM a CTA
+  const int nk = (K + kBK - 1) / kBK, tiles = m_tiles * n_tiles;
+  int splits = 1, kps = nk;
+  static const int splitk = [] { const char* e = getenv("SIM_GEMM_SPLITK"); return e ? atoi(e) : 1; }();
+  if (splitk && !po && tiles * 2 <= 148 && nk >= 32) {
+    splits = std::min((148 + tiles - 1) / tiles, nk / 8);
+    kps = (nk + splits - 1) / splits;
+    splits = (nk + kps - 1) / kps;
+  }
+  if (splits > 1 && cudaMemset2DAsync(Y, (size_t)ldd * 4, 0, (size_t)N * 4, M, stream) != cudaSuccess)
+    return check_launch("gemm_split3 memset");
+  kern<<<dim3(tiles, splits), 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, static_cast<__nv_bfloat16*>(po),
+                                                        po_cols, po_ld, po_plane, kps);
   return check_launch("gemm_split3");
 }
 

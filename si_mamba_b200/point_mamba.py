@@ -39,6 +39,48 @@ class RMSNorm(nn.Module):
 _ENCODER_ROWS = __import__("os").environ.get("SIM_ENCODER_ROWS", "1") != "0"
 
 
+class _conv_tf32_policy:
+    """Matmuls that stand in for the reference's Conv1d layers follow torch.backends.cudnn.allow_tf32 (cuDNN's switch,
+    True by default) instead of the matmul switch."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+class _ConvLinear(torch.autograd.Function):
+    """F.linear(x (rows, K), w (N, K), b) whose forward, dgrad and wgrad GEMMs all run under _conv_tf32_policy (a plain
+    F.linear would run its backward GEMMs after the policy scope has closed)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        with _conv_tf32_policy():
+            return F.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = db = None
+        with _conv_tf32_policy():
+            if ctx.needs_input_grad[0]:
+                dx = dy @ w
+            if ctx.needs_input_grad[1]:
+                dw = dy.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def _conv_linear(x, w, b=None):
+    return _ConvLinear.apply(x, w, b)
+
+
 class Encoder(nn.Module):
     """Per-patch mini-PointNet (models/point_mamba.py:42-73); dense contractions stay on cuDNN / cuBLAS."""
 
@@ -95,25 +137,22 @@ class Encoder(nn.Module):
         """Differentiable form of forward() on the (B*G*M, C) point matrix: the 1x1 convolutions as row-major linears
         (cuBLAS forward / dgrad / wgrad instead of cuDNN's NCHW wgrad reduction, which was 10 % of the C2 training step),
         BatchNorm1d on the 2-D rows (same statistics and running buffers as on (N, C, L)), and the conv over
-        cat([global, local]) split into a per-point and a per-patch linear.  Same TF32 policy as the convolutions."""
+        cat([global, local]) split into a per-point and a per-patch linear.  Same TF32 policy as the convolutions they
+        replace - in the backward too (_conv_linear), where cuDNN's dgrad / wgrad follow cudnn.allow_tf32 as well."""
         bs, g, n, _ = point_groups.shape
         BG, P = bs * g, bs * g * n
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-        try:
-            c0, bn0, c3 = self.first_conv[0], self.first_conv[1], self.first_conv[3]
-            d0, bn1, d3 = self.second_conv[0], self.second_conv[1], self.second_conv[3]
-            h = F.relu(bn0(F.linear(point_groups.reshape(P, 3), c0.weight[:, :, 0], c0.bias)))
-            f = F.linear(h, c3.weight[:, :, 0], c3.bias)                                            # (P, 256)
-            fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
-            c_loc = f.shape[-1]
-            w3 = d0.weight[:, :, 0]
-            t = F.linear(f, w3[:, c_loc:]).view(BG, n, -1) + F.linear(fg, w3[:, :c_loc], d0.bias)[:, None, :]
-            h2 = F.relu(bn1(t.reshape(P, -1)))
-            o = F.linear(h2, d3.weight[:, :, 0], d3.bias)                                           # (P, C)
-            return o.view(BG, n, -1).max(dim=1).values.view(bs, g, self.encoder_channel)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        lin = _conv_linear if (point_groups.dtype == torch.float32 and not torch.is_autocast_enabled()) else F.linear
+        c0, bn0, c3 = self.first_conv[0], self.first_conv[1], self.first_conv[3]
+        d0, bn1, d3 = self.second_conv[0], self.second_conv[1], self.second_conv[3]
+        h = F.relu(bn0(lin(point_groups.reshape(P, 3), c0.weight[:, :, 0], c0.bias)))
+        f = lin(h, c3.weight[:, :, 0], c3.bias)                                                 # (P, 256)
+        fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
+        c_loc = f.shape[-1]
+        w3 = d0.weight[:, :, 0]
+        t = lin(f, w3[:, c_loc:], None).view(BG, n, -1) + lin(fg, w3[:, :c_loc], d0.bias)[:, None, :]
+        h2 = F.relu(bn1(t.reshape(P, -1)))
+        o = lin(h2, d3.weight[:, :, 0], d3.bias)                                                # (P, C)
+        return o.view(BG, n, -1).max(dim=1).values.view(bs, g, self.encoder_channel)
 
     def forward(self, point_groups):
         """point_groups (B, G, M, 3) -> (B, G, C)."""

@@ -542,9 +542,8 @@ def test_conv_xproj_fused(ops, B, L, D, N, ld):
 
 @pytest.mark.parametrize("M,N,K", [(4096, 1536, 384), (16384, 56, 768), (4096, 768, 24), (1000, 384, 768)])
 def test_linear_x3_training(ops, M, N, K):
-    """fp32 training Linear on the split-plane GEMM (opt-in, SIM_TRAIN_X3=1): y, dX and dW against float64.  y and dX are
-    at fp32-GEMM accuracy; dW contracts over all M rows, where the tensor core's truncating accumulation shows
-    (1.9e-5 at M = 16384) - one reason the path is not the default."""
+    """fp32 training Linear on the split-plane GEMM: y, dX and dW against float64 at fp32-GEMM accuracy.  dW contracts
+    over all M rows with few output tiles -> split-K (short accumulation chains; one long chain drifts to 1.9e-5)."""
     g = torch.Generator().manual_seed(M + N + K)
     x = dev(torch.randn(M, K, generator=g)).requires_grad_(True)
     w = dev(torch.randn(N, K, generator=g) * K ** -0.5).requires_grad_(True)
@@ -560,4 +559,4 @@ def test_linear_x3_training(ops, M, N, K):
     # the same three GEMMs as cuBLAS SGEMM (what the reference runs) for scale
     s_y, s_dx, s_dw = rel(x.detach() @ w.detach().t(), xd @ wd.t()), rel(dy @ w.detach(), dyd @ wd), rel(dy.t() @ x.detach(), dyd.t() @ xd)
     print(f"M={M} N={N} K={K}: x3 {e_y:.2e} {e_dx:.2e} {e_dw:.2e} | sgemm {s_y:.2e} {s_dx:.2e} {s_dw:.2e}")
-    assert e_y < 3e-6 and e_dx < 3e-6 and e_dw < 4e-5
+    assert e_y < 3e-6 and e_dx < 3e-6 and e_dw < 3e-6

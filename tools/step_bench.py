@@ -169,9 +169,7 @@ def main():
                     loss.backward()
 
                 tag = ""
-                if args.graph and not ddp and os.environ.get("SIM_GRAPH_C4") == "1":  # off: see note below
-                    # torch 2.11 + cuDNN pick a 144 GiB workspace for the head's Conv1d backward under stream capture
-                    # (the same step needs 2 GiB eagerly), so C4 stays eager by default
+                if args.graph and not ddp:
                     from si_mamba_b200.train import GraphedStep
                     noise = torch.rand(B, 128, device=dev)  # HLT tie-break noise: a graph input
 
