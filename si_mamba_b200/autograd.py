@@ -84,6 +84,29 @@ _TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "1") != "0"
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
 
 
+class _SplitCols(torch.autograd.Function):
+    """x (..., sum(sizes)) -> views x[..., a:b] per size; the backward writes the pieces' gradients side by side with
+    one torch.cat (autograd's own SliceBackward allocates a zero tensor of the full shape per slice and then adds them:
+    10 % of the C2 training step for the in_proj output alone)."""
+
+    @staticmethod
+    def forward(ctx, x, *sizes):
+        ctx.sizes = sizes
+        ctx.meta = (x.shape, x.dtype, x.device)
+        outs, a = [], 0
+        for n in sizes:
+            outs.append(x[..., a:a + n])
+            a += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        shape, dtype, device = ctx.meta
+        parts = [g if g is not None else torch.zeros(*shape[:-1], n, dtype=dtype, device=device)
+                 for g, n in zip(grads, ctx.sizes)]
+        return (torch.cat(parts, dim=-1),) + (None,) * len(ctx.sizes)
+
+
 def wants_split3(hidden_dtype: torch.dtype, in_proj_w: torch.Tensor, d_model: int) -> bool:
     """True when the mixer would consume its input as a Split3 (fp32 inference on the x3 GEMM path): the Block's
     fused add + LayerNorm then writes the split planes directly instead of an fp32 tensor."""
@@ -140,7 +163,10 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         join_z = (cur, side, z)
     else:
         xz = linear(hidden if isinstance(hidden, ops.Split3) else hidden.to(act), w_in)  # (B, L, 2*d_inner)
-        x, z = xz[..., :d_inner], xz[..., d_inner:]
+        if need_grad:
+            x, z = _SplitCols.apply(xz, d_inner, d_inner)
+        else:
+            x, z = xz[..., :d_inner], xz[..., d_inner:]
     if need_grad:
         u = u_op = ops.CausalConv1dTM.apply(x, conv_w, conv_b, True)
     elif (x3 and _XPROJ_F32A and _CONV_XPROJ and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64 and conv_w.shape[-1] == 4
@@ -184,10 +210,15 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         if dt_planes is None:
             dt_planes = ops.split3(x_dbl[..., :32])
         dt = ops.linear_split3(dt_planes, wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
+        Bm = x_dbl[..., dt_rank:dt_rank + d_state]
+        Cm = x_dbl[..., dt_rank + d_state:]
+    elif need_grad and x_dbl.shape[-1] == dt_rank + 2 * d_state:
+        dt_in, Bm, Cm = _SplitCols.apply(x_dbl, dt_rank, d_state, d_state)
+        dt = linear(dt_in, w_dt)  # bias is applied inside the scan
     else:
         dt = linear(x_dbl[..., :dt_rank], w_dt)  # bias is applied inside the scan
-    Bm = x_dbl[..., dt_rank:dt_rank + d_state]
-    Cm = x_dbl[..., dt_rank + d_state:]
+        Bm = x_dbl[..., dt_rank:dt_rank + d_state]
+        Cm = x_dbl[..., dt_rank + d_state:]
     if join_z is not None:
         cur, side, z = join_z
         cur.wait_stream(side)

@@ -477,6 +477,153 @@ __global__ void __launch_bounds__(128) causal_conv1d_bwd_kernel(const T* __restr
   }
 }
 
+// Tiled backward (default when D % 32 == 0).  The register-window kernel above issues one dependent global load per
+// step per thread and 20 atomics per thread (195 us at the C2 layer shape, 0.12 of the HBM roofline).  Here a CTA owns
+// 32 channels of one cloud and walks L in 64-step tiles: x (3-row halo on both sides) and dy (3 rows past the end) are
+// staged in shared memory with 16-byte loads, dp = dy * silu'(pre) is formed in place, dx comes out of shared memory, and
+// dw / db accumulate in registers over the whole sequence -> one warp-shuffle + shared-memory reduction and 160 atomics
+// per CTA at the end.
+constexpr int kBwdCH = 32, kBwdTC = 64, kBwdLC = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(256) causal_conv1d_bwd_tiled_kernel(const T* __restrict__ x, long ld_x,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ bias,
+                                                                      const T* __restrict__ dy, long ld_dy,
+                                                                      T* __restrict__ dx, long ld_dx,
+                                                                      float* __restrict__ dw, float* __restrict__ db, int L,
+                                                                      int D, int silu) {
+  constexpr int CH = kBwdCH, TC = kBwdTC, NV = CH / 4, NRG = 256 / NV;  // 8 channel quads x 32 row groups
+  __shared__ __align__(16) float xs[(TC + 2 * (kConvW - 1)) * CH];  // x rows t0-3 .. t0+TC+2
+  __shared__ __align__(16) float dp[(TC + kConvW - 1) * CH];        // dy, then dp, rows t0 .. t0+TC+2
+  __shared__ float red[8][NV][20];
+  const int nchunk = D / CH;
+  const int b = blockIdx.x / nchunk, c0 = (blockIdx.x % nchunk) * CH;
+  const int tid = threadIdx.x, c4 = tid % NV, rg = tid / NV;
+  const int d0 = c0 + 4 * c4;
+  float wr[4][kConvW];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long)(d0 + c) * kConvW);
+    wr[c][0] = wv.x, wr[c][1] = wv.y, wr[c][2] = wv.z, wr[c][3] = wv.w;
+  }
+  const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const T* xb = x + ((long)b * L) * ld_x + d0;
+  const T* gb = dy + ((long)b * L) * ld_dy + d0;
+  T* ob = dx + ((long)b * L) * ld_dx + d0;
+  float dwa[4][kConvW] = {};
+  float dba[4] = {};
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // tiles of this CTA: steps [t_begin, t_end) (gridDim.y chunks of kBwdLC steps keep ~7 waves of CTAs in flight); the
+  // next tile's rows are fetched into registers while the current tile is processed (software pipeline, no smem cost)
+  constexpr int NLX = (TC + 2 * (kConvW - 1) + NRG - 1) / NRG, NLG = (TC + kConvW - 1 + NRG - 1) / NRG;
+  const int t_begin = blockIdx.y * kBwdLC, t_end = min(L, t_begin + kBwdLC);
+  float4 px[NLX], pg[NLG];
+  auto fetch = [&](int t0) {
+#pragma unroll
+    for (int i = 0; i < NLX; ++i) {
+      const int r = rg + i * NRG, t = t0 - (kConvW - 1) + r;
+      px[i] = (r < TC + 2 * (kConvW - 1) && t >= 0 && t < L) ? Vec4<T>::load(xb + (long)t * ld_x) : zero4;
+    }
+#pragma unroll
+    for (int i = 0; i < NLG; ++i) {
+      const int r = rg + i * NRG, t = t0 + r;
+      pg[i] = (r < TC + kConvW - 1 && t < L) ? Vec4<T>::load(gb + (long)t * ld_dy) : zero4;
+    }
+  };
+  fetch(t_begin);
+  for (int t0 = t_begin; t0 < t_end; t0 += TC) {
+#pragma unroll
+    for (int i = 0; i < NLX; ++i) {
+      const int r = rg + i * NRG;
+      if (r < TC + 2 * (kConvW - 1)) *reinterpret_cast<float4*>(xs + r * CH + 4 * c4) = px[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NLG; ++i) {
+      const int r = rg + i * NRG;
+      if (r < TC + kConvW - 1) *reinterpret_cast<float4*>(dp + r * CH + 4 * c4) = pg[i];
+    }
+    __syncthreads();
+    if (t0 + TC < t_end) fetch(t0 + TC);
+    // dp[s] = dy[s] * silu'(pre[s]) in place; parameter gradients from the rows this tile owns (r < TC)
+    for (int r = rg; r < TC + kConvW - 1; r += NRG) {
+      float4 xv[kConvW];
+#pragma unroll
+      for (int j = 0; j < kConvW; ++j) xv[j] = *reinterpret_cast<const float4*>(xs + (r + j) * CH + 4 * c4);  // x[s-3+j]
+      float4 d = *reinterpret_cast<const float4*>(dp + r * CH + 4 * c4);
+      if (silu) {
+        float4 pre = bv;
+#pragma unroll
+        for (int j = 0; j < kConvW; ++j) {
+          pre.x = fmaf(wr[0][j], xv[j].x, pre.x);
+          pre.y = fmaf(wr[1][j], xv[j].y, pre.y);
+          pre.z = fmaf(wr[2][j], xv[j].z, pre.z);
+          pre.w = fmaf(wr[3][j], xv[j].w, pre.w);
+        }
+        const float sx = sigmoid_f(pre.x), sy = sigmoid_f(pre.y), sz = sigmoid_f(pre.z), sw = sigmoid_f(pre.w);
+        d.x = d.x * sx * (1.f + pre.x * (1.f - sx));
+        d.y = d.y * sy * (1.f + pre.y * (1.f - sy));
+        d.z = d.z * sz * (1.f + pre.z * (1.f - sz));
+        d.w = d.w * sw * (1.f + pre.w * (1.f - sw));
+        *reinterpret_cast<float4*>(dp + r * CH + 4 * c4) = d;
+      }
+      if (r < TC && t0 + r < t_end) {  // each step's parameter gradient belongs to exactly one chunk
+#pragma unroll
+        for (int j = 0; j < kConvW; ++j) {
+          dwa[0][j] = fmaf(d.x, xv[j].x, dwa[0][j]);
+          dwa[1][j] = fmaf(d.y, xv[j].y, dwa[1][j]);
+          dwa[2][j] = fmaf(d.z, xv[j].z, dwa[2][j]);
+          dwa[3][j] = fmaf(d.w, xv[j].w, dwa[3][j]);
+        }
+        dba[0] += d.x, dba[1] += d.y, dba[2] += d.z, dba[3] += d.w;
+      }
+    }
+    __syncthreads();
+    // dx[t] = sum_j w_j dp[t+3-j]
+    for (int r = rg; r < TC && t0 + r < t_end; r += NRG) {
+      float4 o = zero4;
+#pragma unroll
+      for (int j = 0; j < kConvW; ++j) {
+        const float4 q = *reinterpret_cast<const float4*>(dp + (r + kConvW - 1 - j) * CH + 4 * c4);
+        o.x = fmaf(wr[0][j], q.x, o.x);
+        o.y = fmaf(wr[1][j], q.y, o.y);
+        o.z = fmaf(wr[2][j], q.z, o.z);
+        o.w = fmaf(wr[3][j], q.w, o.w);
+      }
+      Vec4<T>::store(ob + (long)(t0 + r) * ld_dx, o);
+    }
+    __syncthreads();  // the next tile overwrites xs / dp
+  }
+  // reduce dw / db over the 32 row groups: lanes with equal (lane % 8) inside a warp, then the 8 warps
+  float vals[20];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int j = 0; j < kConvW; ++j) vals[c * kConvW + j] = dwa[c][j];
+    vals[16 + c] = dba[c];
+  }
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+    vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], 8);
+    vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], 16);
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane < NV) {
+#pragma unroll
+    for (int i = 0; i < 20; ++i) red[warp][lane][i] = vals[i];
+  }
+  __syncthreads();
+  if (tid < NV * 20) {
+    const int q = tid / 20, i = tid % 20;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][q][i];
+    if (i < 16) atomicAdd(dw + (long)(c0 + 4 * q + i / kConvW) * kConvW + (i % kConvW), v);
+    else if (db) atomicAdd(db + c0 + 4 * q + (i - 16), v);
+  }
+}
+
 int causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float* bias, const void* dy, long ld_dy,
                       void* dx, long ld_dx, float* dw, float* db, int batch, int L, int D, int width, int silu,
                       int dtype, cudaStream_t stream) {
@@ -489,6 +636,19 @@ int causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float* bia
   SIM_REQUIRE(((uintptr_t)x & vmask) == 0 && ((uintptr_t)dy & vmask) == 0 && ((uintptr_t)dx & vmask) == 0 &&
                   aligned16(w) && ld_x % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && (!bias || aligned16(bias)),
               SIM_ERR_ALIGN, "causal_conv1d_bwd: tensors need vector-aligned bases and row strides");
+  static const int force_window = [] { const char* e = getenv("SIM_CONV_BWD_WINDOW"); return e ? atoi(e) : 0; }();
+  if (D % kBwdCH == 0 && !force_window) {
+    const dim3 grid(batch * (D / kBwdCH), (L + kBwdLC - 1) / kBwdLC);
+    if (dtype == 0)
+      causal_conv1d_bwd_tiled_kernel<float><<<grid, 256, 0, stream>>>(
+          static_cast<const float*>(x), ld_x, w, bias, static_cast<const float*>(dy), ld_dy, static_cast<float*>(dx), ld_dx,
+          dw, db, L, D, silu);
+    else
+      causal_conv1d_bwd_tiled_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(x), ld_x, w, bias, static_cast<const __nv_bfloat16*>(dy), ld_dy,
+          static_cast<__nv_bfloat16*>(dx), ld_dx, dw, db, L, D, silu);
+    return check_launch("causal_conv1d_bwd_tiled");
+  }
   constexpr int TC = 64;
   const long items = (long)batch * ((L + TC - 1) / TC) * (D / 4);
   const int grid = (int)((items + 127) / 128);

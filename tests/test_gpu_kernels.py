@@ -341,7 +341,7 @@ def test_scan_backward_channel_major_api(ops):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("B,D,L", [(2, 64, 5), (2, 768, 130), (1, 128, 64)])
+@pytest.mark.parametrize("B,D,L", [(2, 64, 5), (2, 768, 130), (1, 128, 64), (3, 100, 70), (2, 96, 257)])
 def test_conv_backward_vs_oracle(ops, dtype, tol, B, D, L):
     g = torch.Generator().manual_seed(L + D)
     x = torch.randn(B, L, D, generator=g).to(dtype)
