@@ -57,8 +57,9 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
 // and the CTA's shared memory drops to the operand tiles, so 3x more warps are resident.
 constexpr int SUB = 4;  // steps per sub-tile
 
-template <typename T, int CH_, int LPC_>
+template <typename T, int CH_, int LPC_, bool SAVE_A_ = false>
 struct BwdCfg {
+  static constexpr bool SAVE_A = SAVE_A_;  // keep exp(dt A) of a recomputed sub-tile in registers for its adjoint steps
   static constexpr int CH = CH_;
   static constexpr int LPC = LPC_;       // lanes per channel
   static constexpr int S = kN / LPC_;    // states per thread
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   float* my_acc = a_dBC + warp * TT * 2 * kN + (vfin < S ? sub * S + vfin : kN + sub * S + vfin - S);
 
   // one forward step of this thread's 8 states: hn = a * hp + dt*u*B; returns the thread's share of <h, C>
-  auto fwd_step = [&](int r, const float (&hp)[S], float (&hn)[S]) -> float {
+  auto fwd_step = [&](int r, const float (&hp)[S], float (&hn)[S], float* aout = nullptr) -> float {
     const float4 w = w4[r * CH + c];
     const float dtv = w.x, dtu = w.w;
     float2 y2 = make_float2(0.f, 0.f);
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
         const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
         const float2 bu = __fmul2_rn(make_float2(dtu, dtu), make_float2(Bv[i], Bv[i + 1]));
         const float2 h2 = __ffma2_rn(a, make_float2(hp[n], hp[n + 1]), bu);
+        if (aout) aout[n] = a.x, aout[n + 1] = a.y;  // kept for the adjoint step (SAVE_A)
         hn[n] = h2.x, hn[n + 1] = h2.y;
         y2 = __ffma2_rn(h2, make_float2(Cv[i], Cv[i + 1]), y2);
       }
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     for (int sb = TT / SUB - 1; sb >= 0; --sb) {
       const int rb = SUB * sb;
       float hs[S], hq[SUB][S];
+      [[maybe_unused]] float aq[Cfg::SAVE_A ? SUB : 1][S];  // exp(dt A) of the sub-tile's steps
       if (sb == 0) {
 #pragma unroll
         for (int n = 0; n < S; ++n) hs[n] = h0[n];
@@ -263,7 +266,8 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < SUB; ++i) {
         const int r = rb + i;
-        float y = (i == 0) ? fwd_step(r, hs, hq[0]) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i]);
+        float* ao = Cfg::SAVE_A ? aq[Cfg::SAVE_A ? i : 0] : nullptr;
+        float y = (i == 0) ? fwd_step(r, hs, hq[0], ao) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i], ao);
         y = sum_subs(y);
         if (sub == 0) w_y[r * CH + c] = y;  // <h, C>; D u is added in the epilogue
       }
@@ -286,8 +290,13 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
             const int n = 4 * q + j;
             const float2 hprev = (i == 0) ? make_float2(hs[n], hs[n + 1]) : make_float2(hq[i > 0 ? i - 1 : 0][n], hq[i > 0 ? i - 1 : 0][n + 1]);
             const float2 dhn = __ffma2_rn(dy2, make_float2(Cv[j], Cv[j + 1]), make_float2(dh[n], dh[n + 1]));  // dL/dh_t
-            const float2 x = __fmul2_rn(dt2, make_float2(A2[n], A2[n + 1]));
-            const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            float2 a;
+            if constexpr (Cfg::SAVE_A) {
+              a = make_float2(aq[Cfg::SAVE_A ? i : 0][n], aq[Cfg::SAVE_A ? i : 0][n + 1]);
+            } else {
+              const float2 x = __fmul2_rn(dt2, make_float2(A2[n], A2[n + 1]));
+              a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            }
             const float2 rc = __fmul2_rn(dy2, make_float2(hq[i][n], hq[i][n + 1]));
             const float2 rb2 = __fmul2_rn(dhn, dtu2);
             red[S + n] = rc.x, red[S + n + 1] = rc.y;
@@ -355,9 +364,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   if (p.ddbias) atomicAdd(p.ddbias + c0 + ce, dbias);
 }
 
-template <typename T, int CH, int LPC>
+template <typename T, int CH, int LPC, bool SAVE_A = false>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = BwdCfg<T, CH, LPC>;
+  using Cfg = BwdCfg<T, CH, LPC, SAVE_A>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
@@ -398,7 +407,9 @@ int selective_scan_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
     SIM_REQUIRE(aligned16(ptrs[i]) && (lds[i] * es) % 16 == 0, SIM_ERR_ALIGN,
                 "selective_scan_bwd: tensor %d needs a 16-byte aligned base and row stride (TMA tensor maps)", i);
   }
-  static const int lpc = [] { const char* e = getenv("SIM_SCAN_BWD_LPC"); return e ? atoi(e) : 4; }();  // bench override
+  static const int lpc = [] { const char* e = getenv("SIM_SCAN_BWD_LPC"); return e ? atoi(e) : 41; }();  // bench override (4: recompute exp(dt A) in the adjoint, 2: two lanes per channel)
+  if (lpc == 41)  // 4 lanes per channel + exp(dt A) kept from the recompute (one exp less per state-step, 16 registers more)
+    return dtype == 0 ? launch_bwd<float, 32, 4, true>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true>(p, dtype, stream);
   if (lpc == 4)
     return dtype == 0 ? launch_bwd<float, 32, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4>(p, dtype, stream);
   return dtype == 0 ? launch_bwd<float, 32, 2>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 2>(p, dtype, stream);
