@@ -6,17 +6,16 @@
 // w.r.t. u, delta, z (token-major, input dtype), B, C (fp32, summed over channels), A, D, bias (fp32).
 //
 // No (B, D, L, N) state tensor is stored: the training forward keeps only the state at the start of every
-// kScanTile-step tile (ScanParams::ckpt, one fp32 tensor the size of an activation).  Per tile, walking the
-// sequence backwards, this kernel (1) recomputes h_t forward from the checkpoint into shared memory and y_t on the
-// fly, (2) runs the adjoint recurrence dh_{t-1} = a_t dh_t in reverse.  Thread = one channel x 8 of the 16 states
-// (two lanes per channel: reductions over states are thread-local plus one shuffle); dB / dC (reductions over
-// channels) go through a transposed warp butterfly (16 values over the warp's 16 channels) and one shared + one
-// global fp32 atomic per (t, n) per CTA.  (r01 first version: one thread per channel x 16 states, one warp per
-// CTA, 5 warps per SM: 1742 us at the C2 layer shape.)
-// Operand tiles arrive by TMA tensor copies exactly as in the forward kernel.
+// kScanTile-step tile (ScanParams::ckpt, one fp32 tensor the size of an activation), which arrives with the operand
+// tiles (TMA tensor copies + one bulk copy).  Per tile, walking the sequence backwards, the kernel recomputes the states
+// sub-tile by sub-tile into registers and runs the adjoint recurrence dh_{t-1} = a_t dh_t straight from them (see BwdCfg).
+// Thread = one channel x 16 / LPC states (default LPC = 4 lanes per channel): reductions over states are thread-local
+// plus log2(LPC) shuffles; dB / dC (reductions over channels) go through a transposed warp butterfly over the warp's
+// 32 / LPC channels, per-warp shared-memory accumulators and one global fp32 atomic per (t, n) per CTA.
+// History (profiles/r01_scan_bwd_ncu.md): one thread per channel x 16 states, 1742 us at the C2 layer shape -> 878 us.
 //
-// Roofline class: SM issue (about 25 instructions per state update); HBM algorithmic bytes are
-// (5 reads + 3 writes) * E * s + checkpoint E * 4 + O(S).  First version - correctness first.
+// Roofline class: SM issue (about 45 instructions per pair of state updates); HBM algorithmic bytes are
+// (4 reads + 3 writes) * E * s + checkpoint E * 4 + O(S).
 
 #include <stdlib.h>
 
@@ -47,8 +46,6 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
                      __uint_as_float(r.y & 0xffff0000u));
 }
 
-// Thread = (channel, 8 of the 16 states): two lanes per channel (LPC = 2), 16 channels per warp.
-//
 // State history without a (step x state) buffer.  The first cut kept every h_t of a 16-step tile in shared memory
 // (32 KB per two warps): 6 warps per SM, ncu: 1.3 warps per scheduler, issue 30 %, 1.29 ms at the C2 layer shape.  Now a
 // tile is walked as four 4-step sub-tiles, back to front: a forward sweep over steps 0..11 leaves the sub-tile start
@@ -57,7 +54,7 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
 // and the CTA's shared memory drops to the operand tiles, so 3x more warps are resident.
 constexpr int SUB = 4;  // steps per sub-tile
 
-template <typename T, int CH_, int LPC_, bool SAVE_A_ = false>
+template <typename T, int CH_, int LPC_, bool SAVE_A_ = false, int NS_ = 2>
 struct BwdCfg {
   static constexpr bool SAVE_A = SAVE_A_;  // keep exp(dt A) of a recomputed sub-tile in registers for its adjoint steps
   static constexpr int CH = CH_;
@@ -65,7 +62,9 @@ struct BwdCfg {
   static constexpr int S = kN / LPC_;    // states per thread
   static constexpr int NT = LPC_ * CH_;  // threads per CTA
   static constexpr int NW = NT / 32;
-  static constexpr int NS = 2;
+  // raw TMA stages.  The pre-pass consumes a stage completely, so ONE stage already lets the next tile's copies fly during
+  // the whole recurrence phase; the second stage only costs shared memory (fp32: 3 -> 4 CTAs per SM, bf16: 4 -> 5)
+  static constexpr int NS = NS_;
   static constexpr int RAW_MAIN = TT * CH_ * (int)sizeof(T);
   static constexpr int RAW_BC = TT * kN * (int)sizeof(T);
   static constexpr int RAW_CK = CH_ * kN * 4;                   // tile-start states of the CTA's channels (fp32)
@@ -364,9 +363,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   if (p.ddbias) atomicAdd(p.ddbias + c0 + ce, dbias);
 }
 
-template <typename T, int CH, int LPC, bool SAVE_A = false>
+template <typename T, int CH, int LPC, bool SAVE_A = false, int NS = 2>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = BwdCfg<T, CH, LPC, SAVE_A>;
+  using Cfg = BwdCfg<T, CH, LPC, SAVE_A, NS>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
@@ -408,7 +407,12 @@ int selective_scan_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
                 "selective_scan_bwd: tensor %d needs a 16-byte aligned base and row stride (TMA tensor maps)", i);
   }
   static const int lpc = [] { const char* e = getenv("SIM_SCAN_BWD_LPC"); return e ? atoi(e) : 41; }();  // bench override (4: recompute exp(dt A) in the adjoint, 2: two lanes per channel)
-  if (lpc == 41)  // 4 lanes per channel + exp(dt A) kept from the recompute (one exp less per state-step, 16 registers more)
+  if (lpc == 411)  // ... and a single raw stage
+    return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true, 1>(p, dtype, stream);
+  if (lpc == 41)  // default: 4 lanes per channel, exp(dt A) kept from the recompute (one exp less per state-step, 17 registers
+                  // more); fp32 with one raw stage = 4 CTAs per SM (440 -> 431 us), bf16 keeps two (one: 878 -> 892 us)
+    return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true>(p, dtype, stream);
+  if (lpc == 412)
     return dtype == 0 ? launch_bwd<float, 32, 4, true>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true>(p, dtype, stream);
   if (lpc == 4)
     return dtype == 0 ? launch_bwd<float, 32, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4>(p, dtype, stream);
