@@ -192,11 +192,17 @@ int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, 
  * sim_group_bias_relu x[p,c] = relu(x[p,c] + gvec[p / M, c]) in place: the conv over cat([global, local]) (:67-69) split
  *                     into a per-point and a per-patch GEMM, recombined here;
  * sim_layernorm_mean  out[b,c] += mean over the L tokens of LayerNorm(x[b,t,:])[c] (self.norm(x).mean(1), :1122-1123;
- *                     fp32, out zeroed by the caller). */
+ *                     fp32, out zeroed by the caller);
+ * sim_mlp3_relu_rows  y = W3 relu(W2 relu(W1 x + b1) + b2) + b3 per row: cls_head_finetune in eval mode (:1124-1130) with
+ *                     BatchNorm folded into W / b by the caller; weights TRANSPOSED (in, out) fp32, widths d1, d2, d3 <= 256,
+ *                     biases may be NULL. */
 int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream);
 int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, sim_stream_t stream);
 int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
                        sim_stream_t stream);
+int sim_mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1,
+                       const float* w2t, const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y,
+                       long ldy, sim_stream_t stream);
 
 /* a-19: 3-nearest-centre inverse-squared-distance interpolation (PointNetFeaturePropagation.forward,
  * part_segmentation/models/pointnet2_utils.py:273-311; replaces square_distance + full sort + index_points gathers).

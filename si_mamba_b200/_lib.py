@@ -70,6 +70,7 @@ SIGNATURES = {
     "sim_conv_xproj_f32": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _p, _l, _i, _i, _i, _i, _p, _i, _l, _l, _p]),
     "sim_group_max": (_i, [_p, _p, _l, _i, _i, _i, _p]),
     "sim_group_bias_relu": (_i, [_p, _p, _l, _i, _i, _i, _p]),
+    "sim_mlp3_relu_rows": (_i, [_p, _l, _l, _i, _p, _p, _i, _p, _p, _i, _p, _p, _i, _p, _l, _p]),
     "sim_layernorm_mean": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
     "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),

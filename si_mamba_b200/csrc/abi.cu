@@ -311,6 +311,13 @@ int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int 
   return sim::group_bias_relu(x, gvec, rows, M, C, dtype, static_cast<cudaStream_t>(stream));
 }
 
+int sim_mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1,
+                       const float* w2t, const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y,
+                       long ldy, sim_stream_t stream) {
+  return sim::mlp3_relu_rows(x, ldx, rows, d0, w1t, b1, d1, w2t, b2, d2, w3t, b3, d3, y, ldy,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
                        sim_stream_t stream) {
   return sim::layernorm_mean(x, gamma, beta, out, B, L, C, eps, static_cast<cudaStream_t>(stream));

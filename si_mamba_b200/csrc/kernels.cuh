@@ -113,6 +113,9 @@ int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, c
                       float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream);
 int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream);
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream);
+int mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1, const float* w2t,
+                   const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y, long ldy,
+                   cudaStream_t stream);
 int layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
                    cudaStream_t stream);
 int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,

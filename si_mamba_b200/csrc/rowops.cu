@@ -421,6 +421,67 @@ int layernorm_mean(const float* x, const float* gamma, const float* beta, float*
   return check_launch("layernorm_mean");
 }
 
+// ----------------------------------------------------------------------------- classifier head (a-14 tail)
+// y = W3 relu(W2 relu(W1 x + b1) + b2) + b3 for a handful of rows: cls_head_finetune in eval mode
+// (models/point_mamba.py:1124-1130: Linear-BN-ReLU-Dropout x2 + Linear; BatchNorm folded into W / b by the caller,
+// Dropout is the identity).  The reference's 32-row GEMMs are pure launch + latency (11 small kernels, ~80 us cold); here
+// one CTA per row keeps the activations in shared memory, weights are pre-transposed (in, out) so a warp reads 128
+// contiguous bytes per k, and the contraction is split over kMlpParts thread groups to shorten the dependent FMA chain.
+constexpr int kMlpWidth = 256, kMlpParts = 4;
+
+__device__ __forceinline__ void mlp_layer(const float* __restrict__ in, int din, const float* __restrict__ wt,
+                                          const float* __restrict__ b, int dout, float* __restrict__ part,
+                                          float* __restrict__ out_s, float* __restrict__ out_g, bool relu) {
+  const int j = threadIdx.x % kMlpWidth, pz = threadIdx.x / kMlpWidth;
+  const int k0 = (int)((long)din * pz / kMlpParts), k1 = (int)((long)din * (pz + 1) / kMlpParts);
+  float acc = 0.f;
+  if (j < dout) {
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) acc = fmaf(in[k], __ldg(wt + (long)k * dout + j), acc);
+  }
+  part[pz * kMlpWidth + j] = acc;
+  __syncthreads();
+  if (pz == 0 && j < dout) {
+    float v = b ? b[j] : 0.f;
+#pragma unroll
+    for (int q = 0; q < kMlpParts; ++q) v += part[q * kMlpWidth + j];
+    if (relu) v = fmaxf(v, 0.f);
+    if (out_g) out_g[j] = v;
+    else out_s[j] = v;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMlpWidth * kMlpParts) mlp3_relu_rows_kernel(
+    const float* __restrict__ x, long ldx, int d0, const float* __restrict__ w1t, const float* __restrict__ b1, int d1,
+    const float* __restrict__ w2t, const float* __restrict__ b2, int d2, const float* __restrict__ w3t,
+    const float* __restrict__ b3, int d3, float* __restrict__ y, long ldy) {
+  extern __shared__ float sm[];
+  float* s0 = sm;                        // [d0]
+  float* s1 = s0 + d0;                   // [kMlpWidth]
+  float* s2 = s1 + kMlpWidth;            // [kMlpWidth]
+  float* part = s2 + kMlpWidth;          // [kMlpParts][kMlpWidth]
+  const long row = blockIdx.x;
+  for (int k = threadIdx.x; k < d0; k += blockDim.x) s0[k] = x[row * ldx + k];
+  __syncthreads();
+  mlp_layer(s0, d0, w1t, b1, d1, part, s1, nullptr, true);
+  mlp_layer(s1, d1, w2t, b2, d2, part, s2, nullptr, true);
+  mlp_layer(s2, d2, w3t, b3, d3, part, nullptr, y + row * ldy, false);
+}
+
+int mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1, const float* w2t,
+                   const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y, long ldy,
+                   cudaStream_t stream) {
+  SIM_REQUIRE(x && w1t && w2t && w3t && y && rows > 0 && d0 > 0 && d1 > 0 && d2 > 0 && d3 > 0, SIM_ERR_INVALID,
+              "mlp3_relu_rows: null tensor / empty problem");
+  SIM_REQUIRE(d1 <= kMlpWidth && d2 <= kMlpWidth && d3 <= kMlpWidth && d0 <= 8192 && rows <= 65535, SIM_ERR_INVALID,
+              "mlp3_relu_rows: built for a classifier head (layer widths <= %d, <= 65535 rows)", kMlpWidth);
+  const size_t smem = ((size_t)d0 + (2 + kMlpParts) * kMlpWidth) * sizeof(float);
+  mlp3_relu_rows_kernel<<<(int)rows, kMlpWidth * kMlpParts, smem, stream>>>(x, ldx, d0, w1t, b1, d1, w2t, b2, d2, w3t, b3, d3,
+                                                                           y, ldy);
+  return check_launch("mlp3_relu_rows");
+}
+
 // ----------------------------------------------------------------------------- SAST order gather
 // out[b, s*G + r, :] = x[b, perm[b,s,r], :] (+ x2[...]) and, if reverse, the mirrored row
 // out[b, 2kG-1-(s*G+r), :] gets the same data: each source row is read once and written twice.

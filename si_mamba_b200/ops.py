@@ -247,6 +247,20 @@ def layernorm_mean(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ep
     return out
 
 
+def mlp3_relu_rows(x: torch.Tensor, w1t, b1, w2t, b2, w3t, b3) -> torch.Tensor:
+    """y = W3 relu(W2 relu(W1 x + b1) + b2) + b3 for a few rows (sim_mlp3_relu_rows): x (rows, d0) fp32, weights
+    transposed (in, out) fp32 contiguous with widths <= 256 (the eval-mode classifier head, BatchNorm folded)."""
+    _cuda(x, w1t, w2t, w3t)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, d0 = x.shape
+    d1, d2, d3 = w1t.shape[1], w2t.shape[1], w3t.shape[1]
+    assert w1t.shape[0] == d0 and w2t.shape[0] == d1 and w3t.shape[0] == d2
+    y = torch.empty(rows, d3, dtype=torch.float32, device=x.device)
+    _lib.call("sim_mlp3_relu_rows", _p(x), x.stride(0), rows, d0, _p(w1t), _p(b1), d1, _p(w2t), _p(b2), d2, _p(w3t), _p(b3),
+              d3, _p(y), y.stride(0), _stream())
+    return y
+
+
 # ----------------------------------------------------------------------------- Chamfer-L2 (a-18)
 class ChamferL2(torch.autograd.Function):
     """(R,P,3), (R,Q,3) fp32 -> (R,) pytorch3d chamfer_distance(..., batch_reduction=None)[0] (squared L2, mean over

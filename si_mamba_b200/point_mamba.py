@@ -39,6 +39,9 @@ class RMSNorm(nn.Module):
 _ENCODER_ROWS = __import__("os").environ.get("SIM_ENCODER_ROWS", "1") != "0"
 
 
+_HEAD_KERNEL = __import__("os").environ.get("SIM_HEAD_KERNEL", "1") != "0"  # 0: classifier head through nn.Sequential
+
+
 class _conv_tf32_policy:
     """Matmuls that stand in for the reference's Conv1d layers follow torch.backends.cudnn.allow_tf32 (cuDNN's switch,
     True by default) instead of the matmul switch."""
@@ -356,6 +359,28 @@ class PointMamba(nn.Module):
             if m.bias is not None:
                 nn.init.constant_(m.bias, 0)
 
+    def _head(self, f):
+        """cls_head_finetune (models/point_mamba.py:1124-1130).  Inference on CUDA in fp32: ONE kernel
+        (sim_mlp3_relu_rows) on BatchNorm-folded, pre-transposed weights instead of 11 launch-bound ATen kernels."""
+        h = self.cls_head_finetune
+        if (self.training or torch.is_grad_enabled() or not f.is_cuda or f.dtype != torch.float32 or not _HEAD_KERNEL
+                or torch.is_autocast_enabled() or len(h) != 9 or max(h[0].out_features, h[4].out_features, h[8].out_features) > 256):
+            return h(f)
+        from .autograd import _CACHE  # inference-only cache, invalidated by the tensors' version counters
+
+        def fold():
+            out = []
+            for lin, bn in ((h[0], h[1]), (h[4], h[5])):
+                scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                out += [(lin.weight * scale[:, None]).t().contiguous().detach(),
+                        ((lin.bias - bn.running_mean) * scale + bn.bias).contiguous().detach()]
+            return out + [h[8].weight.t().contiguous().detach(), h[8].bias.contiguous().detach()]
+
+        deps = tuple(t for m in (h[0], h[1], h[4], h[5], h[8]) for t in (m.weight, m.bias)) + (
+            h[1].running_mean, h[1].running_var, h[5].running_mean, h[5].running_var)
+        w1t, b1, w2t, b2, w3t, b3 = _CACHE.get_multi(h[0].weight, "head_fold", deps, fold)
+        return ops.mlp3_relu_rows(f.contiguous(), w1t, b1, w2t, b2, w3t, b3)
+
     def spectral_order(self, center):
         """centres -> dict(vals, vecs, perm, inv_perm): graph + Laplacian + eigensolver + argsort in one kernel
         (replaces create_graph_* + calc_top_k_eigenvalues_eigenvectors* + the sorts, point_mamba.py:872-898)."""
@@ -437,7 +462,7 @@ class PointMamba(nn.Module):
         else:
             x = self.norm(x)
             concat_f = x[:, :].mean(1)
-        ret = self.cls_head_finetune(concat_f)
+        ret = self._head(concat_f)
         if gt is not None:
             policy = torch.zeros((batch_size,), device=center.device, dtype=center.dtype)
             return ret, policy

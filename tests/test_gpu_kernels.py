@@ -560,3 +560,20 @@ def test_linear_x3_training(ops, M, N, K):
     s_y, s_dx, s_dw = rel(x.detach() @ w.detach().t(), xd @ wd.t()), rel(dy @ w.detach(), dyd @ wd), rel(dy.t() @ x.detach(), dyd.t() @ xd)
     print(f"M={M} N={N} K={K}: x3 {e_y:.2e} {e_dx:.2e} {e_dw:.2e} | sgemm {s_y:.2e} {s_dx:.2e} {s_dw:.2e}")
     assert e_y < 3e-6 and e_dx < 3e-6 and e_dw < 3e-6
+
+
+@pytest.mark.parametrize("rows,d0,d1,d2,d3", [(32, 384, 256, 256, 40), (5, 100, 64, 200, 15), (1, 7, 256, 3, 256)])
+def test_mlp3_relu_rows(ops, rows, d0, d1, d2, d3):
+    """Fused eval-mode classifier head (models/point_mamba.py:1124-1130 with BatchNorm folded) against float64."""
+    g = torch.Generator().manual_seed(rows + d0)
+    x = dev(torch.randn(rows, d0, generator=g))
+    ws = [dev(torch.randn(a, b, generator=g) * a ** -0.5) for a, b in ((d0, d1), (d1, d2), (d2, d3))]
+    bs = [dev(torch.randn(b, generator=g) * 0.1) for b in (d1, d2, d3)]
+    y = ops.mlp3_relu_rows(x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])
+    h = torch.relu(x.double() @ ws[0].double() + bs[0].double())
+    h = torch.relu(h @ ws[1].double() + bs[1].double())
+    ref = h @ ws[2].double() + bs[2].double()
+    assert (y.double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    y0 = ops.mlp3_relu_rows(x, ws[0], None, ws[1], None, ws[2], None)
+    h = torch.relu(torch.relu(x.double() @ ws[0].double()) @ ws[1].double()) @ ws[2].double()
+    assert (y0.double() - h).abs().max().item() < 1e-5 * max(1.0, h.abs().max().item())
