@@ -133,19 +133,25 @@ def layer_norm(sd, prefix, x, eps=1e-5):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
 
 
-def mixer_model(sd: dict, prefix: str, tokens, pos, n_layer: int, eps: float = 1e-5, fetch_idx=None):
+def mixer_model(sd: dict, prefix: str, tokens, pos, n_layer: int, eps: float = 1e-5, fetch_idx=None,
+                mixer=None, trace=None):
     """MixerModel.forward (point_mamba.py:247-258) in eval mode (DropPath/Dropout identity).
 
     Block.forward (block.py:56-72): residual = h (+ residual); h = LN(residual); h = mixer(h).
     With ``fetch_idx`` returns the seg variant's list of norm_f(h + residual) taps
-    (pt_mamba.py:390-416)."""
+    (pt_mamba.py:390-416).  ``mixer`` (default: mamba_mixer) and ``trace`` (list that receives each layer's
+    (h, residual)) exist so tests/test_oracle_vs_reference.py can pin this loop against the reference's own Block
+    driven with a stand-in mixer."""
+    mixer = mixer or mamba_mixer
     h = tokens + pos
     residual = None
     taps = []
     for i in range(n_layer):
         residual = h if residual is None else h + residual
         h = layer_norm(sd, f"{prefix}layers.{i}.norm.", residual, eps)
-        h = mamba_mixer(sd, f"{prefix}layers.{i}.mixer.", h)
+        h = mixer(sd, f"{prefix}layers.{i}.mixer.", h)
+        if trace is not None:
+            trace.append((h, residual))
         if fetch_idx is not None and i in fetch_idx:
             taps.append(layer_norm(sd, prefix + "norm_f.", h + residual, eps))
     if fetch_idx is not None:

@@ -119,6 +119,75 @@ def seeded_centres(B, G, seed):
     return x.contiguous()
 
 
+def _bf16_exact_(module, seed):
+    """Random-init weights AND BatchNorm statistics, rounded so that a bf16 copy stores them losslessly."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, t in list(module.named_parameters()) + list(module.named_buffers()):
+            if not t.is_floating_point():
+                continue
+            if name.endswith("running_var"):
+                t.copy_(0.5 + torch.rand(t.shape, generator=g))
+            elif name.endswith("running_mean") or name.endswith("bias"):
+                t.copy_(0.1 * torch.randn(t.shape, generator=g))
+            elif t.dim() == 1:  # norm weights
+                t.copy_(1.0 + 0.1 * torch.randn(t.shape, generator=g))
+            t.copy_(t.bfloat16().float())
+    return {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in module.state_dict().items()}
+
+
+def reference_modules(pm):
+    """nn.Modules of the path that are plain PyTorch in the reference: Encoder (:42-73), Block's add -> LayerNorm ->
+    mixer residual plumbing (models/block.py:47-73, with a Linear standing in for the absent mamba-ssm mixer), and the
+    part-seg PointNetFeaturePropagation (part_segmentation/models/pointnet2_utils.py:262-312).  eval mode."""
+    out = {}
+    g = torch.Generator().manual_seed(2024)
+
+    torch.manual_seed(11)
+    enc = pm.Encoder(384).eval()
+    sd = _bf16_exact_(enc, 12)
+    groups = 0.2 * torch.randn(2, 16, 32, 3, generator=g)
+    with torch.no_grad():
+        out["encoder"] = {"sd": sd, "groups": groups, "tokens": enc(groups).clone()}
+
+    # Block stack exactly as MixerModel.forward drives it (:247-272): residual=None first, fp32 residual, final add
+    blk_mod = importlib.import_module("models.block")
+
+    class StandInMixer(torch.nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.lin = torch.nn.Linear(dim, dim)
+
+        def forward(self, x, inference_params=None):
+            return torch.tanh(self.lin(x))
+
+    torch.manual_seed(13)
+    blocks = [blk_mod.Block(48, StandInMixer, norm_cls=torch.nn.LayerNorm, fused_add_norm=False,
+                            residual_in_fp32=True).eval() for _ in range(3)]
+    sds = [_bf16_exact_(b, 20 + i) for i, b in enumerate(blocks)]
+    x = torch.randn(2, 24, 48, generator=g)
+    hs, res, trace = x, None, []
+    with torch.no_grad():
+        for b in blocks:
+            hs, res = b(hs, res)
+            trace.append((hs.clone(), res.clone()))
+    out["block"] = {"sd": sds, "x": x, "trace": trace}
+
+    sys.path.insert(0, os.path.join(REF, "part_segmentation", "models"))
+    pn = importlib.import_module("pointnet2_utils")
+    torch.manual_seed(17)
+    fp = pn.PointNetFeaturePropagation(in_channel=24 + 16, mlp=[32, 24]).eval()
+    sd = _bf16_exact_(fp, 18)
+    xyz1 = torch.randn(2, 3, 96, generator=g)
+    xyz2 = xyz1[:, :, ::6].contiguous() + 0.01 * torch.randn(2, 3, 16, generator=g)
+    p1 = torch.randn(2, 16, 96, generator=g)
+    p2 = torch.randn(2, 24, 16, generator=g)
+    with torch.no_grad():
+        out["feature_propagation"] = {"sd": sd, "xyz1": xyz1, "xyz2": xyz2, "points1": p1, "points2": p2,
+                                      "out": fp(xyz1, xyz2, p1, p2).clone()}
+    return out
+
+
 def main():
     pm = load_reference()
     torch.manual_seed(0)
@@ -197,10 +266,13 @@ def main():
                                      "sorted_mask": s_mask, "sorted_learnable": s_learn, "sorted_indices": s_idx,
                                      "a": a, "found": pos, "neighborhood": nb, "sorted_neighborhood": s_nb})
 
+    out_mod = reference_modules(pm)
+
     os.makedirs(OUT, exist_ok=True)
+    torch.save(out_mod, os.path.join(OUT, "reference_modules.pt"))
     torch.save(out_spec, os.path.join(OUT, "reference_spectral.pt"))
     torch.save(out_mae, os.path.join(OUT, "reference_mae.pt"))
-    for f in ("reference_spectral.pt", "reference_mae.pt"):
+    for f in ("reference_spectral.pt", "reference_mae.pt", "reference_modules.pt"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
 
