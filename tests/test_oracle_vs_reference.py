@@ -321,3 +321,86 @@ def test_cuda_modules_match_reference(lib, ref_mod):
             hs, res = m(hs, res)
         assert torch.allclose(res.cpu(), r_ref, rtol=1e-5, atol=1e-5)
         assert torch.allclose(hs.cpu(), h_ref, rtol=1e-3, atol=1e-4)  # the stand-in Linear runs on cuBLAS
+
+
+# ----------------------------------------------------------------------------- the reference's whole forward
+def _forward_state_dict(f):
+    from oracle import mamba
+    sd = _f32(f["sd"])
+    for i in range(f["cfg"]["depth"]):
+        p = mamba.init_mamba_params(d_model=384, n_layer=f["cfg"]["depth"], seed=f["mamba_seed"] + i)
+        for k, v in p.items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    return sd
+
+
+def test_whole_forward_matches_reference(ref_mod):
+    """PointMamba.forward (point_mamba.py:843-1125) as the reference executes it - Group index arithmetic, Encoder,
+    pos_embed, SAST assembly + reverse flip, MixerModel / Block, norm, mean, head - vs oracle.model.
+    point_mamba_forward on the same weights and clouds.  (FPS / kNN / the Mamba mixer inside that run were the oracle's
+    restatements standing in for the absent wheels: this pins the wiring, see tools/make_reference_golden.py.)"""
+    from oracle import model
+    f = ref_mod["forward"]
+    sd, cfg = _forward_state_dict(f), dict(f["cfg"])
+    logits, inter = model.point_mamba_forward(sd, cfg, f["pts"], return_intermediates=True)
+    assert logits.shape == f["logits"].shape == (2, 8)
+    # the oracle (and the product) sort by SIGN-CANONICALISED eigenvectors, as north_star specifies; the reference's
+    # forward sorts by whatever sign LAPACK returned (it applies no sign rule), which reverses some of the k sorted
+    # copies.  Same vectors up to sign ...
+    v, r = inter["eigvecs"].double(), f["eigvecs"].double()
+    sign = torch.sign((v * r).sum(dim=1, keepdim=True))
+    assert (v * sign - r).abs().max() < 1e-4
+    assert (inter["eigvals"].double() - f["eigvals"].double()).abs().max() < 1e-5
+    # ... and under the reference's signs the whole forward agrees to 1e-4; the sign convention itself moves these
+    # logits by ~3e-4 relative (bounded below 2e-3, the GPU parity bound)
+    err_canonical = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
+    assert err_canonical < 2e-3, err_canonical
+    perm = spectral.sast_perm(f["eigvecs"])  # the keys the reference itself sorted (near-ties resolved as it did)
+    logits_ref_sign = model.point_mamba_forward(sd, cfg, f["pts"], perm_override=perm)
+    err = (logits_ref_sign - f["logits"]).abs().max() / f["logits"].abs().max()
+    assert err < 1e-4, err
+
+
+@pytest.mark.gpu
+def test_cuda_whole_forward_matches_reference(lib, ref_mod):
+    """The product's PointMamba (CUDA path, reference config keys and state-dict names) against the logits the
+    reference's own forward produced.  2e-3 relative, the bound of tests/test_gpu_model.py; it includes the effect
+    of the sign convention (canonical here, LAPACK-arbitrary in the reference: ~3e-4 on these logits)."""
+    import si_mamba_b200 as sm
+    from si_mamba_b200.config import Config
+    f = ref_mod["forward"]
+    m = sm.PointMamba(Config(**f["cfg"]))
+    missing, unexpected = m.load_state_dict(_forward_state_dict(f), strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        logits = m(f["pts"].cuda()).cpu()
+    err = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
+    assert err < 2e-3, err
+
+
+def test_hlt_forward_layout_matches_reference(ref_mod):
+    """method == 'HLT' branch of the reference's forward (point_mamba.py:1050-1110; the part-seg model repeats it at
+    pt_mamba.py:670-723): multilevel codes + torch.rand tie-break noise -> argsort -> chunked layout with zero slots.
+    The tokens / positions the reference handed to its mixer stack, and its logits, vs the oracle's hlt_* functions
+    (same weights as the SAST fixture: same construction seeds)."""
+    from oracle import mamba, model, tokenizer
+    f, fs = ref_mod["forward_hlt"], ref_mod["forward"]
+    sd, cfg = _forward_state_dict(fs), f["cfg"]
+    assert cfg["method"] == "HLT"
+    nbr, center, _, _, _ = tokenizer.group(f["pts"], cfg["num_group"], cfg["group_size"])
+    tok = model.encoder(sd, "encoder.", nbr)
+    pos = model.pos_embed(sd, "pos_embed.", center)
+    k = cfg["k_top_eigenvectors"]
+    order = spectral.hlt_order(f["eigvecs"], k, f["noise"])
+    x = spectral.hlt_layout(tok, order, k, cfg["reverse"])
+    p = spectral.hlt_layout(pos, order, k, cfg["reverse"])
+    C = f["x"].shape[-1]
+    assert x.shape[1] == 2 * cfg["num_group"]
+    assert torch.equal(x[..., :C] == 0, f["x"] == 0)  # zero slots where the reference leaves them
+    assert torch.allclose(x[..., :C], f["x"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(p[..., :C], f["pos"], rtol=1e-5, atol=1e-6)
+    h = mamba.layer_norm(sd, "norm.", mamba.mixer_model(sd, "blocks.", x, p, cfg["depth"]))
+    logits = model.cls_head(sd, "cls_head_finetune.", h.mean(1))
+    err = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
+    assert err < 1e-4, err

@@ -188,6 +188,109 @@ def reference_modules(pm):
     return out
 
 
+class _Cfg(dict):
+    """EasyDict stand-in: attribute access, hasattr and `in` as the reference uses them."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+FWD_CFG = dict(NAME="PointMamba", trans_dim=384, depth=2, cls_dim=8, num_heads=6, group_size=16, num_group=32,
+               encoder_dims=384, rms_norm=False, drop_path=0.0, drop_out=0.0, method="SAST", reverse=True,
+               reverse_2=False, reverse_3=False, knn_graph=8, k_top_eigenvectors=4, alpha=100.0, smallest=True,
+               symmetric=True, self_loop=False, binary=True, matrix="laplacian", add_after_layer=False, rotation=False)
+MAMBA_SEED = 4100  # layer i of the stand-in mixer uses oracle.mamba.init_mamba_params(seed=MAMBA_SEED + i)
+
+
+def reference_forward(pm, method="SAST"):
+    """The reference's own PointMamba.forward (:843-1125) - Group index arithmetic, Encoder, pos_embed, SAST assembly,
+    reverse flip, MixerModel / Block, norm, token mean, classifier head - run end to end on the CPU.
+
+    Three names it imports from absent CUDA-only wheels are bound to stand-ins built on the oracle's restatements
+    (so this vector pins the WIRING of the forward, not those three algorithms, which stay unpinned):
+    pytorch3d.ops.sample_farthest_points / knn_points -> oracle.tokenizer.fps / knn_group, mamba_ssm Mamba ->
+    a module with mamba-ssm's parameter names whose forward is oracle.mamba.mamba_mixer."""
+    sys.path.insert(0, ROOT)
+    from oracle import mamba as omamba, tokenizer as otok
+
+    def sample_farthest_points(points, K):
+        idx = otok.fps(points, K)
+        return torch.gather(points, 1, idx[..., None].expand(-1, -1, 3)), idx
+
+    def knn_points(center, xyz, K, return_sorted=False):
+        idx = otok.knn_group(xyz, center, K)[0]
+        return types.SimpleNamespace(idx=idx)
+
+    class OracleMamba(torch.nn.Module):
+        def __init__(self, d_model, layer_idx=None, device=None, dtype=None, **kw):
+            super().__init__()
+            d_inner, d_state, dt_rank = 2 * d_model, 16, -(-d_model // 16)
+            self.in_proj = torch.nn.Linear(d_model, 2 * d_inner, bias=False)
+            self.conv1d = torch.nn.Conv1d(d_inner, d_inner, 4, groups=d_inner, padding=3)
+            self.x_proj = torch.nn.Linear(d_inner, dt_rank + 2 * d_state, bias=False)
+            self.dt_proj = torch.nn.Linear(dt_rank, d_inner, bias=True)
+            self.dt_proj.bias._no_reinit = True
+            self.A_log = torch.nn.Parameter(torch.zeros(d_inner, d_state))
+            self.D = torch.nn.Parameter(torch.ones(d_inner))
+            self.out_proj = torch.nn.Linear(d_inner, d_model, bias=False)
+            self.layer_idx = layer_idx
+
+        def forward(self, hidden_states, inference_params=None):
+            return omamba.mamba_mixer(dict(self.state_dict()), "", hidden_states)
+
+    pm.sample_farthest_points, pm.knn_points, pm.Mamba = sample_farthest_points, knn_points, OracleMamba
+    torch.manual_seed(31)
+    model = pm.PointMamba(_Cfg(dict(FWD_CFG, method=method))).eval()
+    _bf16_exact_(model, 32)
+    with torch.no_grad():
+        for i, layer in enumerate(model.blocks.layers):
+            p = omamba.init_mamba_params(d_model=384, n_layer=FWD_CFG["depth"], seed=MAMBA_SEED + i)
+            layer.mixer.load_state_dict(p, strict=True)
+    keep = ("encoder.", "pos_embed.", "blocks.", "norm.", "cls_head_finetune.")
+    sd = {k: v for k, v in model.state_dict().items() if k.startswith(keep) and ".mixer." not in k}
+    sd = {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd.items()}
+    pts = otok.synthetic_clouds(2, 256, 77, "surface")
+    # record (not alter) the eigenvectors the forward sorts by: their signs are whatever LAPACK returned - the
+    # reference's forward applies no sign rule - and a test needs them to reproduce the reference's ordering
+    seen = {}
+    inner = model.calc_top_k_eigenvalues_eigenvectors
+
+    def recording(*a, **k):
+        r = inner(*a, **k)
+        seen["vals"], seen["vecs"] = r[0].clone(), r[1].clone()
+        return r
+
+    model.calc_top_k_eigenvalues_eigenvectors = recording
+    blocks_forward = model.blocks.forward
+
+    def recording_blocks(x, pos, *a, **k):  # what the ordering stage hands to the mixer stack
+        seen["x"], seen["pos"] = x.clone(), pos.clone()
+        return blocks_forward(x, pos, *a, **k)
+
+    model.blocks.forward = recording_blocks
+
+    class Mode(CudaToCpu):  # also note the tie-break noise the HLT branch draws with torch.rand (:1056)
+        def __torch_function__(self, func, types_, args=(), kwargs=None):
+            r = super().__torch_function__(func, types_, args, kwargs)
+            if func is torch.rand:
+                seen["noise"] = r.clone()
+            return r
+
+    torch.manual_seed(5)
+    with Mode(), torch.no_grad():
+        logits = model(pts)
+    out = {"cfg": dict(FWD_CFG, method=method), "mamba_seed": MAMBA_SEED, "sd": sd, "pts": pts,
+           "logits": logits.clone(), "eigvals": seen["vals"], "eigvecs": seen["vecs"]}
+    if method == "HLT":
+        # the state dict is the SAST fixture's (same seeds); keep only what the HLT test needs
+        out.pop("sd")
+        out.update(noise=seen["noise"], x=seen["x"][..., :KEEP].clone(), pos=seen["pos"][..., :KEEP].clone())
+    return out
+
+
 def main():
     pm = load_reference()
     torch.manual_seed(0)
@@ -267,6 +370,8 @@ def main():
                                      "a": a, "found": pos, "neighborhood": nb, "sorted_neighborhood": s_nb})
 
     out_mod = reference_modules(pm)
+    out_mod["forward"] = reference_forward(pm)
+    out_mod["forward_hlt"] = reference_forward(pm, "HLT")
 
     os.makedirs(OUT, exist_ok=True)
     torch.save(out_mod, os.path.join(OUT, "reference_modules.pt"))
