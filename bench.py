@@ -51,9 +51,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def synthetic_clouds(B, N, seed):
+    """Synthetic "surface" clouds of SURVEY.md section 8(d): a few anisotropic blobs with noise, normalised like the
+    datasets (datasets/ModelNetDataset.py:52-57: centroid 0, max-norm 1).  bench.py's own generator - the timed arm
+    imports nothing from oracle/; tests/test_abi_host.py checks it draws the same clouds as the tests' generator."""
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.empty(B, N, 3)
+    for b in range(B):
+        n_patch = int(torch.randint(3, 7, (1,), generator=g))
+        which = torch.randint(0, n_patch, (N,), generator=g)
+        ctr = torch.randn(n_patch, 3, generator=g) * 0.5
+        axes = torch.rand(n_patch, 3, generator=g) * 0.6 + 0.1
+        v = torch.randn(N, 3, generator=g)
+        v = v / v.norm(dim=-1, keepdim=True)
+        pts[b] = ctr[which] + v * axes[which] + 0.01 * torch.randn(N, 3, generator=g)
+    pts = pts - pts.mean(dim=1, keepdim=True)
+    pts = pts / pts.norm(dim=-1).max(dim=1).values[:, None, None]
+    return pts.contiguous().float()
+
+
 def make_clouds(batch, rank, sets=N_SETS):
-    from oracle import tokenizer  # synthetic-input generator only (shared with the tests)
-    return [tokenizer.synthetic_clouds(batch, N_POINTS, 1234 + 1000 * 1 + 17 * rank + i, "surface") for i in range(sets)]
+    return [synthetic_clouds(batch, N_POINTS, 1234 + 1000 * 1 + 17 * rank + i) for i in range(sets)]
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """One JSON line on stdout, nothing else: from here on anything a library writes to fd 1 (NCCL's version banner,
+    torchrun children ...) lands on stderr, and emit() writes to the real stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def build_model():
@@ -137,7 +174,7 @@ def run_reference(args):
     val = args.ref_sample * args.steps / dt
     cores = torch.get_num_threads()
     sample = f"{args.ref_sample} cloud(s) of the same workload per step, {args.steps} steps"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -145,7 +182,7 @@ def run_reference(args):
                                "of the reference path; the reference's CUDA wheels cannot run on CPU)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -160,7 +197,6 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     # fp32 mirrors the reference's runtime defaults (no autocast in runner_finetune): fp32 matmuls, while
@@ -331,7 +367,7 @@ def run_ours(args):
                              "= 0.58 of this roofline (DESIGN.md 4.1); timed inside a CUDA graph of 20 launches"},
         "cpu_baseline": cpu_base,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -339,6 +375,7 @@ def run_ours(args):
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

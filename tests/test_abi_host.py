@@ -141,3 +141,14 @@ def test_droppath_semantics():
     assert all(v.unique().numel() == 1 for v in per_sample)        # whole sample kept or dropped
     assert set(y.unique().tolist()) <= {0.0, 2.0}                   # scale 1/keep
     assert torch.equal(dp.eval()(x), x)
+
+
+def test_bench_generator_matches_test_generator():
+    """bench.py's own synthetic-cloud generator (the timed arm imports nothing from oracle/) draws exactly the clouds
+    the tests' generator does."""
+    import importlib.util
+    from oracle import tokenizer
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert torch.equal(bench.synthetic_clouds(3, 256, 4321), tokenizer.synthetic_clouds(3, 256, 4321, "surface"))

@@ -404,3 +404,32 @@ def test_hlt_forward_layout_matches_reference(ref_mod):
     logits = model.cls_head(sd, "cls_head_finetune.", h.mean(1))
     err = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
     assert err < 1e-4, err
+
+
+# ----------------------------------------------------------------------------- part segmentation, whole forward
+def _seg_state_dict(f):
+    from oracle import mamba
+    from seeded_fill import seeded_state_dict
+    sd = seeded_state_dict(f["spec"], f["seed"])
+    for i in range(f["cfg"]["depth"]):
+        for k, v in mamba.init_mamba_params(d_model=384, n_layer=f["cfg"]["depth"], seed=f["seed"] + 1 + i).items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    return sd
+
+
+def test_seg_forward_matches_reference(ref_mod):
+    """part_segmentation/models/pt_mamba.py get_model.forward (:631-788) as the reference executes it (HLT ordering
+    with its own tie-break noise, MixerModelForSegmentation taps, label conv, feature propagation, conv head) vs
+    oracle.seg.seg_forward, same weights (tests/seeded_fill.py) and clouds."""
+    from oracle import seg
+    f = ref_mod["seg_forward"]
+    k = f["cfg"]["k_top_eigenvectors"]
+    order = spectral.hlt_order(f["eigvecs"], k, f["noise"])  # the keys the reference itself sorted
+    logp, inter = seg.seg_forward(_seg_state_dict(f), dict(f["cfg"]), f["pts"], f["cls_label"], f["noise"],
+                                  order_override=order)
+    assert logp.shape == f["log_probs"].shape == (2, 512, 10)
+    assert (logp - f["log_probs"]).abs().max() < 1e-4, (logp - f["log_probs"]).abs().max()
+    # same eigenvectors up to sign (the oracle's are fp64 + canonical sign)
+    v, r = inter["eigvecs"].double(), f["eigvecs"].double()
+    sign = torch.sign((v * r).sum(dim=1, keepdim=True))
+    assert (v * sign - r).abs().max() < 1e-4

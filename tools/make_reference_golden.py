@@ -291,6 +291,93 @@ def reference_forward(pm, method="SAST"):
     return out
 
 
+SEG_CFG = dict(trans_dim=384, depth=3, fetch_idx=[0, 1, 2], rms_norm=False, drop_path=0.0, drop_out=0.0,
+               drop_path_rate=0.0, method="HLT", reverse=True, k_top_eigenvectors=4, smallest=True, knn_graph=10,
+               symmetric=True, self_loop=False, alpha=10.0, binary=False)
+SEG_SEED = 7300
+
+
+def reference_seg_forward():
+    """part_segmentation/models/pt_mamba.py get_model.forward (:631-788) run end to end on the CPU: Group, Encoder,
+    HLT ordering (its own torch.rand noise, recorded), MixerModelForSegmentation taps, label conv, feature propagation,
+    conv head, log_softmax.  Same three stand-ins for the absent wheels as reference_forward.  All weights come from
+    tests/seeded_fill.py (name + shape + seed), so the fixture stores no state dict."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(REF, "part_segmentation"))
+    sys.path.insert(0, os.path.join(REF, "part_segmentation", "models"))
+    from oracle import mamba as omamba, tokenizer as otok
+    from seeded_fill import seeded_state_dict
+    for _ in range(20):
+        try:
+            ptm = importlib.import_module("pt_mamba")
+            break
+        except ModuleNotFoundError as e:
+            print("stubbing absent module:", e.name.split(".")[0])
+            STUB_ROOTS.append(e.name.split(".")[0])
+
+    def sample_farthest_points(points, K):
+        idx = otok.fps(points, K)
+        return torch.gather(points, 1, idx[..., None].expand(-1, -1, 3)), idx
+
+    def knn_points(center, xyz, K, return_sorted=False):
+        return types.SimpleNamespace(idx=otok.knn_group(xyz, center, K)[0])
+
+    class OracleMamba(torch.nn.Module):
+        def __init__(self, d_model, layer_idx=None, device=None, dtype=None, **kw):
+            super().__init__()
+            d_inner, d_state, dt_rank = 2 * d_model, 16, -(-d_model // 16)
+            self.in_proj = torch.nn.Linear(d_model, 2 * d_inner, bias=False)
+            self.conv1d = torch.nn.Conv1d(d_inner, d_inner, 4, groups=d_inner, padding=3)
+            self.x_proj = torch.nn.Linear(d_inner, dt_rank + 2 * d_state, bias=False)
+            self.dt_proj = torch.nn.Linear(dt_rank, d_inner, bias=True)
+            self.A_log = torch.nn.Parameter(torch.zeros(d_inner, d_state))
+            self.D = torch.nn.Parameter(torch.ones(d_inner))
+            self.out_proj = torch.nn.Linear(d_inner, d_model, bias=False)
+
+        def forward(self, hidden_states, inference_params=None):
+            return omamba.mamba_mixer(dict(self.state_dict()), "", hidden_states)
+
+    ptm.sample_farthest_points, ptm.knn_points, ptm.Mamba = sample_farthest_points, knn_points, OracleMamba
+    torch.manual_seed(41)
+    model = ptm.get_model(10, _Cfg(SEG_CFG)).eval()
+    spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items() if v.is_floating_point() and ".mixer." not in k]
+    sd = seeded_state_dict(spec, SEG_SEED)
+    for i in range(SEG_CFG["depth"]):
+        for k, v in omamba.init_mamba_params(d_model=384, n_layer=SEG_CFG["depth"], seed=SEG_SEED + 1 + i).items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+
+    seen = {}
+    inner = model.calc_top_k_eigenvalues_eigenvectors
+
+    def recording(*a, **k):
+        r = inner(*a, **k)
+        seen["vecs"] = r[1].clone()
+        return r
+
+    model.calc_top_k_eigenvalues_eigenvectors = recording
+
+    class Mode(CudaToCpu):
+        def __torch_function__(self, func, types_, args=(), kwargs=None):
+            r = super().__torch_function__(func, types_, args, kwargs)
+            if func is torch.rand:
+                seen["noise"] = r.clone()
+            return r
+
+    # (B,3,N) as main.py hands it over: a transposed VIEW of the loader's contiguous (B,N,3) - Group.forward's
+    # xyz.view(...) (:187) only works on that layout
+    pts = otok.synthetic_clouds(2, 512, 78, "surface").transpose(1, 2)
+    label = torch.zeros(2, 16)
+    label[0, 3] = label[1, 11] = 1.0
+    torch.manual_seed(6)
+    with Mode(), torch.no_grad():
+        logp = model(pts, label)
+    return {"cfg": dict(SEG_CFG), "cls_dim": 10, "seed": SEG_SEED, "spec": spec, "pts": pts.contiguous(), "cls_label": label,
+            "noise": seen["noise"], "eigvecs": seen["vecs"], "log_probs": logp.clone()}
+
+
 def main():
     pm = load_reference()
     torch.manual_seed(0)
@@ -372,6 +459,7 @@ def main():
     out_mod = reference_modules(pm)
     out_mod["forward"] = reference_forward(pm)
     out_mod["forward_hlt"] = reference_forward(pm, "HLT")
+    out_mod["seg_forward"] = reference_seg_forward()
 
     os.makedirs(OUT, exist_ok=True)
     torch.save(out_mod, os.path.join(OUT, "reference_modules.pt"))
