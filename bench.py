@@ -178,8 +178,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "C1 SI-Mamba-cls forward: 1024 pts, 64 patches x 32, depth 12, d=384 (CPU oracle port "
-                               "of the reference path; the reference's CUDA wheels cannot run on CPU)"},
+        "config": {"workload": f"C1 SI-Mamba-cls forward: 1024 pts, 64 patches x 32, L=512, depth 12, d=384, batch "
+                               f"{args.batch} per GPU, eval mode, random-init weights",
+                   "arm": "CPU oracle port of the reference path (its CUDA-only wheels cannot run on the host cores); "
+                          f"each step is a bounded sample of {args.ref_sample} cloud(s) of that workload"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
