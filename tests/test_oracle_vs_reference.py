@@ -433,3 +433,47 @@ def test_seg_forward_matches_reference(ref_mod):
     v, r = inter["eigvecs"].double(), f["eigvecs"].double()
     sign = torch.sign((v * r).sum(dim=1, keepdim=True))
     assert (v * sign - r).abs().max() < 1e-4
+
+
+# ----------------------------------------------------------------------------- MAE encoder (masked spectral sort)
+def test_mae_encoder_matches_reference(ref_mod):
+    """MaskMamba_3.forward (point_mamba.py:2717-2803) as the reference executes it vs the oracle's masked-sort chain
+    (oracle.mae.compact_visible / mask_full, oracle.spectral.order_gather, oracle.mamba.mixer_model): same mask,
+    same eigenvectors, same weights (tests/seeded_fill.py)."""
+    from oracle import mamba, model, tokenizer
+    from seeded_fill import seeded_state_dict
+    f = ref_mod["mae_encoder"]
+    sd = seeded_state_dict(f["spec"], f["seed"])
+    for i in range(f["tc"]["depth"]):
+        for k, v in mamba.init_mamba_params(d_model=384, n_layer=f["tc"]["depth"], seed=f["seed"] + 1 + i).items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    nbr, center, _, _, _ = tokenizer.group(f["pts"], 64, 32)
+    tok = model.encoder(sd, "encoder.", nbr)
+    pos = model.pos_embed(sd, "pos_embed.", center)
+    # the reference's torch.sort is not stable: its recorded permutation must sort the same keys, and may differ from
+    # the oracle's stable argsort only inside runs of exactly equal keys (twin patches of the binary graph)
+    perm_o, perm = spectral.sast_perm(f["eigvecs"]), f["perm"]
+    keys = f["eigvecs"].transpose(1, 2)
+    assert torch.equal(torch.gather(keys, 2, perm), torch.gather(keys, 2, perm_o))
+    srt = torch.gather(keys, 2, perm_o)
+    tie = torch.zeros_like(perm_o, dtype=torch.bool)
+    tie[..., 1:] |= srt[..., 1:] == srt[..., :-1]
+    tie[..., :-1] |= srt[..., :-1] == srt[..., 1:]
+    assert torch.equal(perm[~tie], perm_o[~tie]) and tie.float().mean() < 0.05
+    mask = f["mask"]
+    B, G = mask.shape
+    mfull = mae.mask_full(mask, perm)
+    k = perm.shape[1]
+    assert torch.equal(mfull[:, :k * G], f["sorted_mask_cat"])
+    assert torch.equal(mfull[:, k * G:], f["sorted_mask_flipped"])
+    C = f["pos_full"].shape[-1]
+    pos_full = spectral.order_gather(pos, perm, True)
+    assert torch.allclose(pos_full[..., :C], f["pos_full"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(pos_full[mfull].reshape(B, -1, 384)[..., :C], f["pos_mask"], rtol=1e-5, atol=1e-6)
+    nb = spectral.order_gather(nbr.reshape(B, G, -1), perm, True).reshape(B, 2 * k * G, 32, 3)
+    assert torch.equal(nb[:, :, :4], f["sorted_neighborhood"])
+    x_vis = mae.compact_visible(tok, perm, mask)
+    p_vis = mae.compact_visible(pos, perm, mask)
+    x_vis = mamba.layer_norm(sd, "norm.", mamba.mixer_model(sd, "blocks.", x_vis, p_vis, f["tc"]["depth"]))
+    assert x_vis.shape == f["x_vis"].shape == (B, 2 * k * (G - 38), 384)
+    assert torch.allclose(x_vis, f["x_vis"], rtol=1e-4, atol=1e-4), (x_vis - f["x_vis"]).abs().max()

@@ -378,6 +378,90 @@ def reference_seg_forward():
             "noise": seen["noise"], "eigvecs": seen["vecs"], "log_probs": logp.clone()}
 
 
+MAE_TC = dict(mask_ratio=0.6, mask_type="rand", trans_dim=384, encoder_dims=384, depth=2, num_heads=6)
+MAE_SEED = 8200
+
+
+def reference_mae_encoder(pm):
+    """MaskMamba_3.forward (:2717-2803), the MAE encoder of pretrain.yaml: random mask (numpy RNG, recorded), Encoder,
+    masked spectral sort of tokens / positions / neighbourhoods per eigenvector, visible-token compaction, cat of the
+    k copies + flipped copy, MixerModel, norm.  Eigenvectors come from the reference's own batched solver (:3001-3050)
+    on its own graph (:2958-2999).  Mamba stand-in and seeded weights as in reference_seg_forward; timm's DropPath
+    (absent) is bound to an identity module - eval mode."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import mamba as omamba, tokenizer as otok
+    from seeded_fill import seeded_state_dict
+
+    class OracleMamba(torch.nn.Module):
+        def __init__(self, d_model, layer_idx=None, device=None, dtype=None, **kw):
+            super().__init__()
+            d_inner, d_state, dt_rank = 2 * d_model, 16, -(-d_model // 16)
+            self.in_proj = torch.nn.Linear(d_model, 2 * d_inner, bias=False)
+            self.conv1d = torch.nn.Conv1d(d_inner, d_inner, 4, groups=d_inner, padding=3)
+            self.x_proj = torch.nn.Linear(d_inner, dt_rank + 2 * d_state, bias=False)
+            self.dt_proj = torch.nn.Linear(dt_rank, d_inner, bias=True)
+            self.A_log = torch.nn.Parameter(torch.zeros(d_inner, d_state))
+            self.D = torch.nn.Parameter(torch.ones(d_inner))
+            self.out_proj = torch.nn.Linear(d_inner, d_model, bias=False)
+
+        def forward(self, hidden_states, inference_params=None):
+            return omamba.mamba_mixer(dict(self.state_dict()), "", hidden_states)
+
+    class DropPathEval(torch.nn.Module):
+        def __init__(self, p=0.0):
+            super().__init__()
+
+        def forward(self, x):
+            return x
+
+    blk = importlib.import_module("models.block")
+    pm.Mamba, pm.DropPath, blk.DropPath = OracleMamba, DropPathEval, DropPathEval
+    pm.print_log = lambda *a, **k: None
+    cfg = _Cfg(rms_norm=False, transformer_config=_Cfg(MAE_TC))
+    torch.manual_seed(51)
+    enc = pm.MaskMamba_3(cfg).eval()
+    spec = [(k, tuple(v.shape)) for k, v in enc.state_dict().items() if v.is_floating_point() and ".mixer." not in k]
+    sd = seeded_state_dict(spec, MAE_SEED)
+    for i in range(MAE_TC["depth"]):
+        for k, v in omamba.init_mamba_params(d_model=384, n_layer=MAE_TC["depth"], seed=MAE_SEED + 1 + i).items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+
+    pts = otok.synthetic_clouds(2, 1024, 79, "surface")
+    nbr, center, _, _, _ = otok.group(pts, 64, 32)
+    me = types.SimpleNamespace(alpha=10.0)
+    seen = {}
+    mask_fn = enc._mask_center_rand
+
+    def recording_mask(*a, **k):
+        seen["mask"] = mask_fn(*a, **k).clone()
+        return seen["mask"]
+
+    enc._mask_center_rand = recording_mask
+    # the reference's torch.sort is not stable; record the permutations it actually used (tokens call, every 2nd call)
+    sort_fn = enc.sort_points_by_fiedler
+    seen["perms"] = []
+
+    def recording_sort(points, *a, **k):
+        r = sort_fn(points, *a, **k)
+        seen["perms"].append(r[3].clone())
+        return r
+
+    enc.sort_points_by_fiedler = recording_sort
+    np.random.seed(123)
+    with CudaToCpu(), torch.no_grad():
+        adj = pm.Point_MAE_Mamba.create_graph_from_centers(me, center, 20, 10.0, True, False, True)
+        _, vecs, _, _ = pm.Point_MAE_Mamba.calc_top_k_eigenvalues_eigenvectors(me, adj, 4, True)
+        x_vis, m_list, pos_mask, pos_full, m_tensor, s_nbr, found = enc(nbr, center, vecs, 4, True)
+    return {"tc": dict(MAE_TC), "seed": MAE_SEED, "spec": spec, "pts": pts, "eigvecs": vecs.clone(),
+            "mask": seen["mask"], "perm": torch.stack(seen["perms"][0::2], dim=1), "x_vis": x_vis.clone(), "sorted_mask_cat": torch.cat(m_list, -1).clone(),
+            "sorted_mask_flipped": m_tensor.clone(), "pos_full": pos_full[..., :KEEP].clone(),
+            "pos_mask": pos_mask[..., :KEEP].clone(), "sorted_neighborhood": s_nbr[:, :, :4].clone()}
+
+
 def main():
     pm = load_reference()
     torch.manual_seed(0)
@@ -460,6 +544,7 @@ def main():
     out_mod["forward"] = reference_forward(pm)
     out_mod["forward_hlt"] = reference_forward(pm, "HLT")
     out_mod["seg_forward"] = reference_seg_forward()
+    out_mod["mae_encoder"] = reference_mae_encoder(pm)
 
     os.makedirs(OUT, exist_ok=True)
     torch.save(out_mod, os.path.join(OUT, "reference_modules.pt"))
