@@ -477,3 +477,33 @@ def test_mae_encoder_matches_reference(ref_mod):
     x_vis = mamba.layer_norm(sd, "norm.", mamba.mixer_model(sd, "blocks.", x_vis, p_vis, f["tc"]["depth"]))
     assert x_vis.shape == f["x_vis"].shape == (B, 2 * k * (G - 38), 384)
     assert torch.allclose(x_vis, f["x_vis"], rtol=1e-4, atol=1e-4), (x_vis - f["x_vis"]).abs().max()
+
+
+@pytest.mark.gpu
+def test_cuda_mae_encoder_matches_reference(lib, ref_mod):
+    """The product's MAE encoder (sim_mae_index_maps + sim_mae_compact_fwd + the CUDA mixer stack) fed the reference's
+    own mask and permutations, against the x_vis its MaskMamba_3.forward returned; the reference's parameter names
+    load without missing / unexpected keys."""
+    import si_mamba_b200 as sm
+    from oracle import mamba, tokenizer
+    from seeded_fill import seeded_state_dict
+    from si_mamba_b200 import mae as pmae
+    f = ref_mod["mae_encoder"]
+    sd = seeded_state_dict(f["spec"], f["seed"])
+    for i in range(f["tc"]["depth"]):
+        for k, v in mamba.init_mamba_params(d_model=384, n_layer=f["tc"]["depth"], seed=f["seed"] + 1 + i).items():
+            sd[f"blocks.layers.{i}.mixer.{k}"] = v
+    cfg = sm.pretrain()
+    cfg.transformer_config.update(depth=f["tc"]["depth"])
+    enc = pmae.MaskMamba_2(cfg)
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+    enc = enc.cuda().eval()
+    nbr, center, _, _, _ = tokenizer.group(f["pts"], 64, 32)
+    with torch.no_grad():
+        x_vis, maps = enc(nbr.cuda(), center.cuda(), f["perm"].int().cuda().contiguous(), True,
+                          bool_masked_pos=f["mask"].cuda())
+    assert torch.equal(maps["mask_full"].cpu()[:, :256], f["sorted_mask_cat"])
+    assert torch.equal(maps["mask_full"].cpu()[:, 256:], f["sorted_mask_flipped"])
+    err = (x_vis.cpu() - f["x_vis"]).abs().max() / f["x_vis"].abs().max()
+    assert err < 2e-3, err
