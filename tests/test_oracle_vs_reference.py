@@ -507,3 +507,61 @@ def test_cuda_mae_encoder_matches_reference(lib, ref_mod):
     assert torch.equal(maps["mask_full"].cpu()[:, 256:], f["sorted_mask_flipped"])
     err = (x_vis.cpu() - f["x_vis"]).abs().max() / f["x_vis"].abs().max()
     assert err < 2e-3, err
+
+
+@pytest.mark.gpu
+def test_cuda_seg_forward_matches_reference(lib, ref_mod, monkeypatch):
+    """The product's part-seg get_model (CUDA tokenizer, eigensolver, HLT layout kernels, mixer stack with taps, 3-NN
+    interpolation kernel, conv head) against the log-probs the reference's own get_model.forward produced.
+
+    HLT bucket codes depend on the eigenvector SIGN, which the reference leaves to LAPACK, so the
+    kernel's eigenvectors are first checked against the reference's up to sign (1e-4) and then handed on with the
+    reference's signs; everything downstream is the product's CUDA path."""
+    import si_mamba_b200 as sm
+    from si_mamba_b200 import ops, seg as pseg
+    f = ref_mod["seg_forward"]
+    cfg = sm.part_seg_config()
+    cfg.update(**f["cfg"])
+    m = sm.get_model(f["cls_dim"], cfg)
+    missing, unexpected = m.load_state_dict(_seg_state_dict(f), strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+    m = m.cuda().eval()
+    real = ops.spectral_eig
+    ref_vecs = f["eigvecs"].cuda()
+
+    def with_reference_signs(*a, **k):
+        out = real(*a, **k)
+        v = out["vecs"]
+        sign = torch.sign((v * ref_vecs).sum(dim=1, keepdim=True))
+        assert (v * sign - ref_vecs).abs().max() < 1e-4
+        out["vecs"] = ref_vecs
+        return out
+
+    monkeypatch.setattr(pseg.ops, "spectral_eig", with_reference_signs)
+    # strict fp32 convolutions, as in tests/test_gpu_mae_seg.py: the 3392 -> 512 conv head under cuDNN's default TF32
+    # policy alone costs ~3e-3 against an fp32 CPU reference
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    with torch.no_grad():
+        logp = m(f["pts"].cuda(), f["cls_label"].cuda(), hlt_noise=f["noise"]).cpu()
+    assert logp.shape == f["log_probs"].shape
+    # the HLT layout holds 96 zero tokens whose "centre" is the origin: a point with one of them among its three
+    # nearest centres has 96 exactly tied candidates carrying different features, and which one a sort returns is
+    # implementation-defined in the reference itself (DESIGN.md section 7) - those points are exempt
+    from oracle import seg as oseg, tokenizer
+    pts = f["pts"].transpose(1, 2).contiguous()
+    center = tokenizer.group(pts, 128, 32)[1]
+    order = spectral.hlt_order(f["eigvecs"], f["cfg"]["k_top_eigenvectors"], f["noise"])
+    sc = spectral.hlt_layout(center, order, f["cfg"]["k_top_eigenvectors"], True)
+    zero = sc.abs().sum(-1) == 0
+    idx3 = oseg.square_distance(pts, sc).sort(dim=-1).indices[:, :, :3]
+    exempt = torch.gather(zero[:, None, :].expand(-1, pts.shape[1], -1), 2, idx3).any(-1)
+    assert exempt.float().mean() < 0.02
+    per_point = ((logp - f["log_probs"]).abs().amax(-1) / f["log_probs"].abs().max())[~exempt]
+    # measured on B200: median 4e-7, 90 % below 6.1e-7, 99 % below 8.9e-4, ONE point of 1017 at 3.2e-3.  The bulk agrees
+    # to fp32 rounding; the handful of outliers are points whose 3rd / 4th nearest centres are nearly tied - the
+    # reference ranks them by the expanded form -2ab + a^2 + b^2 (pointnet2_utils.py square_distance), the kernel by
+    # direct differences - so the bound is on the bulk, with a loose cap on the stragglers
+    assert torch.quantile(per_point, 0.9) < 1e-5, torch.quantile(per_point, 0.9)
+    assert (per_point > 2e-3).float().mean() < 0.01
+    assert per_point.max() < 2e-2, per_point.max()
