@@ -13,7 +13,9 @@ How the reference is made to run here without touching it:
 Not reachable this way (their arithmetic lives in absent wheels): Group.forward (pytorch3d), Mamba (mamba-ssm),
 misc.fps (pointnet2_ops).  Those stay "parity unpinned" (DESIGN.md section 2).
 
-    python tools/make_reference_golden.py        # writes tests/golden/reference_spectral.pt, reference_mae.pt
+    python tools/make_reference_golden.py        # writes tests/golden/reference_{spectral,mae,modules}.pt
+
+Re-running it in this image reproduces the committed files bit for bit (checked with `git status` after each run).
 """
 
 from __future__ import annotations
