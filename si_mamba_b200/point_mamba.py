@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import layout, ops
 from .block import Block, DropPath, fused_add_norm
 from .mamba import Mamba
 
@@ -409,8 +409,9 @@ class PointMamba(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, pts, gt: torch.Tensor = None, tau: float = None, use_wavelets: bool = False,
-                save_pts_dir: str = None, epoch: int = None):
-        """pts (B, N, 3) -> logits (B, cls_dim)   [(logits, policy) when ``gt`` is given, as the reference]."""
+                save_pts_dir: str = None, epoch: int = None, hlt_noise: torch.Tensor = None):
+        """pts (B, N, 3) -> logits (B, cls_dim)   [(logits, policy) when ``gt`` is given, as the reference].
+        ``hlt_noise`` (B,G) replaces the U[0,1) tie-break the HLT branch draws with torch.rand (:1056)."""
         if use_wavelets:
             raise NotImplementedError("use_wavelets is broken at the reference HEAD (point_mamba.py:879) and out of scope")
         batch_size = pts.size(0)
@@ -442,12 +443,25 @@ class PointMamba(nn.Module):
                 spec = self.spectral_order(center)
             perm, inv = spec["perm"], spec["inv_perm"]
             reverse = bool(self.reverse)
+        elif self.method == "HLT":
+            # point_mamba.py:1050-1110: bucket codes from the eigenvector sign bits + tie-break noise -> argsort ->
+            # chunked layout with zero slots (the layout of the part-seg model, pt_mamba.py:670-723)
+            spec = self.spectral_order(center)
+            ids = self.multilevel_travers(spec["vecs"], self.k_top_eigenvectors).reshape(batch_size, -1).float()
+            if hlt_noise is None:
+                hlt_noise = torch.rand(ids.shape[0], ids.shape[1])  # CPU RNG then moved, as the reference
+            order, _ = ops.argsort_rows((ids + hlt_noise.to(ids.device)).contiguous())
+            src = layout.hlt_src_index(order, self.k_top_eigenvectors, bool(self.reverse))  # (B, 2G), -1 = zero token
+            perm = None
         else:
-            raise NotImplementedError(f"method {self.method!r} (HLT lives in the part-segmentation model)")
+            raise NotImplementedError(f"method {self.method!r}")
 
         training_graph = torch.is_grad_enabled() and (group_input_tokens.requires_grad or pos.requires_grad)
         p_drop = self.drop_out.p if self.training else 0.0
-        if not training_graph and p_drop == 0.0:
+        if perm is None:
+            x = self.drop_out(layout.gather_rows(group_input_tokens, src))
+            x = self.blocks(x, layout.gather_rows(pos, src))
+        elif not training_graph and p_drop == 0.0:
             # tokens + pos folded into the gather: gather(tok) + gather(pos) == gather(tok + pos) bit for bit
             x = ops.order_gather_add(group_input_tokens, pos, perm, reverse)
             x = self.blocks(x, None)

@@ -106,7 +106,10 @@ def test_block_and_mixer_signatures():
     sig = inspect.signature(sm.Block.forward)
     assert list(sig.parameters) == ["self", "hidden_states", "residual", "inference_params"]
     sig = inspect.signature(sm.PointMamba.forward)
-    assert list(sig.parameters) == ["self", "pts", "gt", "tau", "use_wavelets", "save_pts_dir", "epoch"]
+    # the reference's positional signature (point_mamba.py:843), then one optional keyword of this package
+    # (a caller-supplied HLT tie-break, as in the part-seg model) that no reference call site passes
+    assert list(sig.parameters) == ["self", "pts", "gt", "tau", "use_wavelets", "save_pts_dir", "epoch", "hlt_noise"]
+    assert sig.parameters["hlt_noise"].default is None
     sig = inspect.signature(sm.MixerModel.__init__)
     for k in ("d_model", "n_layer", "ssm_cfg", "norm_epsilon", "rms_norm", "initializer_cfg", "fused_add_norm",
               "residual_in_fp32", "drop_out_in_block", "drop_path", "device", "dtype"):

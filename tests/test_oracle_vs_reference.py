@@ -565,3 +565,34 @@ def test_cuda_seg_forward_matches_reference(lib, ref_mod, monkeypatch):
     assert torch.quantile(per_point, 0.9) < 1e-5, torch.quantile(per_point, 0.9)
     assert (per_point > 2e-3).float().mean() < 0.01
     assert per_point.max() < 2e-2, per_point.max()
+
+
+@pytest.mark.gpu
+def test_cuda_hlt_cls_forward_matches_reference(lib, ref_mod, monkeypatch):
+    """method == 'HLT' of the classification model on the CUDA path (eigensolver, argsort, HLT gather kernels, mixer
+    stack, head) against the logits of the reference's own forward, HLT branch.  As in the part-seg test the kernel's
+    eigenvectors are checked up to sign and handed on with the reference's signs (HLT codes are sign-dependent)."""
+    import si_mamba_b200 as sm
+    from si_mamba_b200 import ops
+    from si_mamba_b200.config import Config
+    f, fs = ref_mod["forward_hlt"], ref_mod["forward"]
+    m = sm.PointMamba(Config(**f["cfg"]))
+    missing, unexpected = m.load_state_dict(_forward_state_dict(fs), strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    m = m.cuda().eval()
+    real = ops.spectral_eig
+    ref_vecs = f["eigvecs"].cuda()
+
+    def with_reference_signs(*a, **k):
+        out = real(*a, **k)
+        v = out["vecs"]
+        sign = torch.sign((v * ref_vecs).sum(dim=1, keepdim=True))
+        assert (v * sign - ref_vecs).abs().max() < 1e-4
+        out["vecs"] = ref_vecs
+        return out
+
+    monkeypatch.setattr(ops, "spectral_eig", with_reference_signs)
+    with torch.no_grad():
+        logits = m(f["pts"].cuda(), hlt_noise=f["noise"]).cpu()
+    err = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
+    assert err < 2e-3, err
