@@ -140,14 +140,6 @@ int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float*
                           void* dx, long ld_dx, float* dw, float* dbias, int batch, int L, int D, int width,
                           int silu, int dtype, sim_stream_t stream);
 
-/* a-10  fp32-accurate projection GEMM on the tensor cores: Y[M,N] = X[M,K] . W[N,K]^T with fp32 in / out / accumulate,
- * operands split on the fly into 3 bf16 terms (tcgen05 "9xBF16" emulation).  Replaces the fp32 F.linear calls of
- * Mamba.forward (in_proj / x_proj / dt_proj / out_proj, models/block.py:72) on the no-autocast finetune / test path.
- * Row strides lda / ldb / ldd in elements; all of K, N, lda, ldb, ldd must be multiples of 4. */
-size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K);
-int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
-                    void* workspace, size_t workspace_bytes, sim_stream_t stream);
-
 /* a-5 / a-7 / a-8  spectral permutation from sort keys: stable ascending argsort of an eigenvector column
  * (sort_points_by_fiedler, models/point_mamba.py:817-826) or of the HLT bucket keys id + u with the caller's
  * tie-break noise (part_segmentation/models/pt_mamba.py:670-680).  Same contract as sim_argsort_rows. */
@@ -178,6 +170,12 @@ int sim_mae_restore_bwd(const void* dx_full, const int32_t* vis_pos, const int32
 /* out[b,r] = sum_j x[b, idx[b,r,j]] over idx >= 0: deterministic backward of any row gather given its inverse map */
 int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int R_in, int R_out, int J, int C,
                         int dtype, sim_stream_t stream);
+/* inverse of a row-gather map: inv[b,r,0..J) = ascending output rows t with src_idx[b,t] == r, -1 padded, so that the
+ * backward of sim_gather_rows (HLT layout pt_mamba.py:670-723; MAE pos / reconstruction gathers point_mamba.py:3192-3197)
+ * is sim_gather_sum_rows instead of an atomic scatter-add.  *err_flag = b + 1 if a row of cloud b has more than J
+ * readers.  src_idx (B,R_out), inv (B,R_in,J). */
+int sim_invert_row_map(const int32_t* src_idx, int B, int R_in, int R_out, int J, int32_t* inv, int32_t* err_flag,
+                       sim_stream_t stream);
 
 /* f-1  data-prep farthest-point sampling with pointnet2_ops semantics, as the runners call it right before the model
  * (utils/misc.py:14-21 fps(data, number); tools/runner_finetune.py:177-194): furthest_point_sample + gather_operation

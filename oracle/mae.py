@@ -94,3 +94,25 @@ def point_mae_forward(sd: dict, cfg: dict, pts: torch.Tensor, mask: torch.Tensor
     gt = nbr_full[mfull].reshape(B * M, Gs, 3)
     loss = chamfer_l2(reb, gt).mean()
     return loss, dict(perm=perm, x_vis=x_vis, x_full=x_full, mask_full=mfull, eigvecs=vecs)
+
+
+def mae_index_maps_torch(perm: torch.Tensor, mask: torch.Tensor):
+    """perm (B,k,G) int, mask (B,G) bool with the same number of masked patches in every cloud ->
+    dict(src_vis (B, 2k*n_vis) patch feeding each encoder token,
+         restore_src (B, 2kG) row of the encoder output for each decoder position, -1 = mask token,
+         mask_full (B, 2kG) bool,
+         rec_src (B, 2k*m) decoder positions that are reconstructed, ascending,
+         perm_full (B, 2kG) patch behind every decoder position)."""
+    B, k, G = perm.shape
+    flat = perm.reshape(B, k * G).long()
+    perm_full = torch.cat((flat, flat.flip(1)), dim=1)
+    m_sorted = torch.gather(mask, 1, flat)
+    mask_full = torch.cat((m_sorted, m_sorted.flip(1)), dim=1)
+    n_vis_total = int((~mask_full[0]).sum())
+    order = torch.sort(mask_full.to(torch.int8), dim=1, stable=True).indices  # visible positions first, in order
+    vis_pos, msk_pos = order[:, :n_vis_total], order[:, n_vis_total:]
+    src_vis = torch.gather(perm_full, 1, vis_pos)
+    rank = torch.cumsum((~mask_full).to(torch.int32), dim=1) - 1
+    restore_src = torch.where(mask_full, torch.full_like(rank, -1), rank)
+    return dict(src_vis=src_vis.int(), restore_src=restore_src.int(), mask_full=mask_full, rec_src=msk_pos.int(),
+                perm_full=perm_full.int())

@@ -134,8 +134,10 @@ def layer_norm(sd, prefix, x, eps=1e-5):
 
 
 def mixer_model(sd: dict, prefix: str, tokens, pos, n_layer: int, eps: float = 1e-5, fetch_idx=None,
-                mixer=None, trace=None):
-    """MixerModel.forward (point_mamba.py:247-258) in eval mode (DropPath/Dropout identity).
+                mixer=None, trace=None, drop_scale=None):
+    """MixerModel.forward (point_mamba.py:247-258); eval mode (DropPath/Dropout identity) unless ``drop_scale`` is
+    given: a list with one (B,) tensor per layer i >= 1 holding timm DropPath's per-sample factor mask / keep that
+    multiplies h in ``drop_path(h) + residual`` (block.py:59; layer 0 has no residual yet, so its input is never dropped).
 
     Block.forward (block.py:56-72): residual = h (+ residual); h = LN(residual); h = mixer(h).
     With ``fetch_idx`` returns the seg variant's list of norm_f(h + residual) taps
@@ -147,7 +149,12 @@ def mixer_model(sd: dict, prefix: str, tokens, pos, n_layer: int, eps: float = 1
     residual = None
     taps = []
     for i in range(n_layer):
-        residual = h if residual is None else h + residual
+        if residual is None:
+            residual = h
+        elif drop_scale is not None:
+            residual = h * drop_scale[i - 1].view(-1, 1, 1) + residual
+        else:
+            residual = h + residual
         h = layer_norm(sd, f"{prefix}layers.{i}.norm.", residual, eps)
         h = mixer(sd, f"{prefix}layers.{i}.mixer.", h)
         if trace is not None:

@@ -45,7 +45,6 @@ SIGNATURES = {
     "sim_selective_scan_bwd": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p,
                                     _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _p,
                                     _i, _i, _i, _i, _i, _i, _p]),
-    "sim_gemm_f32_tc_workspace_bytes": (_sz, [_i, _i, _i]),
     "sim_add_layernorm_split3": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _i, _p]),
     "sim_causal_conv1d_fwd_split3": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _i, _i, _i, _i, _i, _p]),
     "sim_selective_scan_fwd_split3": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _l,
@@ -56,6 +55,7 @@ SIGNATURES = {
     "sim_mae_restore_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sim_mae_restore_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sim_gather_sum_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sim_invert_row_map": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "sim_spectral_perm": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
     "sim_three_nn_interp_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sim_three_interp_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
@@ -74,7 +74,6 @@ SIGNATURES = {
     "sim_layernorm_mean": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
     "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),
-    "sim_gemm_f32_tc": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _sz, _p]),
     "sim_causal_conv1d_bwd": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }
 

@@ -21,8 +21,11 @@ def _amp_dtype(x: torch.Tensor) -> torch.dtype:
 class _ParamCache:
     """Inference-only cache of derived parameter tensors (low-precision copies of the projection weights,
     A = -exp(A_log)).  ncu showed 111 cast / elementwise launches per bf16 forward, most of them re-casting the
-    same weights; entries are keyed on the parameter's storage and version counter, so an optimizer step or a
-    load_state_dict invalidates them.  Never used while autograd is recording."""
+    same weights; entries are keyed on the parameter's storage and version counter, so an eager optimizer step or a
+    load_state_dict invalidates them.  Updates that bump neither key - a CUDA-graph replay that contains
+    optimizer.step() (train.GraphedStep), writes through ``p.data`` (EMA swaps) - must call
+    ``invalidate_param_cache()``: GraphedStep.replay() does, and every torch optimizer step does through a global
+    post-step hook.  Never used while autograd is recording."""
 
     def __init__(self):
         from torch.utils.weak import WeakIdKeyDictionary  # identity-keyed: tensors do not compare with ==
@@ -55,7 +58,24 @@ class _ParamCache:
         return val
 
 
+    def clear(self):
+        self._d.clear()
+
+
 _CACHE = _ParamCache()
+
+
+def invalidate_param_cache(*_args, **_kwargs) -> None:
+    """Drop every derived-parameter entry (cast / split weights, A, BatchNorm folds).  Call after parameters or BN
+    running statistics changed without their version counters noticing (graph replay, ``.data`` writes)."""
+    _CACHE.clear()
+
+
+try:  # any eager optimizer.step() invalidates too (cheap: the cache is rebuilt lazily by the next eval forward)
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(invalidate_param_cache)
+except ImportError:  # pragma: no cover
+    pass
 # SIM_FUSE_DT=1: dt_proj inside the scan kernel (inference).  Measured neutral on B200 (106 us fused vs 84 us scan + 22 us
 # dt_proj GEMM at the C1 layer shape: the scan is issue-bound, the elementwise warps' extra 140 instructions per tile cost
 # what the GEMM launch did), so the separate, simpler path stays the default; the fused kernel saves 100 MB of HBM traffic
@@ -81,7 +101,7 @@ _CONV_XPROJ = __import__("os").environ.get("SIM_CONV_XPROJ", "0") != "0"  # caus
 # graph): HLT 21.8 -> 19.4 ms, SAST 48.0 -> 37.0 ms.  dW contracts over all B*L rows with few output tiles: the kernel's
 # split-K both fills the SMs and keeps each tensor-core accumulation chain short (6e-7 against fp64, cuBLAS SGEMM 8e-7).
 _TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "1") != "0"
-_FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | tc (CUTLASS) | cublas
+_FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | cublas (ablation)
 
 
 class _SplitCols(torch.autograd.Function):
@@ -107,12 +127,13 @@ class _SplitCols(torch.autograd.Function):
         return (torch.cat(parts, dim=-1),) + (None,) * len(ctx.sizes)
 
 
-def wants_split3(hidden_dtype: torch.dtype, in_proj_w: torch.Tensor, d_model: int) -> bool:
+def wants_split3(hidden_dtype: torch.dtype, in_proj_w: torch.Tensor, d_model: int, params=()) -> bool:
     """True when the mixer would consume its input as a Split3 (fp32 inference on the x3 GEMM path): the Block's
-    fused add + LayerNorm then writes the split planes directly instead of an fp32 tensor."""
-    return (_FP32_GEMM not in ("cublas", "tc") and hidden_dtype == torch.float32 and in_proj_w.dtype == torch.float32
+    fused add + LayerNorm then writes the split planes directly instead of an fp32 tensor.  ``params`` = every mixer
+    parameter: the predicate is mamba_inner_tm's own ``need_grad`` test, so a partially frozen mixer never gets one."""
+    return (_FP32_GEMM != "cublas" and hidden_dtype == torch.float32 and in_proj_w.dtype == torch.float32
             and in_proj_w.is_cuda and d_model % 8 == 0
-            and not (torch.is_grad_enabled() and in_proj_w.requires_grad))
+            and not (torch.is_grad_enabled() and any(t.requires_grad for t in (in_proj_w, *params))))
 
 
 def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D, out_proj_w,
@@ -132,19 +153,16 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         A = _CACHE.get(A_log, "A", lambda t: -torch.exp(t.float()))
     # fp32 inference: the four projections run on the tensor cores with fp32-accurate 3 x bf16 operand splitting.
     # x3: hand-written TMA + tcgen05 kernel on pre-split planes (weights split once and cached, 3.7x cuBLAS SGEMM on
-    # in_proj); tc: CUTLASS FastF32 collectives (1.8x); cublas: F.linear (SIMT SGEMM).
+    # in_proj); cublas: F.linear (SIMT SGEMM), kept as the ablation switch.
     linear = F.linear
     x3 = False
     if not need_grad and act == torch.float32 and hidden.is_cuda and _FP32_GEMM != "cublas":
-        if _FP32_GEMM == "tc":
-            linear = ops.linear_f32_tc
-        else:
-            x3 = d_inner % 64 == 0  # every producer below then emits the split operand of the next projection itself
+        x3 = d_inner % 64 == 0  # every producer below then emits the split operand of the next projection itself
 
-            def linear(x, w):
-                return ops.linear_f32_x3(x, _CACHE.get(w, "x3", ops.split3), w.shape[1])
+        def linear(x, w):
+            return ops.linear_f32_x3(x, _CACHE.get(w, "x3", ops.split3), w.shape[1])
     if (need_grad and _TRAIN_X3 and act == torch.float32 and hidden.is_cuda and in_proj_w.dtype == torch.float32
-            and _FP32_GEMM not in ("cublas", "tc") and d_inner % 8 == 0 and hidden.shape[-1] % 8 == 0 and dt_rank % 4 == 0):
+            and _FP32_GEMM != "cublas" and d_inner % 8 == 0 and hidden.shape[-1] % 8 == 0 and dt_rank % 4 == 0):
         linear = ops.linear_x3_train  # fp32 training: forward, dX and dW GEMMs on the split-plane tensor-core kernel
     join_z = None
     if x3 and _OVERLAP_Z:

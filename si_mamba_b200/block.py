@@ -41,7 +41,10 @@ def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor
     needed; plain torch ops (so autograd works) when training."""
     needs_grad = torch.is_grad_enabled() and (hidden.requires_grad or (residual is not None and residual.requires_grad)
                                               or norm.weight.requires_grad)
-    if not isinstance(norm, nn.LayerNorm) or not hidden.is_cuda or norm.weight is None or norm.bias is None:
+    if not hidden.is_cuda:
+        raise RuntimeError("si-mamba Block runs on CUDA tensors only (there is no CPU fallback)")
+    if not isinstance(norm, nn.LayerNorm) or norm.weight is None or norm.bias is None:
+        # `rms_norm: True` / affine-free norms: not selected by any shipped config, no kernel - plain torch ops on the device
         res = hidden + residual if residual is not None else hidden
         res = res.float() if res.dtype != torch.float32 else res
         return norm(res.to(dtype=norm.weight.dtype)), res
@@ -67,7 +70,9 @@ class Block(nn.Module):
         # fp32 inference: LayerNorm writes the in_proj operand (three bf16 planes) directly, see autograd.wants_split3
         want = getattr(self.mixer, "wants_split3", None)
         split = bool(want and want(hidden_states))
-        hidden_states, residual = fused_add_norm(self.norm, self.drop_path(hidden_states), residual, split=split)
+        # block.py:59: `drop_path(h) + residual if residual is not None else h` - the first block's input is never dropped
+        h = self.drop_path(hidden_states) if residual is not None else hidden_states
+        hidden_states, residual = fused_add_norm(self.norm, h, residual, split=split)
         hidden_states = self.mixer(hidden_states, inference_params=inference_params)
         return hidden_states, residual
 

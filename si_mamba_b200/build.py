@@ -28,18 +28,6 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 
-def cutlass_include() -> Path:
-    """CUTLASS / CuTe header tree vendored in the image (flashinfer ships CUTLASS 4.x); used by gemm_fastf32.cu only."""
-    import importlib.util
-    for pkg, rel in (("flashinfer", "data/cutlass/include"), ("tilelang", "3rdparty/cutlass/include")):
-        spec = importlib.util.find_spec(pkg)
-        if spec and spec.origin:
-            p = Path(spec.origin).parent / rel
-            if (p / "cutlass" / "cutlass.h").exists():
-                return p
-    raise RuntimeError("no CUTLASS header tree found (expected under site-packages/flashinfer/data/cutlass/include)")
-
-
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
@@ -64,8 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path):
         obj = BUILD / (src.stem + ".o")
-        extra = ["-I", str(cutlass_include())] if "cutlass" in src.read_text() else []
-        cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *ARCH, *CFLAGS, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 

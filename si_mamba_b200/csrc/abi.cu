@@ -205,14 +205,6 @@ int sim_causal_conv1d_bwd(const void* x, long ld_x, const float* w, const float*
                                 static_cast<cudaStream_t>(stream));
 }
 
-size_t sim_gemm_f32_tc_workspace_bytes(int M, int N, int K) { return sim::gemm_f32_tc_workspace_bytes(M, N, K); }
-
-int sim_gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
-                    void* workspace, size_t workspace_bytes, sim_stream_t stream) {
-  return sim::gemm_f32_tc(X, lda, W, ldb, Y, ldd, M, N, K, workspace, workspace_bytes,
-                          static_cast<cudaStream_t>(stream));
-}
-
 int sim_mae_index_maps(const int32_t* perm, const unsigned char* mask, int B, int k, int G, int n_vis,
                        int32_t* perm_full, unsigned char* mask_full, int32_t* restore_src, int32_t* src_vis,
                        int32_t* vis_pos, int32_t* rec_src, int32_t* inv_vis, int32_t* err_flag, sim_stream_t stream) {
@@ -246,6 +238,11 @@ int sim_mae_restore_bwd(const void* dx_full, const int32_t* vis_pos, const int32
 int sim_gather_sum_rows(const void* x, const int32_t* idx, void* out, int B, int R_in, int R_out, int J, int C,
                         int dtype, sim_stream_t stream) {
   return sim::gather_sum_rows(x, idx, out, B, R_in, R_out, J, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_invert_row_map(const int32_t* src_idx, int B, int R_in, int R_out, int J, int32_t* inv, int32_t* err_flag,
+                       sim_stream_t stream) {
+  return sim::invert_row_map(src_idx, B, R_in, R_out, J, inv, err_flag, static_cast<cudaStream_t>(stream));
 }
 
 int sim_spectral_perm(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,

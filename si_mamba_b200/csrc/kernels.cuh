@@ -91,16 +91,13 @@ struct SpectralParams {
 size_t spectral_workspace_bytes(int, int, int);
 int spectral_eig(SpectralParams, void*, size_t, cudaStream_t);
 
-size_t gemm_f32_tc_workspace_bytes(int M, int N, int K);
-int gemm_f32_tc(const float* X, long lda, const float* W, long ldb, float* Y, long ldd, int M, int N, int K,
-                void* workspace, size_t workspace_bytes, cudaStream_t stream);
-
 int mae_index_maps(const int* perm, const unsigned char* mask, int B, int k, int G, int n_vis, int* perm_full,
                    unsigned char* mask_full, int* restore_src, int* src_vis, int* vis_pos, int* rec_src, int* inv_vis,
                    int* err_flag, cudaStream_t stream);
 int gather_sum_rows(const void* x, const int* idx, void* out, int B, int R_in, int R_out, int J, int C, int dtype,
                     cudaStream_t stream);
 int masked_colsum(const void* x, const int* sel, long rows, int C, float* dfill, int dtype, cudaStream_t stream);
+int invert_row_map(const int* src_idx, int B, int R_in, int R_out, int J, int* inv, int* err_flag, cudaStream_t stream);
 int three_nn_interp_fwd(const float* xyz1, const float* xyz2, const float* points2, int B, int N, int S, int C, float* out,
                         int* idx, float* weight, cudaStream_t stream);
 int three_interp_bwd(const float* dout, const int* idx, const float* weight, int B, int N, int S, int C, float* dpoints2,

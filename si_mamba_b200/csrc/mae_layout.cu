@@ -112,6 +112,29 @@ __global__ void __launch_bounds__(256) gather_sum_rows_kernel(const T* __restric
   }
 }
 
+// inv[b, r, 0..J) = ascending list of the output rows t with src_idx[b, t] == r (-1 padded): the inverse of any row
+// gather map, so that its backward runs as gather_sum_rows (deterministic, no atomics).  One CTA per cloud; thread r
+// walks the map (staged in shared memory) for source row r.  A row read by more than J outputs raises err = b + 1.
+__global__ void __launch_bounds__(256) invert_row_map_kernel(const int* __restrict__ src_idx, int R_in, int R_out, int J,
+                                                             int* __restrict__ inv, int* __restrict__ err) {
+  extern __shared__ int s_map[];
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < R_out; t += blockDim.x) s_map[t] = src_idx[(long)b * R_out + t];
+  __syncthreads();
+  for (int r = threadIdx.x; r < R_in; r += blockDim.x) {
+    int* o = inv + ((long)b * R_in + r) * J;
+    int n = 0;
+    for (int t = 0; t < R_out; ++t) {
+      if (s_map[t] == r) {
+        if (n < J) o[n] = t;
+        ++n;
+      }
+    }
+    if (n > J) atomicExch(err, b + 1);
+    for (; n < J; ++n) o[n] = -1;
+  }
+}
+
 // dfill[c] += sum over rows with sel[row] < 0 of x[row, c]   (gradient of the mask token)
 template <typename T>
 __global__ void __launch_bounds__(256) masked_colsum_kernel(const T* __restrict__ x, const int* __restrict__ sel, long rows,
@@ -157,6 +180,14 @@ int gather_sum_rows(const void* x, const int* idx, void* out, int B, int R_in, i
     return SIM_ERR_INVALID;
   }
   return check_launch("gather_sum_rows");
+}
+
+int invert_row_map(const int* src_idx, int B, int R_in, int R_out, int J, int* inv, int* err_flag, cudaStream_t stream) {
+  SIM_REQUIRE(src_idx && inv && err_flag, SIM_ERR_INVALID, "invert_row_map: null tensor");
+  SIM_REQUIRE(B > 0 && R_in > 0 && R_out > 0 && J > 0 && R_out <= 12288, SIM_ERR_INVALID,
+              "invert_row_map: bad sizes (R_out <= 12288)");
+  invert_row_map_kernel<<<B, 256, R_out * sizeof(int), stream>>>(src_idx, R_in, R_out, J, inv, err_flag);
+  return check_launch("invert_row_map");
 }
 
 int masked_colsum(const void* x, const int* sel, long rows, int C, float* dfill, int dtype, cudaStream_t stream) {

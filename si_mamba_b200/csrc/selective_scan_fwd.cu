@@ -277,183 +277,6 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
   if (tid == 0) bulk_wait0();
 }
 
-// ================================================================================================
-// Warp-autonomous variant ("wa").  ncu on the tile-synchronous kernel above showed it latency-bound at B=32: the MUFU
-// pipe 54 % busy, issue slots 45 %, stalls = fixed-latency waits + short scoreboard, two block barriers and a
-// separate pre-pass phase per tile.  Here every warp runs on its own: no __syncthreads in steady state, no
-// work arrays and no pre-pass - the lane that will WRITE step r (transposed butterfly) also evaluates
-// softplus(delta_r) / silu(z_r) for it and hands dt to its partner lanes with a shuffle; operands are read
-// straight from the TMA stage (B / C as broadcast LDS.128), results go to global memory as 64-byte row
-// segments.  Stage recycling uses an mbarrier pair per stage (full: TMA bytes landed; empty: one arrival per warp).
-template <typename T, int S_, int CH_, int NS_>
-struct ScanWaCfg {
-  static constexpr int S = S_;
-  static constexpr int LPC = kNState / S_;
-  static constexpr int CH = CH_;
-  static constexpr int TT = kScanTile;
-  static constexpr int NS = NS_;
-  static constexpr int NT = CH_ * LPC;
-  static constexpr int NW = NT / 32;
-  static constexpr int RAW_MAIN = TT * CH_ * (int)sizeof(T);
-  static constexpr int RAW_BC = TT * kNState * (int)sizeof(T);
-  static constexpr int RAW_STAGE = 3 * RAW_MAIN + 2 * RAW_BC;
-  static constexpr int SMEM = NS_ * RAW_STAGE + 2 * NS_ * 8 + 16;
-  static_assert(RAW_STAGE % 128 == 0 && RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0, "TMA tiles must stay 128-B aligned");
-  static_assert(NT % 32 == 0, "whole warps");
-};
-
-template <typename Cfg, typename T>
-__global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_wa_kernel(const __grid_constant__ ScanTmaps tm,
-                                                                        const ScanParams p) {
-  constexpr int S = Cfg::S, LPC = Cfg::LPC, CH = Cfg::CH, TT = Cfg::TT, NS = Cfg::NS, NW = Cfg::NW;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* raw = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::RAW_STAGE);
-  uint64_t* empty = full + NS;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int nchunk = p.D / CH;
-  const int b = blockIdx.x / nchunk;
-  const int c0 = (blockIdx.x % nchunk) * CH;
-  const int sub = tid % LPC;
-  const int c = tid / LPC;  // channel within the CTA
-  const int ntiles = (p.L + TT - 1) / TT;
-  const bool has_z = p.z != nullptr;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tm.u);
-    tma_prefetch_desc(&tm.delta);
-    tma_prefetch_desc(&tm.B);
-    tma_prefetch_desc(&tm.C);
-    if (has_z) tma_prefetch_desc(&tm.z);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NW);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  auto issue_tile = [&](int tile) {
-    const int s = tile % NS;
-    const int t0 = tile * TT;
-    unsigned char* st = raw + s * Cfg::RAW_STAGE;
-    mbar_arrive_expect_tx(&full[s], (has_z ? 3u : 2u) * Cfg::RAW_MAIN + 2u * Cfg::RAW_BC);
-    tma_load_3d(st, &tm.u, c0, t0, b, &full[s]);
-    tma_load_3d(st + Cfg::RAW_MAIN, &tm.delta, c0, t0, b, &full[s]);
-    if (has_z) tma_load_3d(st + 2 * Cfg::RAW_MAIN, &tm.z, c0, t0, b, &full[s]);
-    tma_load_3d(st + 3 * Cfg::RAW_MAIN, &tm.B, 0, t0, b, &full[s]);
-    tma_load_3d(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC, &tm.C, 0, t0, b, &full[s]);
-  };
-  if (tid == 0) {
-    for (int k = 0; k < NS && k < ntiles; ++k) issue_tile(k);
-  }
-
-  float2 A2[S / 2], h[S / 2];
-#pragma unroll
-  for (int j = 0; j < S / 2; ++j) {
-    const float* Ap = p.A + (long)(c0 + c) * kNState + sub * S + 2 * j;
-    A2[j] = make_float2(Ap[0] * kLog2e, Ap[1] * kLog2e);
-    h[j] = make_float2(0.f, 0.f);
-  }
-  const float Dc = p.Dv ? p.Dv[c0 + c] : 0.f;
-  const float bias_c = p.dbias ? p.dbias[c0 + c] : 0.f;
-  T* gout = static_cast<T*>(p.out) + ((long)b * p.L) * p.ld_out + c0 + c;
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int s = tile % NS;
-    const int t0 = tile * TT;
-    const int rows = min(TT, p.L - t0);
-    unsigned char* st = raw + s * Cfg::RAW_STAGE;
-    const T* su = reinterpret_cast<const T*>(st);
-    const T* sd = reinterpret_cast<const T*>(st + Cfg::RAW_MAIN);
-    const T* sz = reinterpret_cast<const T*>(st + 2 * Cfg::RAW_MAIN);
-    const T* sB = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN);
-    const T* sC = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC);
-
-    if (p.ckpt) {
-      float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + c) * kNState + sub * S);
-#pragma unroll
-      for (int j = 0; j < S / 2; ++j) dst[j] = h[j];
-    }
-    // producer duty: the stage of the PREVIOUS tile can be refilled once every warp has left it
-    if (tid == 0 && tile >= 1 && tile - 1 + NS < ntiles) {
-      mbar_wait(&empty[(tile - 1) % NS], ((tile - 1) / NS) & 1);
-      issue_tile(tile - 1 + NS);
-    }
-    mbar_wait(&full[s], (tile / NS) & 1);
-
-#pragma unroll
-    for (int r0 = 0; r0 < TT; r0 += LPC) {
-      // my step of this group (the one I will write): activation math for it
-      const int rm = r0 + sub;
-      const float x = to_f32<T>(sd[rm * CH + c]) + bias_c;
-      const float dt_mine = p.softplus ? softplus_f(x) : x;
-      const float u_mine = to_f32<T>(su[rm * CH + c]);
-      const float g_mine = has_z ? silu_f(to_f32<T>(sz[rm * CH + c])) : 1.f;
-      float part[LPC];
-#pragma unroll
-      for (int q = 0; q < LPC; ++q) {
-        // dt / u of step r0+q live in the lane with sub == q of my channel
-        const float dtv = __shfl_sync(0xffffffffu, dt_mine, (lane & ~(LPC - 1)) | q);
-        const float uv = __shfl_sync(0xffffffffu, u_mine, (lane & ~(LPC - 1)) | q);
-        float Bv[S], Cv[S];
-        lds_row<T, S>(sB + (r0 + q) * kNState + sub * S, Bv);
-        lds_row<T, S>(sC + (r0 + q) * kNState + sub * S, Cv);
-        const float dtu = dtv * uv;
-        const float2 dt2 = make_float2(dtv, dtv);
-        const float2 dtu2 = make_float2(dtu, dtu);
-        float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < S / 2; ++j) {
-          const float2 xx = __fmul2_rn(dt2, A2[j]);
-          const float2 a = make_float2(ex2_approx(xx.x), ex2_approx(xx.y));
-          const float2 bu = __fmul2_rn(dtu2, make_float2(Bv[2 * j], Bv[2 * j + 1]));
-          h[j] = __ffma2_rn(a, h[j], bu);
-          acc2 = __ffma2_rn(h[j], make_float2(Cv[2 * j], Cv[2 * j + 1]), acc2);
-        }
-        part[q] = acc2.x + acc2.y;
-      }
-#pragma unroll
-      for (int o = LPC / 2; o >= 1; o >>= 1) {
-        const bool up = (sub & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-          const float send = up ? part[i] : part[i + o];
-          const float keep = up ? part[i + o] : part[i];
-          part[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-      }
-      if (rm < rows) gout[(long)(t0 + rm) * p.ld_out] = from_f32<T>((part[0] + Dc * u_mine) * g_mine);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-}
-
-template <typename T, int S, int CH, int NS>
-static int launch_scan_wa(const ScanParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = ScanWaCfg<T, S, CH, NS>;
-  constexpr int TT = Cfg::TT;
-  auto kern = selective_scan_fwd_wa_kernel<Cfg, T>;
-  static SmemAttrCache attr;
-  if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_fwd_wa attr");
-  ScanTmaps tm;
-  int rc;
-  if ((rc = make_tmap_tokens(&tm.u, p.u, dtype, p.D, p.L, p.batch, p.ld_u, CH, TT))) return rc;
-  if ((rc = make_tmap_tokens(&tm.delta, p.delta, dtype, p.D, p.L, p.batch, p.ld_delta, CH, TT))) return rc;
-  if (p.z) {
-    if ((rc = make_tmap_tokens(&tm.z, p.z, dtype, p.D, p.L, p.batch, p.ld_z, CH, TT))) return rc;
-  } else {
-    tm.z = tm.u;
-  }
-  if ((rc = make_tmap_tokens(&tm.B, p.Bm, dtype, kNState, p.L, p.batch, p.ld_B, kNState, TT))) return rc;
-  if ((rc = make_tmap_tokens(&tm.C, p.Cm, dtype, kNState, p.L, p.batch, p.ld_C, kNState, TT))) return rc;
-  tm.out = tm.u;  // unused: results are written with plain stores
-  kern<<<p.batch * (p.D / CH), Cfg::NT, Cfg::SMEM, stream>>>(tm, p);
-  return check_launch("selective_scan_fwd_wa");
-}
-
 template <typename T, int S, int CPT, int CH, int TT, int NS, int DBG = 0>
 static int launch_scan(const ScanParams& p, int dtype, cudaStream_t stream) {
   using Cfg = ScanCfg<T, S, CPT, CH, TT, NS, DBG>;
@@ -486,43 +309,9 @@ static int dispatch_scan(const ScanParams& p, int dtype, int variant, cudaStream
   // for channel counts that are not a multiple of 64.
   if (variant == 0) variant = (p.D % 64 == 0) ? 5008 : 108;
   if (variant >= 5000 && variant < 9000) return selective_scan_fwd_ws(p, dtype, variant, stream);
-  if (variant < 100) variant += 100;
-  if (p.D % 64 == 0) {
-    switch (variant) {
-      case 102: return launch_scan<T, 2, 1, 32, 16, 3>(p, dtype, stream);
-      case 104: return launch_scan<T, 4, 1, 64, 16, 3>(p, dtype, stream);
-      case 108: return launch_scan<T, 8, 1, 64, 16, 3>(p, dtype, stream);
-      case 116: return launch_scan<T, 16, 1, 64, 16, 3>(p, dtype, stream);
-      case 202: return launch_scan<T, 2, 2, 64, 16, 3>(p, dtype, stream);
-      case 204: return launch_scan<T, 4, 2, 64, 16, 3>(p, dtype, stream);
-      case 208: return launch_scan<T, 8, 2, 64, 16, 3>(p, dtype, stream);
-      case 216: return launch_scan<T, 16, 2, 64, 16, 3>(p, dtype, stream);
-      case 402: return launch_scan<T, 2, 4, 64, 16, 3>(p, dtype, stream);
-      case 404: return launch_scan<T, 4, 4, 64, 16, 3>(p, dtype, stream);
-      case 408: return launch_scan<T, 8, 4, 64, 16, 3>(p, dtype, stream);
-      // bench-only ablations of variant 108 (WRONG results; see ScanCfg::DBG)
-      case 9001: return launch_scan<T, 8, 1, 64, 16, 3, 1>(p, dtype, stream);
-      case 9002: return launch_scan<T, 8, 1, 64, 16, 3, 2>(p, dtype, stream);
-      case 9004: return launch_scan<T, 8, 1, 64, 16, 3, 4>(p, dtype, stream);
-      case 9008: return launch_scan<T, 8, 1, 64, 16, 3, 8>(p, dtype, stream);
-      case 9015: return launch_scan<T, 8, 1, 64, 16, 3, 15>(p, dtype, stream);
-      case 9016: return launch_scan<T, 8, 1, 64, 16, 3, 16>(p, dtype, stream);
-      case 9018: return launch_scan<T, 8, 1, 64, 16, 3, 18>(p, dtype, stream);
-      // warp-autonomous kernels: 1000 + states per thread (+ 100 for 32-channel CTAs)
-      case 1002: return launch_scan_wa<T, 2, 32, 4>(p, dtype, stream);
-      case 1004: return launch_scan_wa<T, 4, 64, 4>(p, dtype, stream);
-      case 1008: return launch_scan_wa<T, 8, 64, 4>(p, dtype, stream);
-      case 1016: return launch_scan_wa<T, 16, 64, 4>(p, dtype, stream);
-      case 1104: return launch_scan_wa<T, 4, 32, 4>(p, dtype, stream);
-      case 1108: return launch_scan_wa<T, 8, 32, 4>(p, dtype, stream);
-      // fewer stages -> less shared memory -> more resident CTAs per SM (large batches)
-      case 2004: return launch_scan_wa<T, 4, 64, 2>(p, dtype, stream);
-      case 2008: return launch_scan_wa<T, 8, 64, 2>(p, dtype, stream);
-      case 2016: return launch_scan_wa<T, 16, 64, 2>(p, dtype, stream);
-      case 3008: return launch_scan_wa<T, 8, 64, 3>(p, dtype, stream);
-    }
-  } else if (p.D % 16 == 0) {
-    return launch_scan<T, 2, 1, 16, 16, 3>(p, dtype, stream);
+  if (variant == 108) {  // the one ablation kept: the tile-synchronous kernel on 64-channel CTAs (93 us vs 84 us at C1)
+    if (p.D % 64 == 0) return launch_scan<T, 8, 1, 64, 16, 3>(p, dtype, stream);
+    if (p.D % 16 == 0) return launch_scan<T, 2, 1, 16, 16, 3>(p, dtype, stream);
   }
   set_error("selective_scan_fwd: unsupported D=%d / variant=%d (D must be a multiple of 16)", p.D, variant);
   return SIM_ERR_INVALID;

@@ -13,37 +13,21 @@ from . import ops
 
 
 def mae_index_maps(perm: torch.Tensor, mask: torch.Tensor, n_vis: int = None, check: bool = False):
-    """Index maps of the MAE layout from ONE kernel (ops.mae_index_maps / sim_mae_index_maps); see
-    mae_index_maps_torch for the meaning of every map (kept as the in-tree description and for CPU use).
-    ``n_vis`` = visible patches per cloud (G - int(mask_ratio * G)); None counts them from the mask (host sync)."""
-    if not perm.is_cuda:
-        return mae_index_maps_torch(perm, mask)
-    if n_vis is None:
-        n_vis = int((~mask[0]).sum())
-        check = True
-    return ops.mae_index_maps(perm, mask, n_vis, check=check)
-
-
-def mae_index_maps_torch(perm: torch.Tensor, mask: torch.Tensor):
-    """perm (B,k,G) int, mask (B,G) bool with the same number of masked patches in every cloud ->
+    """Index maps of the MAE layout from ONE kernel (ops.mae_index_maps / sim_mae_index_maps):
+    perm (B,k,G) int, mask (B,G) bool with the same number of masked patches in every cloud ->
     dict(src_vis (B, 2k*n_vis) patch feeding each encoder token,
          restore_src (B, 2kG) row of the encoder output for each decoder position, -1 = mask token,
          mask_full (B, 2kG) bool,
          rec_src (B, 2k*m) decoder positions that are reconstructed, ascending,
-         perm_full (B, 2kG) patch behind every decoder position)."""
-    B, k, G = perm.shape
-    flat = perm.reshape(B, k * G).long()
-    perm_full = torch.cat((flat, flat.flip(1)), dim=1)
-    m_sorted = torch.gather(mask, 1, flat)
-    mask_full = torch.cat((m_sorted, m_sorted.flip(1)), dim=1)
-    n_vis_total = int((~mask_full[0]).sum())
-    order = torch.sort(mask_full.to(torch.int8), dim=1, stable=True).indices  # visible positions first, in order
-    vis_pos, msk_pos = order[:, :n_vis_total], order[:, n_vis_total:]
-    src_vis = torch.gather(perm_full, 1, vis_pos)
-    rank = torch.cumsum((~mask_full).to(torch.int32), dim=1) - 1
-    restore_src = torch.where(mask_full, torch.full_like(rank, -1), rank)
-    return dict(src_vis=src_vis.int(), restore_src=restore_src.int(), mask_full=mask_full, rec_src=msk_pos.int(),
-                perm_full=perm_full.int())
+         perm_full (B, 2kG) patch behind every decoder position, vis_pos / inv_vis the inverse maps).
+    The torch restatement the kernel is tested against lives in oracle/mae.py (mae_index_maps_torch).
+    ``n_vis`` = visible patches per cloud (G - int(mask_ratio * G)); None counts them from the mask (host sync)."""
+    if not perm.is_cuda:
+        raise RuntimeError("mae_index_maps runs on CUDA tensors only (there is no CPU fallback)")
+    if n_vis is None:
+        n_vis = int((~mask[0]).sum())
+        check = True
+    return ops.mae_index_maps(perm, mask, n_vis, check=check)
 
 
 _HLT_SLOTS = {}
@@ -81,30 +65,34 @@ def hlt_src_index(order: torch.Tensor, k: int, reverse: bool = True) -> torch.Te
 
 
 class _GatherRows(torch.autograd.Function):
-    """Differentiable sim_gather_rows: backward is the scatter-add of the same map (plus the fill-row reduction)."""
+    """Differentiable sim_gather_rows: the backward is a deterministic gather over the inverse map
+    (sim_invert_row_map + sim_gather_sum_rows), no atomics."""
 
     @staticmethod
-    def forward(ctx, x, src_idx, fill):
+    def forward(ctx, x, src_idx, fanout):
         ctx.save_for_backward(src_idx)
-        ctx.r_in = x.shape[1]
-        ctx.has_fill = fill is not None
-        return ops.gather_rows(x, src_idx, fill)
+        ctx.r_in, ctx.fanout = x.shape[1], fanout
+        return ops.gather_rows(x, src_idx, None)
 
     @staticmethod
     def backward(ctx, dout):
         (src_idx,) = ctx.saved_tensors
-        B, R_out, C = dout.shape
-        valid = (src_idx >= 0)
-        idx = src_idx.clamp(min=0).long()[..., None].expand(-1, -1, C)
-        dx = torch.zeros(B, ctx.r_in, C, dtype=dout.dtype, device=dout.device)
-        dx.scatter_add_(1, idx, dout * valid[..., None].to(dout.dtype))
-        dfill = (dout * (~valid)[..., None].to(dout.dtype)).sum(dim=(0, 1)) if ctx.has_fill else None
-        return dx, None, dfill
+        inv = ops.invert_row_map(src_idx, ctx.r_in, ctx.fanout)
+        return ops.gather_sum_rows(dout.contiguous(), inv), None, None
 
 
-def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: torch.Tensor = None) -> torch.Tensor:
-    """out[b,t] = x[b, src_idx[b,t]] (src >= 0) else fill / zeros; differentiable w.r.t. x and fill."""
+def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: torch.Tensor = None, fanout: int = None) -> torch.Tensor:
+    """out[b,t] = x[b, src_idx[b,t]] (src >= 0) else fill / zeros; differentiable w.r.t. x.  ``fanout`` = the largest
+    number of output rows that read one source row (2 for the HLT layout, 2k for the MAE position gather); None counts
+    it from the map (a host sync - pass it when the step is captured in a CUDA graph)."""
     src_idx = src_idx.to(torch.int32).contiguous()
-    if torch.is_grad_enabled() and (x.requires_grad or (fill is not None and fill.requires_grad)):
-        return _GatherRows.apply(x.contiguous(), src_idx, fill)
+    if torch.is_grad_enabled() and fill is not None and fill.requires_grad:
+        raise NotImplementedError("gather_rows: a trainable fill row is MaeRestore's job (ops.MaeRestore)")
+    if torch.is_grad_enabled() and x.requires_grad:
+        if fill is not None:
+            raise NotImplementedError("gather_rows: differentiable gather with a fill row is ops.MaeRestore")
+        if fanout is None:
+            flat = (src_idx.long() + torch.arange(src_idx.shape[0], device=src_idx.device)[:, None] * x.shape[1])
+            fanout = max(1, int(torch.bincount(flat[src_idx >= 0].reshape(-1), minlength=1).max()))
+        return _GatherRows.apply(x.contiguous(), src_idx, int(fanout))
     return ops.gather_rows(x, src_idx, fill)

@@ -22,11 +22,10 @@ from .point_mamba import Encoder, Group, MixerModel
 def chamfer_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """pytorch3d ``chamfer_distance(x, y, batch_reduction=None)[0]`` with squared L2 and point_reduction="mean"
     (models/point_mamba.py:2950, 3203): (N,P,3), (N,Q,3) -> (N,).  One warp per pair on the device
-    (csrc/chamfer.cu, sim_chamfer_l2_fwd / _bwd); plain torch only for CPU tensors or sets above 256 points."""
-    if x.is_cuda and x.shape[1] <= 256 and y.shape[1] <= 256:
-        return ops.chamfer_l2(x, y)
-    d = (x[:, :, None, :] - y[:, None, :, :]).pow(2).sum(-1)
-    return d.min(dim=2).values.mean(dim=1) + d.min(dim=1).values.mean(dim=1)
+    (csrc/chamfer.cu, sim_chamfer_l2_fwd / _bwd).  No CPU / eager fallback: CPU tensors or sets above 256 points raise."""
+    if not x.is_cuda or x.shape[1] > 256 or y.shape[1] > 256:
+        raise RuntimeError("chamfer_l2 runs on CUDA tensors with at most 256 points per set (there is no CPU fallback)")
+    return ops.chamfer_l2(x, y)
 
 
 def rand_mask_host(B: int, G: int, mask_ratio: float) -> torch.Tensor:
@@ -195,9 +194,9 @@ class Point_MAE_Mamba(nn.Module):
         B, _, C = x_vis.shape
         # token restore: decoder position t shows the mask token or the encoder row with the same visible rank
         x_full = ops.MaeRestore.apply(x_vis, self.mask_token, maps["restore_src"], maps["vis_pos"])
-        pos_full = layout.gather_rows(maps["pos"], maps["perm_full"])
+        pos_full = layout.gather_rows(maps["pos"], maps["perm_full"], fanout=2 * perm.shape[1])
         x_rec = self.MAE_decoder(x_full, pos_full, None)
-        x_rec = layout.gather_rows(x_rec, maps["rec_src"])                       # (B, 2k*m, C) masked positions
+        x_rec = layout.gather_rows(x_rec, maps["rec_src"], fanout=1)                    # (B, 2k*m, C) masked positions
         M = x_rec.shape[1]
         rebuild_points = self.increase_dim(x_rec.transpose(1, 2)).transpose(1, 2).reshape(B * M, -1, 3)
         patch_of_rec = torch.gather(maps["perm_full"].long(), 1, maps["rec_src"].long())   # (B, 2k*m)

@@ -83,7 +83,8 @@ class Mamba(nn.Module):
         from .autograd import wants_split3
         return (hidden_states.is_cuda and not hidden_states.requires_grad
                 and wants_split3(hidden_states.dtype if not torch.is_autocast_enabled("cuda") else
-                                 torch.get_autocast_dtype("cuda"), self.in_proj.weight, self.d_model)
+                                 torch.get_autocast_dtype("cuda"), self.in_proj.weight, self.d_model,
+                                 tuple(self.parameters()))
                 and self.d_inner % 64 == 0)
 
     def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):

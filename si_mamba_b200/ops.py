@@ -30,9 +30,20 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _cuda(*ts):
+    """Every tensor must live on the CURRENT CUDA device: kernels launch on torch.cuda.current_stream() of that device
+    (a model on cuda:1 under current device cuda:0 would otherwise run foreign pointers on the wrong context; under
+    nn.DataParallel / DDP each replica thread already runs with its own device current)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("si-mamba ops run on CUDA tensors only (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"si-mamba ops launch on the current CUDA device (cuda:{cur}) but got a tensor on {t.device}: "
+                               "wrap the call in torch.cuda.device(tensor.device)")
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -214,6 +225,30 @@ def gather_rows(x: torch.Tensor, src_idx: torch.Tensor, fill: Optional[torch.Ten
     out = torch.empty(B, R_out, Cc, dtype=x.dtype, device=x.device)
     f = None if fill is None else fill.to(x.dtype).contiguous()
     _lib.call("sim_gather_rows", _p(x), _p(src_idx), _p(f), _p(out), B, R_in, R_out, Cc, _dt(x), _stream())
+    return out
+
+
+def invert_row_map(src_idx: torch.Tensor, R_in: int, fanout: int, check: bool = False) -> torch.Tensor:
+    """src_idx (B, R_out) int32 -> inv (B, R_in, fanout) int32: the output rows that read each source row, ascending,
+    -1 padded (sim_invert_row_map).  ``check`` syncs and raises if a row has more than ``fanout`` readers."""
+    _cuda(src_idx)
+    B, R_out = src_idx.shape
+    inv = torch.empty(B, R_in, fanout, dtype=torch.int32, device=src_idx.device)
+    err = torch.zeros(1, dtype=torch.int32, device=src_idx.device)
+    _lib.call("sim_invert_row_map", _p(src_idx), B, R_in, R_out, fanout, _p(inv), _p(err), _stream())
+    if check and int(err.item()) != 0:
+        raise ValueError(f"invert_row_map: a source row of cloud {int(err.item()) - 1} has more than {fanout} readers")
+    return inv
+
+
+def gather_sum_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[b,r] = sum_j x[b, idx[b,r,j]] over idx >= 0 (sim_gather_sum_rows); x (B,R_in,C), idx (B,R_out,J) int32."""
+    _cuda(x, idx)
+    x = x.contiguous()
+    B, R_in, Cc = x.shape
+    R_out, J = idx.shape[1], idx.shape[2]
+    out = torch.empty(B, R_out, Cc, dtype=x.dtype, device=x.device)
+    _lib.call("sim_gather_sum_rows", _p(x), _p(idx), _p(out), B, R_in, R_out, J, Cc, _dt(x), _stream())
     return out
 
 
@@ -451,26 +486,6 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
 
 
 # ----------------------------------------------------------------------------- fp32 GEMM on tensor cores (a-10)
-def linear_f32_tc(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = x @ weight.T for fp32 tensors, fp32-accurate, on the tcgen05 tensor cores (forward only).
-    x (..., K) with unit inner stride and a uniform row stride (column slices of wider buffers are fine),
-    weight (N, K) = nn.Linear.weight."""
-    _cuda(x, weight)
-    assert x.dtype == torch.float32 and weight.dtype == torch.float32
-    K = x.shape[-1]
-    N = weight.shape[0]
-    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else _as_rows(x)
-    M = x2.shape[0]
-    w = weight if weight.stride(1) == 1 else weight.contiguous()
-    if out is None:
-        out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
-    ws_bytes = _lib.load().sim_gemm_f32_tc_workspace_bytes(M, N, K)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 256 else None
-    _lib.call("sim_gemm_f32_tc", _p(x2), x2.stride(0), _p(w), w.stride(0), _p(out), N, M, N, K, _p(ws),
-              ws_bytes if ws is not None else 0, _stream())
-    return out
-
-
 class AddLayerNorm(torch.autograd.Function):
     """(y, res) = (LayerNorm(x + residual), x + residual) with the residual stream in fp32: sim_add_layernorm forward,
     sim_add_layernorm_bwd backward (statistics recomputed from ``res``, which autograd keeps alive anyway)."""

@@ -36,9 +36,6 @@ class RMSNorm(nn.Module):
         return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight.float()).to(x.dtype)
 
 
-_ENCODER_ROWS = __import__("os").environ.get("SIM_ENCODER_ROWS", "1") != "0"
-
-
 _HEAD_KERNEL = __import__("os").environ.get("SIM_HEAD_KERNEL", "1") != "0"  # 0: classifier head through nn.Sequential
 
 
@@ -122,17 +119,11 @@ class Encoder(nn.Module):
             f = F.linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)          # (P, 256)
             w3, b3 = self._fold_bn(self.second_conv[0], self.second_conv[1])
             c_loc = f.shape[-1]
-            if x.is_cuda and f.dtype in (torch.float32, torch.bfloat16):
-                # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
-                fg = ops.group_max(f, n)                                                            # (BG, 256)
-                h2 = ops.group_bias_relu_(F.linear(f, w3[:, c_loc:]), F.linear(fg, w3[:, :c_loc], b3), n)
-                o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)    # (P, C)
-                return ops.group_max(o, n).view(bs, g, self.encoder_channel)
-            fg = f.view(BG, n, -1).max(dim=1).values                                                # (BG, 256)
-            t = F.linear(f, w3[:, c_loc:]).view(BG, n, -1) + F.linear(fg, w3[:, :c_loc], b3)[:, None, :]
-            h2 = F.relu(t).view(P, -1)
-            o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)        # (P, C)
-            return o.view(BG, n, -1).max(dim=1).values.view(bs, g, self.encoder_channel)
+            # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
+            fg = ops.group_max(f, n)                                                            # (BG, 256)
+            h2 = ops.group_bias_relu_(F.linear(f, w3[:, c_loc:]), F.linear(fg, w3[:, :c_loc], b3), n)
+            o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)    # (P, C)
+            return ops.group_max(o, n).view(bs, g, self.encoder_channel)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
@@ -159,18 +150,11 @@ class Encoder(nn.Module):
 
     def forward(self, point_groups):
         """point_groups (B, G, M, 3) -> (B, G, C)."""
+        if not point_groups.is_cuda:
+            raise RuntimeError("si-mamba Encoder runs on CUDA tensors only (there is no CPU fallback)")
         if not self.training and not torch.is_grad_enabled():
             return self._forward_eval(point_groups)
-        if point_groups.is_cuda and _ENCODER_ROWS:
-            return self._forward_rows(point_groups)
-        bs, g, n, _ = point_groups.shape
-        point_groups = point_groups.reshape(bs * g, n, 3)
-        feature = self.first_conv(point_groups.transpose(2, 1))
-        feature_global = torch.max(feature, dim=2, keepdim=True)[0]
-        feature = torch.cat([feature_global.expand(-1, -1, n), feature], dim=1)
-        feature = self.second_conv(feature)
-        feature_global = torch.max(feature, dim=2, keepdim=False)[0]
-        return feature_global.reshape(bs, g, self.encoder_channel)
+        return self._forward_rows(point_groups)
 
 
 class Group(nn.Module):
@@ -459,8 +443,8 @@ class PointMamba(nn.Module):
         training_graph = torch.is_grad_enabled() and (group_input_tokens.requires_grad or pos.requires_grad)
         p_drop = self.drop_out.p if self.training else 0.0
         if perm is None:
-            x = self.drop_out(layout.gather_rows(group_input_tokens, src))
-            x = self.blocks(x, layout.gather_rows(pos, src))
+            x = self.drop_out(layout.gather_rows(group_input_tokens, src, fanout=2))
+            x = self.blocks(x, layout.gather_rows(pos, src, fanout=2))
         elif not training_graph and p_drop == 0.0:
             # tokens + pos folded into the gather: gather(tok) + gather(pos) == gather(tok + pos) bit for bit
             x = ops.order_gather_add(group_input_tokens, pos, perm, reverse)

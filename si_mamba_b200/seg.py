@@ -60,17 +60,6 @@ class MixerModelForSegmentation(nn.Module):
         return feature_list
 
 
-def square_distance(src, dst):
-    """pointnet2_utils.py square_distance: -2 src.dst^T + |src|^2 + |dst|^2."""
-    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
-    dist += torch.sum(src ** 2, -1)[:, :, None]
-    dist += torch.sum(dst ** 2, -1)[:, None, :]
-    return dist
-
-
-_THREE_NN_KERNEL = __import__("os").environ.get("SIM_THREE_NN", "1") != "0"  # 0: the torch topk + gather formulation
-
-
 class PointNetFeaturePropagation(nn.Module):
     """pointnet2_utils.py:262-311 (3-NN inverse-squared-distance interpolation + shared MLP)."""
 
@@ -92,19 +81,11 @@ class PointNetFeaturePropagation(nn.Module):
         _, S, _ = xyz2.shape
         if S == 1:
             interpolated_points = points2.repeat(1, N, 1)
-        elif xyz1.is_cuda and 3 <= S <= 2048 and _THREE_NN_KERNEL:
+        else:
+            if not xyz1.is_cuda or not 3 <= S <= 2048:
+                raise RuntimeError("PointNetFeaturePropagation: CUDA tensors with 3 <= S <= 2048 centres only (no CPU fallback)")
             # one kernel: centres staged in shared memory, warp-level top-3, weighted row gather (sim_three_nn_interp_fwd)
             interpolated_points = ops.three_nn_interpolate(xyz1, xyz2, points2)
-        else:
-            dists, idx = square_distance(xyz1, xyz2).topk(3, dim=-1, largest=False, sorted=True)
-            dist_recip = 1.0 / (dists + 1e-8)
-            weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
-            # index_points (pointnet2_utils.py:41-57) as ONE gather along the S axis: its backward is a scatter-add into
-            # (B, S, C).  (Gathering from an expanded (B, N, S, C) view makes autograd materialise a gradient of that
-            # shape - 144 GiB at the SAST shape.)
-            Cf = points2.shape[-1]
-            gathered = torch.gather(points2, 1, idx.reshape(B, N * 3)[..., None].expand(-1, -1, Cf)).view(B, N, 3, Cf)
-            interpolated_points = torch.sum(gathered * weight.view(B, N, 3, 1), dim=2)
         if points1 is not None:
             new_points = torch.cat([points1.permute(0, 2, 1), interpolated_points], dim=-1)
         else:
@@ -191,8 +172,8 @@ class get_model(nn.Module):
             keys = ids + hlt_noise.to(ids.device)
             order, _ = ops.argsort_rows(keys.contiguous())
             src = layout.hlt_src_index(order, self.k_top_eigenvectors, bool(self.reverse))      # (B, 2G), -1 = zero
-            x = layout.gather_rows(group_input_tokens, src)
-            sorted_pos = layout.gather_rows(pos, src)
+            x = layout.gather_rows(group_input_tokens, src, fanout=2)
+            sorted_pos = layout.gather_rows(pos, src, fanout=2)
             valid = (src >= 0)[..., None]
             sorted_center = torch.gather(center, 1, src.clamp(min=0).long()[..., None].expand(-1, -1, 3)) * valid
         elif self.method == "SAST":

@@ -14,6 +14,8 @@ from typing import Callable
 
 import torch
 
+from .autograd import invalidate_param_cache
+
 
 class GraphedStep:
     """Capture ``step_fn()`` (forward + backward [+ optimizer.step()]) into one CUDA graph after ``warmup`` eager runs on
@@ -36,4 +38,6 @@ class GraphedStep:
 
     def replay(self):
         self.graph.replay()
+        # the replay updated parameters / BatchNorm statistics in place without bumping their version counters
+        invalidate_param_cache()
         return self.output

@@ -230,9 +230,10 @@ def test_scan_conv_golden(ops, golden, case):
     assert torch.allclose(conv.cpu(), g["conv_out"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", [0, 102, 104, 108, 116, 202, 204, 208, 216, 402, 404, 408,
-                                     1002, 1004, 1008, 1016, 1104, 1108,
-                                     5004, 5008, 5016, 5104, 5108, 5208, 5116, 5216, 6008, 6108, 5508, 8008, 8004])
+SCAN_VARIANTS = [0, 108, 5008]  # shipped dispatch, the tile-synchronous ablation, the warp-specialised kernel by name
+
+
+@pytest.mark.parametrize("variant", SCAN_VARIANTS)
 @pytest.mark.parametrize("B,D,L", [(2, 768, 512), (1, 128, 1), (3, 64, 37), (1, 192, 1024)])
 def test_scan_vs_oracle_fp32(ops, variant, B, D, L):
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 10 * L + D)
@@ -264,7 +265,7 @@ def test_scan_optional_args_and_slices(ops):
     assert rel_err(out.cpu().transpose(1, 2), ref) < 1e-4
 
 
-@pytest.mark.parametrize("variant", [0, 108, 1008, 5008, 5108, 6008, 8008])
+@pytest.mark.parametrize("variant", SCAN_VARIANTS)
 def test_scan_bf16(ops, variant):
     B, D, L = 2, 256, 300
     u, delta, A, Bm, Cm, Dv, z, bias = scan_inputs(B, D, L, 5)
@@ -356,21 +357,6 @@ def test_conv_backward_vs_oracle(ops, dtype, tol, B, D, L):
 
 
 # ----------------------------------------------------------------------------- a-10 fp32 GEMM on tensor cores
-@pytest.mark.parametrize("M,N,K,lda", [(16384, 1536, 384, 384), (16384, 56, 768, 768), (16384, 768, 24, 56),
-                                       (16384, 384, 768, 768), (100, 64, 36, 36), (7, 384, 128, 128)])
-def test_gemm_f32_tc(ops, M, N, K, lda):
-    """tcgen05 3 x bf16 emulated fp32 GEMM vs an fp64 reference: at least as accurate as a true fp32 GEMM."""
-    g = torch.Generator().manual_seed(M + N)
-    xb = torch.randn(M, lda, generator=g)
-    w = torch.randn(N, K, generator=g) * K ** -0.5
-    ref = xb[:, :K].double() @ w.double().t()
-    y = ops.linear_f32_tc(dev(xb)[:, :K], dev(w))
-    assert y.shape == (M, N)
-    assert rel_err(y.cpu().double(), ref) < 2e-6
-    x3 = dev(xb)[:, :K].reshape(1, M, K) if lda == K else dev(xb).view(1, M, lda)[..., :K]
-    assert torch.equal(ops.linear_f32_tc(x3, dev(w)).view(M, N), y)
-
-
 @pytest.mark.parametrize("M,N,K,lda", [(16384, 1536, 384, 384), (16384, 56, 768, 768), (16384, 768, 24, 56),
                                        (16384, 384, 768, 768), (100, 64, 36, 36), (7, 384, 128, 128), (300, 256, 40, 40)])
 def test_gemm_bf16x3(ops, M, N, K, lda):

@@ -123,7 +123,7 @@ def test_part_seg_forward_vs_oracle(lib, method):
 
 @pytest.mark.parametrize("B,k,G,m", [(3, 4, 64, 38), (2, 2, 128, 76), (1, 4, 32, 0), (2, 3, 40, 39)])
 def test_mae_index_maps_and_row_kernels(B, k, G, m):
-    """sim_mae_index_maps against the torch restatement of the layout (layout.mae_index_maps_torch) bit for bit, and
+    """sim_mae_index_maps against the torch restatement of the layout (omae.mae_index_maps_torch) bit for bit, and
     the compact / restore row kernels' backward against autograd through torch indexing."""
     from si_mamba_b200 import layout, ops
     g = torch.Generator().manual_seed(B * 100 + G)
@@ -131,7 +131,7 @@ def test_mae_index_maps_and_row_kernels(B, k, G, m):
     mask = torch.zeros(B, G, dtype=torch.bool)
     for b in range(B):
         mask[b, torch.randperm(G, generator=g)[:m]] = True
-    ref = layout.mae_index_maps_torch(perm, mask)
+    ref = omae.mae_index_maps_torch(perm, mask)
     got = ops.mae_index_maps(perm.cuda(), mask.cuda(), G - m, check=True)
     for key in ("perm_full", "mask_full", "restore_src", "src_vis", "rec_src"):
         assert torch.equal(got[key].cpu(), ref[key]), key

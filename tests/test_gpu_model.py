@@ -56,6 +56,31 @@ def test_block_and_mixer_model_vs_oracle(lib):
     assert torch.equal(res.cpu(), tok + pos)  # first block: residual = hidden (block.py:56)
 
 
+def test_droppath_train_mode_matches_reference_semantics(lib):
+    """Train mode, drop_path > 0 (block.py:59): the first block's input is never dropped, later blocks drop
+    per sample with timm's mask / keep scaling.  The CUDA MixerModel (fixed RNG) against the oracle fed the same masks."""
+    import si_mamba_b200 as sm
+    torch.manual_seed(0)
+    p_drop, n_layer, B = 0.5, 4, 8
+    mm = sm.MixerModel(d_model=128, n_layer=n_layer, drop_path=p_drop).cuda().train()
+    sd = {"blocks." + k: v.detach().cpu() for k, v in mm.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    tok, pos = torch.randn(B, 48, 128, generator=g), torch.randn(B, 48, 128, generator=g)
+    torch.manual_seed(11)
+    out = mm(tok.cuda(), pos.cuda())
+    # replay the RNG stream: one (B,1,1) draw per block with a residual (layers 1..n-1), none for layer 0
+    torch.manual_seed(11)
+    keep = 1.0 - p_drop
+    scales = [(keep + torch.rand((B, 1, 1), dtype=torch.float32, device="cuda")).floor_().view(B).cpu() / keep
+              for _ in range(n_layer - 1)]
+    assert any((s == 0).any() for s in scales) and any((s > 0).any() for s in scales)
+    ref = mamba.mixer_model(sd, "blocks.", tok, pos, n_layer, drop_scale=scales)
+    assert torch.allclose(out.detach().cpu(), ref, rtol=1e-3, atol=1e-4)
+    # and the first block alone: residual == input exactly, for every sample
+    h, res = mm.layers[0](tok.cuda() + pos.cuda(), None)
+    assert torch.equal(res.detach().cpu(), tok + pos)
+
+
 @pytest.mark.parametrize("name,B,N", [("modelnet", 4, 1024), ("scan_hardest", 2, 2048)])
 def test_point_mamba_forward_vs_oracle(lib, name, B, N):
     import si_mamba_b200 as sm

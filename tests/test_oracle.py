@@ -217,7 +217,7 @@ def test_mae_index_maps_torch_consistency():
     B, k, G, C = 2, 4, 64, 8
     perm = torch.stack([torch.stack([torch.randperm(G, generator=g) for _ in range(k)]) for _ in range(B)])
     mask = omae.rand_mask(B, G, 0.6, 3)
-    maps = layout.mae_index_maps_torch(perm, mask)
+    maps = omae.mae_index_maps_torch(perm, mask)
     x = torch.randn(B, G, C, generator=g)
     x_vis = torch.gather(x, 1, maps["src_vis"].long()[..., None].expand(-1, -1, C))
     assert torch.equal(x_vis, omae.compact_visible(x, perm, mask))

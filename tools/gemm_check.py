@@ -30,20 +30,18 @@ for name, N, K, lda in (("in_proj", 1536, 384, 384), ("x_proj", 56, 768, 768), (
     x = xb[:, :K]
     w = torch.randn(N, K, generator=g, device="cuda") * K ** -0.5
     ref = (x.double() @ w.double().t())
-    y = ops.linear_f32_tc(x, w)
     y32 = torch.nn.functional.linear(x, w)
     torch.backends.cuda.matmul.allow_tf32 = True
     ytf = torch.nn.functional.linear(x, w)
     t_tf = timeit(lambda: torch.nn.functional.linear(x, w))
     torch.backends.cuda.matmul.allow_tf32 = False
     err = lambda a: ((a.double() - ref).abs().max() / ref.abs().max()).item()
-    t_tc = timeit(lambda: ops.linear_f32_tc(x, w))
     xs, ws = ops.split3(x), ops.split3(w)
     y3 = ops.linear_split3(xs, ws, K)
     t_x3 = timeit(lambda: ops.linear_split3(xs, ws, K))
     t_sp = timeit(lambda: ops.split3(x, out=xs))
     t_32 = timeit(lambda: torch.nn.functional.linear(x, w))
     fl = 2.0 * M * N * K
-    print(f"{name:9s} N={N:5d} K={K:4d}  err tc {err(y):.2e}  cublas-fp32 {err(y32):.2e}  tf32 {err(ytf):.2e} | "
-          f"us tc {t_tc:7.1f} ({fl / t_tc * 1e-6:6.1f} TF)  fp32 {t_32:7.1f} ({fl / t_32 * 1e-6:6.1f} TF)  tf32 {t_tf:7.1f} | "
+    print(f"{name:9s} N={N:5d} K={K:4d}  err cublas-fp32 {err(y32):.2e}  tf32 {err(ytf):.2e} | "
+          f"us fp32 {t_32:7.1f} ({fl / t_32 * 1e-6:6.1f} TF)  tf32 {t_tf:7.1f} | "
           f"x3 err {err(y3):.2e} us {t_x3:7.1f} ({6 * fl / t_x3 * 1e-6:6.1f} bf16-TF)  split {t_sp:6.1f}", flush=True)
