@@ -120,7 +120,7 @@ int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_
                            int L, int D, int N, int delta_softplus, int dtype, int variant, sim_stream_t stream);
 
 /* Training forward only: `checkpoints` (NULL for inference) receives the SSM state at the start of every
- * 16-step tile, fp32 (batch, ceil(L/16), D, 16); it is the only tensor saved for the backward pass (mamba-ssm
+ * 8th step, fp32 (batch, ceil(L/8), D, 16); it is the only tensor saved for the backward pass (mamba-ssm
  * recomputes from chunk states in the same spirit).  Size in bytes: */
 size_t sim_selective_scan_checkpoint_bytes(int batch, int L, int D);
 

@@ -175,7 +175,7 @@ int sim_causal_conv1d_fwd_split3(const float* x, long ld_x, const float* w, cons
 
 size_t sim_selective_scan_checkpoint_bytes(int batch, int L, int D) {
   if (batch <= 0 || L <= 0 || D <= 0) return 0;
-  return (size_t)batch * ((L + sim::kScanTile - 1) / sim::kScanTile) * D * 16 * sizeof(float);
+  return (size_t)batch * ((L + sim::kScanCkpt - 1) / sim::kScanCkpt) * D * 16 * sizeof(float);
 }
 
 int sim_selective_scan_bwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,

@@ -30,7 +30,7 @@ struct ScanParams {
   long ld_u, ld_delta, ld_z, ld_B, ld_C, ld_out;
   int batch, L, D;
   int softplus;
-  float* ckpt;  // optional (batch, ceil(L/kScanTile), D, 16) fp32: state at the START of every tile (for backward)
+  float* ckpt;  // optional (batch, ceil(L/kScanCkpt), D, 16) fp32: state BEFORE every kScanCkpt-th step (for backward)
   // optional (fp32 activations, warp-specialised kernel): write the result as three bf16 planes instead of `out`
   // (operand format of gemm_split3.cu: out_proj consumes it directly); plane q at out_planes + q * plane elements
   void* out_planes = nullptr;
@@ -40,7 +40,8 @@ struct ScanParams {
   // (3, D, 32) for fp32 activations / (1, D, 32) for bf16, K zero-padded from 24 to 32
   const void* wdt = nullptr;
 };
-constexpr int kScanTile = 16;  // time steps per tile of the scan kernels == checkpoint interval
+constexpr int kScanTile = 16;  // time steps per tile of the forward scan kernels
+constexpr int kScanCkpt = 8;   // checkpoint interval of the training forward == tile of the backward kernel (kScanTile % kScanCkpt == 0)
 int selective_scan_fwd(const ScanParams&, int, int, cudaStream_t);
 
 struct ScanBwdParams {

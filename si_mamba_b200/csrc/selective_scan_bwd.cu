@@ -5,17 +5,22 @@
 //   dt = softplus(delta + bias); h_t = exp(dt_t A) h_{t-1} + dt_t B_t u_t; y_t = <h_t, C_t> + D u_t; out = y silu(z)
 // w.r.t. u, delta, z (token-major, input dtype), B, C (fp32, summed over channels), A, D, bias (fp32).
 //
-// No (B, D, L, N) state tensor is stored: the training forward keeps only the state at the start of every
-// kScanTile-step tile (ScanParams::ckpt, one fp32 tensor the size of an activation), which arrives with the operand
-// tiles (TMA tensor copies + one bulk copy).  Per tile, walking the sequence backwards, the kernel recomputes the states
+// No (B, D, L, N) state tensor is stored: the training forward keeps only the state before every kScanCkpt-th (8th) step
+// (ScanParams::ckpt, one fp32 tensor twice the size of an fp32 activation), which arrives with the operand tiles (TMA
+// tensor copies + one bulk copy).  Per 8-step tile, walking the sequence backwards, the kernel recomputes the states
 // sub-tile by sub-tile into registers and runs the adjoint recurrence dh_{t-1} = a_t dh_t straight from them (see BwdCfg).
-// Thread = one channel x 16 / LPC states (default LPC = 4 lanes per channel): reductions over states are thread-local
-// plus log2(LPC) shuffles; dB / dC (reductions over channels) go through a transposed warp butterfly over the warp's
-// 32 / LPC channels, per-warp shared-memory accumulators and one global fp32 atomic per (t, n) per CTA.
-// History (profiles/r01_scan_bwd_ncu.md): one thread per channel x 16 states, 1742 us at the C2 layer shape -> 878 us.
+// Thread = one channel x 16 / LPC states (default LPC = 2 lanes per channel, 8 states per thread): the partial sums over a
+// thread's states (<h, C>, s1, s2) go to shared memory per lane and are added by the elementwise epilogue; dB / dC
+// (reductions over channels) go through a transposed warp butterfly over the warp's 32 / LPC channels, per-warp
+// shared-memory accumulators and one global fp32 atomic per (t, n) per CTA.
+// History: r01 one thread per channel x 16 states with a state-history buffer 1742 us at the C2 bf16 layer shape -> register
+// sub-tiles, 4 lanes per channel 878 us; r02 (profiles/r02_scan_bwd.md): ncu showed the l1tex data pipe (LDS + SHFL
+// wavefronts) as the busiest unit, so 8 states per thread (half the B / C / (dt, u, dy) loads and butterfly shuffles per
+// state update; needs 8-step tiles to keep 3 CTAs per SM) -> 675 us, state sums through shared memory instead of
+// shuffles -> 629 us (C1 fp32 layer shape: 440 -> 312 us).
 //
-// Roofline class: SM issue (about 45 instructions per pair of state updates); HBM algorithmic bytes are
-// (4 reads + 3 writes) * E * s + checkpoint E * 4 + O(S).
+// Roofline class: l1tex data pipe / issue latency; HBM algorithmic bytes are (4 reads + 3 writes) * E * s + checkpoint
+// 2 E * 4 + O(S).
 
 #include <stdlib.h>
 
@@ -27,7 +32,7 @@ namespace sim {
 namespace {
 
 constexpr int kN = 16;
-constexpr int TT = kScanTile;
+constexpr int TT = kScanCkpt;  // steps per tile == checkpoint interval of the training forward
 
 struct BwdTmaps {
   CUtensorMap u, delta, z, B, C, dout, du, ddelta, dz;
@@ -46,17 +51,44 @@ __device__ __forceinline__ float4 ldsv4<__nv_bfloat16>(const __nv_bfloat16* p) {
                      __uint_as_float(r.y & 0xffff0000u));
 }
 
-// State history without a (step x state) buffer.  The first cut kept every h_t of a 16-step tile in shared memory
-// (32 KB per two warps): 6 warps per SM, ncu: 1.3 warps per scheduler, issue 30 %, 1.29 ms at the C2 layer shape.  Now a
-// tile is walked as four 4-step sub-tiles, back to front: a forward sweep over steps 0..11 leaves the sub-tile start
-// states h_4, h_8, h_12 in shared memory (96 B per thread), then each sub-tile is recomputed into REGISTERS (4 x 8
-// states) and its adjoint steps run straight from them.  2.5 instead of 2 exps per state-step, no history traffic,
-// and the CTA's shared memory drops to the operand tiles, so 3x more warps are resident.
+template <int N>
+__device__ __forceinline__ void lds_vec_n(const float* p, float (&v)[N]) {
+  if constexpr (N == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x, v[1] = t.y;
+  } else {
+    static_assert(N == 4, "lanes per channel");
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void sts4(T* dst, float4 v);
+template <>
+__device__ __forceinline__ void sts4<float>(float* dst, float4 v) {
+  *reinterpret_cast<float4*>(dst) = v;
+}
+template <>
+__device__ __forceinline__ void sts4<__nv_bfloat16>(__nv_bfloat16* dst, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<const unsigned*>(&lo);
+  r.y = *reinterpret_cast<const unsigned*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = r;
+}
+
+// State history without a (step x state) buffer.  The first cut kept every h_t of a tile in shared memory (32 KB per two
+// warps): 6 warps per SM, ncu: 1.3 warps per scheduler, issue 30 %.  Now a tile is walked as TT / SUB sub-tiles of 4 steps,
+// back to front: a forward sweep over the leading sub-tiles leaves their end states in shared memory, then each sub-tile is
+// recomputed into REGISTERS (4 steps x the thread's states, plus the decay factors) and its adjoint steps run straight from
+// them.  With the 8-step tiles: 1.5 exps per state-step, no history traffic.
 constexpr int SUB = 4;  // steps per sub-tile
 
-template <typename T, int CH_, int LPC_, bool SAVE_A_ = false, int NS_ = 2>
+template <typename T, int CH_, int LPC_, bool SAVE_A_ = false, int NS_ = 2, int MINB_ = 1>
 struct BwdCfg {
   static constexpr bool SAVE_A = SAVE_A_;  // keep exp(dt A) of a recomputed sub-tile in registers for its adjoint steps
+  static constexpr int MINB = MINB_;       // resident CTAs per SM the register allocation aims at
   static constexpr int CH = CH_;
   static constexpr int LPC = LPC_;       // lanes per channel
   static constexpr int S = kN / LPC_;    // states per thread
@@ -70,7 +102,7 @@ struct BwdCfg {
   static constexpr int RAW_CK = CH_ * kN * 4;                   // tile-start states of the CTA's channels (fp32)
   static constexpr int RAW_STAGE = 4 * RAW_MAIN + 2 * RAW_BC + RAW_CK;  // u, delta, z, dout, B, C, checkpoint
   static constexpr int OUT = 3 * RAW_MAIN;                      // du, ddelta, dz
-  static constexpr int WORK = 9 * TT * CH_ * 4                  // (dt, u, dy, dt*u) packed, sg, dzc, y, s1, s2
+  static constexpr int WORK = (6 + 3 * LPC_) * TT * CH_ * 4     // (dt, u, dy, dt*u) packed, sg, dzc; y, s1, s2 per lane of a channel
                               + 2 * TT * kN * 4                 // B, C fp32
                               + NW * TT * 2 * kN * 4;           // per-warp dB | dC tile sums
   static constexpr int SCK = (TT / SUB - 1) * (S / 4) * NT * 16;  // sub-tile start states, float4 planes
@@ -80,7 +112,7 @@ struct BwdCfg {
 };
 
 template <typename Cfg, typename T>
-__global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __grid_constant__ BwdTmaps tm,
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(const __grid_constant__ BwdTmaps tm,
                                                                      const ScanBwdParams p) {
   constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW, LPC = Cfg::LPC, SQ = Cfg::S / 4;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -92,9 +124,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   float* __restrict__ w_sg = reinterpret_cast<float*>(w4 + TT * CH);
   float* __restrict__ w_dzc = w_sg + TT * CH;
   float* __restrict__ w_y = w_dzc + TT * CH;
-  float* __restrict__ w_s1 = w_y + TT * CH;
-  float* __restrict__ w_s2 = w_s1 + TT * CH;
-  float* __restrict__ w_B = w_s2 + TT * CH;
+  float* __restrict__ w_s1 = w_y + LPC * TT * CH;   // y, s1, s2: [t][channel][lane of the channel] partial sums over the
+  float* __restrict__ w_s2 = w_s1 + LPC * TT * CH;  // lane's states, added up by the epilogue (no shuffle in the recurrence)
+  float* __restrict__ w_B = w_s2 + LPC * TT * CH;
   float* __restrict__ w_C = w_B + TT * kN;
   float* __restrict__ a_dBC = w_C + TT * kN;                                  // [warp][t][dB(16) | dC(16)]
   float4* __restrict__ sck = reinterpret_cast<float4*>(a_dBC + NW * TT * 2 * kN);  // [sub-1][half][thread]
@@ -141,7 +173,6 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     dA[n] = 0.f;
     dh[n] = 0.f;
   }
-  const float Dc = p.Dv ? p.Dv[c0 + c] : 0.f;
   const int ce = tid % CH;  // channel of this thread's elements in the elementwise passes (NT % CH == 0)
   const float De = p.Dv ? p.Dv[c0 + ce] : 0.f;
   const float bias_e = p.dbias ? p.dbias[c0 + ce] : 0.f;
@@ -149,11 +180,6 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   // lane (sub, channel-in-warp cw) ends the dB / dC butterfly with the total of value v = cw (the warp has 32 / LPC
   // channels and every thread 2 S = 32 / LPC values): v < S -> dB of state sub*S + v, else dC of state sub*S + v - S
   const int vfin = lane / LPC;
-  auto sum_subs = [&](float v) {  // total over the LPC lanes of a channel
-#pragma unroll
-    for (int o = 1; o < LPC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
   float* my_acc = a_dBC + warp * TT * 2 * kN + (vfin < S ? sub * S + vfin : kN + sub * S + vfin - S);
 
   // one forward step of this thread's 8 states: hn = a * hp + dt*u*B; returns the thread's share of <h, C>
@@ -200,7 +226,13 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
 
     // ---- pre-pass (elementwise over the tile): activations and their derivatives.  Rows past the end of the sequence
     // were zero-filled by the TMA unit: their dout is 0, so every gradient they produce is 0 and no step needs a guard.
-    for (int e = tid; e < TT * CH; e += NT) {
+    // The softplus / sigmoid chains are serial MUFU chains (ex2 -> lg2, ex2 -> rcp): with one element per loop iteration
+    // the pass was latency-bound (ncu: 18 % of the kernel's samples).  The trip count is a compile-time constant, so the
+    // iterations are unrolled and their chains interleave; element e = tid + i NT keeps the accesses conflict-free.
+    static_assert((TT * CH) % NT == 0, "whole elementwise passes");
+#pragma unroll
+    for (int i = 0; i < TT * CH / NT; ++i) {
+      const int e = tid + i * NT;
       const float x = to_f32<T>(sd[e]) + bias_e;
       const float dtv = p.softplus ? softplus_f(x) : x;
       w_sg[e] = p.softplus ? ((x > 20.f) ? 1.f : sigmoid_f(x)) : 1.f;  // d softplus / dx
@@ -267,8 +299,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
         const int r = rb + i;
         float* ao = Cfg::SAVE_A ? aq[Cfg::SAVE_A ? i : 0] : nullptr;
         float y = (i == 0) ? fwd_step(r, hs, hq[0], ao) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i], ao);
-        y = sum_subs(y);
-        if (sub == 0) w_y[r * CH + c] = y;  // <h, C>; D u is added in the epilogue
+        w_y[(r * CH + c) * LPC + sub] = y;  // partial <h, C>; D u is added in the epilogue
       }
 #pragma unroll
       for (int i = SUB - 1; i >= 0; --i) {
@@ -300,17 +331,17 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
             const float2 rb2 = __fmul2_rn(dhn, dtu2);
             red[S + n] = rc.x, red[S + n + 1] = rc.y;
             red[n] = rb2.x, red[n + 1] = rb2.y;
-            const float2 tmp = __fmul2_rn(__fmul2_rn(dhn, hprev), a);  // dL/da * a
+            const float2 dhp = __fmul2_rn(a, dhn);                    // dL/dh_{t-1} through the decay
+            const float2 tmp = __fmul2_rn(dhp, hprev);                // dL/da * a
             s1 = __ffma2_rn(dhn, make_float2(Bv[j], Bv[j + 1]), s1);
             s2 = __ffma2_rn(tmp, make_float2(A[n], A[n + 1]), s2);
             const float2 dAn = __ffma2_rn(tmp, dt2, make_float2(dA[n], dA[n + 1]));
             dA[n] = dAn.x, dA[n + 1] = dAn.y;
-            const float2 dhp = __fmul2_rn(a, dhn);
             dh[n] = dhp.x, dh[n + 1] = dhp.y;
           }
         }
-        const float s1s = sum_subs(s1.x + s1.y), s2s = sum_subs(s2.x + s2.y);
-        if (sub == 0) w_s1[r * CH + c] = s1s, w_s2[r * CH + c] = s2s;
+        w_s1[(r * CH + c) * LPC + sub] = s1.x + s1.y;
+        w_s2[(r * CH + c) * LPC + sub] = s2.x + s2.y;
         // reduce the 2 S partials over the warp's 32 / LPC channels: transposed butterfly over the channel lane bits
 #pragma unroll
         for (int ov = S, ol = 16; ov >= 1; ov >>= 1, ol >>= 1) {
@@ -328,15 +359,23 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
     __syncthreads();
 
     // ---- epilogue (elementwise, every lane busy): ddelta = (u s1 + s2) softplus', du = dy D + dt s1, dz = dzc (y + D u)
-    for (int e = tid; e < TT * CH; e += NT) {
+#pragma unroll
+    for (int i = 0; i < TT * CH / NT; ++i) {
+      const int e = tid + i * NT;
       const float4 w = w4[e];
-      const float s1v = w_s1[e];
-      const float dd = fmaf(w.y, s1v, w_s2[e]) * w_sg[e];
+      float lp[3][LPC];
+      lds_vec_n<LPC>(w_y + e * LPC, lp[0]);
+      lds_vec_n<LPC>(w_s1 + e * LPC, lp[1]);
+      lds_vec_n<LPC>(w_s2 + e * LPC, lp[2]);
+      float yv = lp[0][0], s1v = lp[1][0], s2v = lp[2][0];
+#pragma unroll
+      for (int l = 1; l < LPC; ++l) yv += lp[0][l], s1v += lp[1][l], s2v += lp[2][l];
+      const float dd = fmaf(w.y, s1v, s2v) * w_sg[e];
       dbias += dd;
       dD = fmaf(w.z, w.y, dD);
       o_du[e] = from_f32<T>(fmaf(w.z, De, w.x * s1v));
       o_dd[e] = from_f32<T>(dd);
-      o_dz[e] = from_f32<T>(w_dzc[e] * fmaf(De, w.y, w_y[e]));
+      o_dz[e] = from_f32<T>(w_dzc[e] * fmaf(De, w.y, yv));
     }
     fence_proxy_async();
     __syncthreads();
@@ -363,9 +402,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_bwd_kernel(const __gri
   if (p.ddbias) atomicAdd(p.ddbias + c0 + ce, dbias);
 }
 
-template <typename T, int CH, int LPC, bool SAVE_A = false, int NS = 2>
+template <typename T, int CH, int LPC, bool SAVE_A = false, int NS = 2, int MINB = 1>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = BwdCfg<T, CH, LPC, SAVE_A, NS>;
+  using Cfg = BwdCfg<T, CH, LPC, SAVE_A, NS, MINB>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
@@ -406,17 +445,17 @@ int selective_scan_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
     SIM_REQUIRE(aligned16(ptrs[i]) && (lds[i] * es) % 16 == 0, SIM_ERR_ALIGN,
                 "selective_scan_bwd: tensor %d needs a 16-byte aligned base and row stride (TMA tensor maps)", i);
   }
-  static const int lpc = [] { const char* e = getenv("SIM_SCAN_BWD_LPC"); return e ? atoi(e) : 41; }();  // bench override (4: recompute exp(dt A) in the adjoint, 2: two lanes per channel)
-  if (lpc == 411)  // ... and a single raw stage
-    return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true, 1>(p, dtype, stream);
-  if (lpc == 41)  // default: 4 lanes per channel, exp(dt A) kept from the recompute (one exp less per state-step, 17 registers
-                  // more); fp32 with one raw stage = 4 CTAs per SM (440 -> 431 us), bf16 keeps two (one: 878 -> 892 us)
-    return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true>(p, dtype, stream);
-  if (lpc == 412)
-    return dtype == 0 ? launch_bwd<float, 32, 4, true>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true>(p, dtype, stream);
-  if (lpc == 4)
-    return dtype == 0 ? launch_bwd<float, 32, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4>(p, dtype, stream);
-  return dtype == 0 ? launch_bwd<float, 32, 2>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 2>(p, dtype, stream);
+  // Configurations (SIM_SCAN_BWD_CFG overrides the default for tools/kernel_bench.py; r02 numbers at the C1 fp32 / C2 bf16
+  // layer shapes, profiles/r02_scan_bwd.md):
+  //   22 (default): 64-channel CTAs, 2 lanes per channel (8 states per thread), 128 threads, 3 CTAs per SM: 312 / 629 us
+  //   42: 32-channel CTAs, 4 lanes per channel (the r01 mapping, twice the operand loads and shuffles per state update): 408 / 792 us
+  //   2200: as 22 with exp(dt A) recomputed in the adjoint (120 registers, 4 CTAs per SM): 332 / 666 us
+  static const int cfg = [] { const char* e = getenv("SIM_SCAN_BWD_CFG"); return e ? atoi(e) : 22; }();
+  if (cfg == 42 || p.D % 64 != 0)
+    return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true, 2>(p, dtype, stream);
+  if (cfg == 2200)
+    return dtype == 0 ? launch_bwd<float, 64, 2, false, 1, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 64, 2, false, 1, 4>(p, dtype, stream);
+  return dtype == 0 ? launch_bwd<float, 64, 2, true, 1, 3>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 64, 2, true, 1, 3>(p, dtype, stream);
 }
 
 }  // namespace sim

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
   const int sub = tid % LPC;          // which S-state slice
   const int ch0 = (tid / LPC) * CPT;  // first of this thread's CPT channels (within the CTA)
   const int ntiles = (p.L + TT - 1) / TT;
+  const int nck = (p.L + kScanCkpt - 1) / kScanCkpt;
   const bool has_z = p.z != nullptr;
 
   if (tid == 0) {
@@ -141,15 +142,16 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     const T* sB = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN);
     const T* sC = reinterpret_cast<const T*>(st + 3 * Cfg::RAW_MAIN + Cfg::RAW_BC);
 
-    if (p.ckpt) {  // training forward: state at the start of this tile, layout (batch, tile, D, 16)
+    // training forward: state before every kScanCkpt-th step, layout (batch, ceil(L / kScanCkpt), D, 16)
+    auto save_ckpt = [&](int idx) {
 #pragma unroll
       for (int cp = 0; cp < CPT; ++cp) {
-        float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * ntiles + tile) * p.D + c0 + ch0 + cp) * kNState +
-                                                sub * S);
+        float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * nck + idx) * p.D + c0 + ch0 + cp) * kNState + sub * S);
 #pragma unroll
         for (int j = 0; j < S / 2; ++j) dst[j] = h[cp][j];
       }
-    }
+    };
+    if (p.ckpt) save_ckpt(tile * (TT / kScanCkpt));
     mbar_wait(&full[s], (tile / NS) & 1);
 
     // ---- pre-pass: softplus(delta + bias), silu(z), widen to fp32.  Always the whole tile: rows past L were
@@ -218,6 +220,9 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
     float part[LPC][CPT];
 #pragma unroll
     for (int t = 0; t < TT; ++t) {
+      if (t > 0 && t % kScanCkpt == 0) {
+        if (p.ckpt && tile * (TT / kScanCkpt) + t / kScanCkpt < nck) save_ckpt(tile * (TT / kScanCkpt) + t / kScanCkpt);
+      }
       if (t + PD < TT) stage_a(t + PD);
       if (t + 1 < TT && !(Cfg::DBG & 8)) {
         lds_vec<S>(w_B + (t + 1) * kNState + sub * S, Bn);

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
   const int b = blockIdx.x / nchunk;
   const int c0 = (blockIdx.x % nchunk) * CH;
   const int ntiles = (p.L + TT - 1) / TT;
+  const int nck = (p.L + kScanCkpt - 1) / kScanCkpt;
   const bool has_z = p.z != nullptr;
 
   if (tid == NR) {
@@ -416,11 +417,13 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
     }
     for (int k = 0; k < ntiles; ++k) {
       const int par = k & 1;
-      if (p.ckpt) {  // training forward: state at the start of this tile, layout (batch, tile, D, 16)
-        float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * ntiles + k) * p.D + c0 + ch) * kNState + sub * S);
+      // training forward: state before every kScanCkpt-th step, layout (batch, ceil(L / kScanCkpt), D, 16)
+      auto save_ckpt = [&](int idx) {
+        float2* dst = reinterpret_cast<float2*>(p.ckpt + (((long)b * nck + idx) * p.D + c0 + ch) * kNState + sub * S);
 #pragma unroll
         for (int j = 0; j < S / 2; ++j) dst[j] = h[j];
-      }
+      };
+      if (p.ckpt) save_ckpt(k * (TT / kScanCkpt));
       const unsigned char* wk = work + par * Cfg::WORK;
       const float2* w_dt = reinterpret_cast<const float2*>(wk) + ch;
       const float* w_B = reinterpret_cast<const float*>(wk + Cfg::WORK_DT) + sub * S;
@@ -430,6 +433,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
       float part[LPC];
 #pragma unroll
       for (int t = 0; t < TT; ++t) {
+        if (t > 0 && t % kScanCkpt == 0) {
+          if (p.ckpt && k * (TT / kScanCkpt) + t / kScanCkpt < nck) save_ckpt(k * (TT / kScanCkpt) + t / kScanCkpt);
+        }
         const float2 d = w_dt[t * CH];  // (dt, dt * u)
         float Bv[S], Cv[S];
         lds_vec<S>(w_B + t * kNState, Bv);

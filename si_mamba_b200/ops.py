@@ -785,7 +785,7 @@ def selective_scan_fused_dt_tm(u, x_dbl, dt_rank: int, wdt_planes, A, D=None, z=
 
 
 def scan_checkpoint_shape(B: int, L: int, D: int):
-    return (B, (L + 15) // 16, D, 16)
+    return (B, (L + 7) // 8, D, 16)  # kScanCkpt = 8 steps between saved states
 
 
 def selective_scan_bwd_tm(u, delta, A, Bm, Cm, D, z, delta_bias, dout, checkpoints, delta_softplus=True):
