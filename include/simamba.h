@@ -77,6 +77,22 @@ int sim_spectral_eig(const float* center, int B, int G, int k_nn, float alpha, i
                      float* eigvecs, int32_t* perm, int32_t* inv_perm, float* adjacency, void* workspace,
                      size_t workspace_bytes, sim_stream_t stream);
 
+/* sim_spectral_eig with the remaining reference entry points folded in:
+ *   adjacency_in (B,G,G) f32 or NULL: skip the graph construction and decompose the Laplacian of a caller-supplied
+ *     adjacency - PointMamba.calc_top_k_eigenvalues_eigenvectors(adj_matrices, k, smallest) and its _symmetric twin
+ *     (models/point_mamba.py:717-814); center may then be NULL;
+ *   sigma (device scalar) or NULL: the `alpha == 0` weights exp(-d^2 / (2 sigma^2)) of create_graph_from_centers
+ *     (:628, :647), sigma = mean of ALL pairwise centre distances of the batch (sim_pairwise_dist_mean);
+ *   first: index (in the requested order, after the dropped pair of SIM_LAP_SYMMETRIC) of the first of the k wanted
+ *     eigenpairs, so ceil(G / 8) calls return the full decomposition the reference's 4-tuple carries. */
+int sim_spectral_eig_ex(const float* center, const float* adjacency_in, const float* sigma, int B, int G, int k_nn,
+                        float alpha, int flags, int first, int k, float* eigvals, float* eigvecs, int32_t* perm,
+                        int32_t* inv_perm, float* adjacency, void* workspace, size_t workspace_bytes,
+                        sim_stream_t stream);
+/* sigma = torch.mean(dist_matrix) of create_graph_from_centers (:626-628): centres (B,G,3) -> *sigma (device f32);
+ * partial (B) f64 scratch.  Deterministic (per-cloud fp64 sums added in index order). */
+int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream);
+
 /* a-5  stable ascending argsort of fp32 keys along rows (the torch.sort inside
  * sort_points_by_fiedler, models/point_mamba.py:820).  keys (rows, n) with row stride ld and element
  * stride es (so a column of (B,G,k) eigenvectors can be sorted in place): perm (rows, n) i32. */

@@ -33,6 +33,8 @@ SIGNATURES = {
     "sim_knn_group": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sim_spectral_eig_workspace_bytes": (_sz, [_i, _i, _i]),
     "sim_spectral_eig": (_i, [_p, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sim_spectral_eig_ex": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sim_pairwise_dist_mean": (_i, [_p, _i, _i, _p, _p, _p]),
     "sim_argsort_rows": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
     "sim_order_gather_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sim_order_gather_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -71,6 +71,36 @@ int sim_spectral_eig(const float* center, int B, int G, int k_nn, float alpha, i
   return sim::spectral_eig(P, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int sim_spectral_eig_ex(const float* center, const float* adjacency_in, const float* sigma, int B, int G, int k_nn,
+                        float alpha, int flags, int first, int k, float* eigvals, float* eigvecs, int32_t* perm,
+                        int32_t* inv_perm, float* adjacency, void* workspace, size_t workspace_bytes, sim_stream_t stream) {
+  sim::SpectralParams P;
+  memset(&P, 0, sizeof(P));
+  P.center = center;
+  P.adj_in = adjacency_in;
+  P.sigma = sigma;
+  P.first = first;
+  P.eigvals = eigvals;
+  P.eigvecs = eigvecs;
+  P.perm = perm;
+  P.inv_perm = inv_perm;
+  P.adjacency = adjacency;
+  P.B = B, P.G = G, P.k_nn = k_nn, P.k = k;
+  P.alpha = alpha;
+  P.symmetric = (flags & SIM_GRAPH_SYMMETRIC) != 0;
+  P.self_loop = (flags & SIM_GRAPH_SELF_LOOP) != 0;
+  P.binary = (flags & SIM_GRAPH_BINARY) != 0;
+  P.smallest = (flags & SIM_EIG_SMALLEST) != 0;
+  P.matrix_sym = (flags & SIM_LAP_SYMMETRIC) != 0;
+  P.eps_clamp = (flags & SIM_LAP_EPS_CLAMP) != 0;
+  P.sign_rule = (flags & SIM_EIG_CANONICAL_SIGN) != 0;
+  return sim::spectral_eig(P, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream) {
+  return sim::pairwise_dist_mean(center, B, G, partial, sigma, static_cast<cudaStream_t>(stream));
+}
+
 int sim_argsort_rows(const float* keys, long ld, long es, int rows, int n, int32_t* perm, int32_t* inv_perm,
                      sim_stream_t stream) {
   return sim::argsort_rows(keys, ld, es, rows, n, perm, inv_perm, static_cast<cudaStream_t>(stream));

@@ -88,7 +88,15 @@ struct SpectralParams {
   int smallest;
   int sign_rule;
   int lu_alias;
+  // extensions (sim_spectral_eig_ex): sigma != NULL selects the alpha == 0 weights exp(-d^2 / (2 sigma^2)) of
+  // create_graph_from_centers (:647), *sigma = mean pairwise distance over the whole batch (device scalar);
+  // adj_in != NULL replaces the graph construction by a caller-supplied (B, G, G) adjacency
+  // (calc_top_k_eigenvalues_eigenvectors(adj, k, smallest), :717); first = index of the first wanted eigenpair.
+  const float* sigma;
+  const float* adj_in;
+  int first;
 };
+int pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, cudaStream_t stream);
 size_t spectral_workspace_bytes(int, int, int);
 int spectral_eig(SpectralParams, void*, size_t, cudaStream_t);
 

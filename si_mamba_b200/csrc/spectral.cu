@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
   float* s_deg = reinterpret_cast<float*>(ptr);  ptr += GP * sizeof(float);
   unsigned char* s_piv = ptr;                    ptr += (size_t)k * GP;
 
+  if (P.adj_in) {
+    // caller-supplied adjacency (calc_top_k_eigenvalues_eigenvectors(adj_matrices, k, smallest), :717)
+    const float* ai = P.adj_in + (size_t)b * G * G;
+    for (int e = tid; e < G * G; e += NT) Adj[e] = ai[e];
+    __syncthreads();
+  } else {
   // ================================================================ 1. distances
   const float* cen = P.center + (size_t)b * G * 3;
   for (int i = tid; i < G * 3; i += NT) s_c[i] = cen[i];
@@ -137,6 +143,12 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
 
   // ================================================================ 2. kNN selection + adjacency scatter
   const int kk = P.k_nn + 1;
+  // alpha == 0 branch of create_graph_from_centers (:628, :647): exp(-d^2 / (2 sigma^2)), sigma = batch-wide mean distance
+  float two_sigma2 = 1.f;
+  if (P.sigma) {
+    const float sg = *P.sigma;
+    two_sigma2 = __fmul_rn(2.f, __fmul_rn(sg, sg));
+  }
   for (int i = warp; i < G; i += NW) {
     const float* di = dist + (size_t)i * G;
     for (int j = lane; j < G; j += 32) {
@@ -147,13 +159,16 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
         rank += (dq < dij) || (dq == dij && q < j);
       }
       if (rank < kk && (P.self_loop || rank >= 1)) {
-        const float wgt = P.binary ? 1.f : expf(__fmul_rn(-P.alpha, __fmul_rn(dij, dij)));
+        const float wgt = P.binary ? 1.f
+                          : P.sigma ? expf(__fdiv_rn(-__fmul_rn(dij, dij), two_sigma2))
+                                    : expf(__fmul_rn(-P.alpha, __fmul_rn(dij, dij)));
         Adj[(size_t)i * G + j] = wgt;
         if (P.symmetric) Adj[(size_t)j * G + i] = wgt;
       }
     }
   }
   __syncthreads();
+  }  // !adj_in
   if (P.adjacency) {
     float* ao = P.adjacency + (size_t)b * G * G;
     for (int e = tid; e < G * G; e += NT) ao[e] = Adj[e];
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
     const int s = tid / PTS, j = tid % PTS;
     const bool active = s < k;
     // 0-based ascending index this group is after
-    const int want = active ? (P.smallest ? (off + s) : (G - 1 - off - s)) : 0;
+    const int want = active ? (P.smallest ? (off + P.first + s) : (G - 1 - off - P.first - s)) : 0;
     for (int round = 0; round < 12; ++round) {
       double x = 0.0;
       int cnt = 0;
@@ -511,10 +526,11 @@ size_t spectral_workspace_bytes(int B, int G, int k) {
 
 int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   SIM_REQUIRE(P.B > 0 && P.G >= 4 && P.G <= 512, SIM_ERR_INVALID, "spectral_eig: G must be in [4, 512] (got %d)", P.G);
-  SIM_REQUIRE(P.k >= 1 && P.k <= 8 && P.k + (P.matrix_sym ? 1 : 0) <= P.G, SIM_ERR_INVALID,
-              "spectral_eig: k must be in [1, 8] (got %d)", P.k);
-  SIM_REQUIRE(P.k_nn >= 1 && P.k_nn + 1 <= P.G, SIM_ERR_INVALID, "spectral_eig: k_nn+1 must be <= G");
-  SIM_REQUIRE(P.center && P.eigvals && P.eigvecs && P.perm, SIM_ERR_INVALID, "spectral_eig: null tensor");
+  // first may be -1 with SIM_LAP_SYMMETRIC: the pair that variant drops is then returned too (full decomposition)
+  SIM_REQUIRE(P.k >= 1 && P.k <= 8 && P.first + (P.matrix_sym ? 1 : 0) >= 0 && P.first + P.k + (P.matrix_sym ? 1 : 0) <= P.G,
+              SIM_ERR_INVALID, "spectral_eig: k must be in [1, 8] and first + k <= G (got k=%d first=%d)", P.k, P.first);
+  SIM_REQUIRE(P.adj_in || (P.k_nn >= 1 && P.k_nn + 1 <= P.G), SIM_ERR_INVALID, "spectral_eig: k_nn+1 must be <= G");
+  SIM_REQUIRE((P.center || P.adj_in) && P.eigvals && P.eigvecs && P.perm, SIM_ERR_INVALID, "spectral_eig: null tensor");
   const int NT = P.G <= 64 ? 256 : 512;
   const bool in_smem = spectral_smem_bytes(P.G, P.k, NT, true) <= 227 * 1024;
   const size_t smem = spectral_smem_bytes(P.G, P.k, NT, in_smem);
@@ -542,6 +558,40 @@ int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cuda
   }
 #undef SIM_SPEC_LAUNCH
   return check_launch("spectral_eig");
+}
+
+// sigma = mean over the WHOLE (B, G, G) tensor of pairwise centre distances (torch.mean(dist_matrix), :628): one CTA per
+// cloud leaves its fp64 sum in `partial`, the last kernel adds the B partials in index order (deterministic).
+__global__ void __launch_bounds__(256) dist_sum_kernel(const float* __restrict__ center, int G, double* __restrict__ partial) {
+  extern __shared__ float sc[];
+  __shared__ double red[8];
+  const float* cen = center + (size_t)blockIdx.x * G * 3;
+  for (int i = threadIdx.x; i < G * 3; i += 256) sc[i] = cen[i];
+  __syncthreads();
+  double s = 0.0;
+  for (int e = threadIdx.x; e < G * G; e += 256) s += (double)__fsqrt_rn(sqdist3s(sc + 3 * (e / G), sc + 3 * (e % G)));
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void dist_mean_kernel(const double* __restrict__ partial, int B, double count, float* __restrict__ sigma) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < B; ++b) t += partial[b];
+    *sigma = (float)(t / count);
+  }
+}
+
+int pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, cudaStream_t stream) {
+  SIM_REQUIRE(center && partial && sigma && B > 0 && G >= 1 && G <= 4096, SIM_ERR_INVALID, "pairwise_dist_mean: bad arguments");
+  dist_sum_kernel<<<B, 256, (size_t)G * 3 * sizeof(float), stream>>>(center, G, partial);
+  dist_mean_kernel<<<1, 32, 0, stream>>>(partial, B, (double)B * G * G, sigma);
+  return check_launch("pairwise_dist_mean");
 }
 
 }  // namespace sim

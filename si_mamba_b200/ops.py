@@ -126,14 +126,34 @@ def spectral_flags(symmetric, self_loop, binary, smallest, matrix="laplacian", e
     return f
 
 
-def spectral_eig(center: torch.Tensor, k_nn: int, alpha: float, symmetric: bool, self_loop: bool, binary: bool,
-                 k: int, smallest: bool, matrix: str = "laplacian", eps_mode: str = "add1e-6",
-                 canonical_sign: bool = True, want_adjacency: bool = False):
-    """centres (B,G,3) -> dict(vals (B,k), vecs (B,G,k), perm (B,k,G) i32, inv_perm, [adjacency (B,G,G)])."""
+def pairwise_dist_mean(center: torch.Tensor) -> torch.Tensor:
+    """torch.mean of all pairwise centre distances of the batch (create_graph_from_centers, point_mamba.py:626-628):
+    centres (B,G,3) -> device scalar (1,) fp32."""
     _cuda(center)
     center = center.detach().float().contiguous()
     B, G, _ = center.shape
-    dev = center.device
+    partial = torch.empty(B, dtype=torch.float64, device=center.device)
+    sigma = torch.empty(1, dtype=torch.float32, device=center.device)
+    _lib.call("sim_pairwise_dist_mean", _p(center), B, G, _p(partial), _p(sigma), _stream())
+    return sigma
+
+
+def spectral_eig(center: Optional[torch.Tensor], k_nn: int, alpha: float, symmetric: bool, self_loop: bool, binary: bool,
+                 k: int, smallest: bool, matrix: str = "laplacian", eps_mode: str = "add1e-6",
+                 canonical_sign: bool = True, want_adjacency: bool = False, sigma_mode: bool = False,
+                 adjacency_in: Optional[torch.Tensor] = None, first: int = 0):
+    """centres (B,G,3) -> dict(vals (B,k), vecs (B,G,k), perm (B,k,G) i32, inv_perm, [adjacency (B,G,G)]).
+    ``sigma_mode``: the alpha == 0 weights of create_graph_from_centers (exp(-d^2 / (2 sigma^2)), sigma = batch-wide mean
+    distance); ``adjacency_in`` (B,G,G): decompose the Laplacian of this adjacency instead of building the graph;
+    ``first``: index of the first wanted eigenpair (k <= 8 per call)."""
+    src = adjacency_in if adjacency_in is not None else center
+    _cuda(center, adjacency_in)
+    if center is not None:
+        center = center.detach().float().contiguous()
+    if adjacency_in is not None:
+        adjacency_in = adjacency_in.detach().float().contiguous()
+    B, G = src.shape[0], src.shape[1]
+    dev = src.device
     vals = torch.empty(B, k, dtype=torch.float32, device=dev)
     vecs = torch.empty(B, G, k, dtype=torch.float32, device=dev)
     perm = torch.empty(B, k, G, dtype=torch.int32, device=dev)
@@ -142,12 +162,39 @@ def spectral_eig(center: torch.Tensor, k_nn: int, alpha: float, symmetric: bool,
     ws_bytes = _lib.load().sim_spectral_eig_workspace_bytes(B, G, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     flags = spectral_flags(symmetric, self_loop, binary, smallest, matrix, eps_mode, canonical_sign)
-    _lib.call("sim_spectral_eig", _p(center), B, G, int(k_nn), float(alpha), flags, int(k), _p(vals), _p(vecs),
-              _p(perm), _p(inv), _p(adj), _p(ws), ws_bytes, _stream())
+    if not sigma_mode and adjacency_in is None and first == 0:
+        _lib.call("sim_spectral_eig", _p(center), B, G, int(k_nn), float(alpha), flags, int(k), _p(vals), _p(vecs),
+                  _p(perm), _p(inv), _p(adj), _p(ws), ws_bytes, _stream())
+    else:
+        sigma = pairwise_dist_mean(center) if (sigma_mode and adjacency_in is None) else None
+        _lib.call("sim_spectral_eig_ex", _p(center), _p(adjacency_in), _p(sigma), B, G, int(k_nn), float(alpha), flags,
+                  int(first), int(k), _p(vals), _p(vecs), _p(perm), _p(inv), _p(adj), _p(ws), ws_bytes, _stream())
     out = dict(vals=vals, vecs=vecs, perm=perm, inv_perm=inv)
     if want_adjacency:
         out["adjacency"] = adj
     return out
+
+
+def eig_from_adjacency(adj: torch.Tensor, k: int, smallest: bool, matrix: str = "laplacian", eps_mode: str = "add1e-6",
+                       full: bool = True, canonical_sign: bool = False):
+    """PointMamba.calc_top_k_eigenvalues_eigenvectors(adj_matrices, k, smallest) -> the reference's 4-tuple
+    (top_k_eigenvalues (B,k), top_k_eigenvectors (B,G,k), eigenvalues (B,G) ascending, eigenvectors (B,G,G)); the full
+    decomposition (only the wavelet code of the reference reads it) costs ceil(G / 8) extra calls - ``full=False`` returns
+    None for the last two.  Signs are LAPACK's in the reference, i.e. unspecified: here the un-normalised kernel output
+    unless ``canonical_sign``."""
+    G = adj.shape[1]
+    sym = matrix != "laplacian"
+    top = spectral_eig(None, 1, 0.0, False, False, True, k, smallest, matrix, eps_mode, canonical_sign, adjacency_in=adj)
+    if not full:
+        return top["vals"], top["vecs"], None, None
+    vals, vecs = [], []
+    for first in range(0, G, 8):
+        kk = min(8, G - first)
+        o = spectral_eig(None, 1, 0.0, False, False, True, kk, True, matrix, eps_mode, canonical_sign, adjacency_in=adj,
+                         first=first - (1 if sym else 0))
+        vals.append(o["vals"])
+        vecs.append(o["vecs"])
+    return top["vals"], top["vecs"], torch.cat(vals, dim=1), torch.cat(vecs, dim=2)
 
 
 def argsort_rows(keys: torch.Tensor):

@@ -377,7 +377,20 @@ class PointMamba(nn.Module):
         return ops.spectral_eig(points, k, alpha, symmetric, self_loop, binary, 1, True,
                                 want_adjacency=True)["adjacency"]
 
-    create_graph_from_centers = create_graph_from_feature_space_gpu_weighted_adjacency
+    def create_graph_from_centers(self, points, k=5, alpha=1, symmetric=False, self_loop=False, binary=False):
+        """point_mamba.py:620-661 -> adjacency (B,G,G).  As in the reference the Gaussian width switches on the MODEL's
+        alpha: ``self.alpha == 0`` selects exp(-d^2 / (2 sigma^2)) with sigma the mean pairwise distance of the batch."""
+        return ops.spectral_eig(points, k, alpha, symmetric, self_loop, binary, 1, True, want_adjacency=True,
+                                sigma_mode=(self.alpha == 0))["adjacency"]
+
+    def calc_top_k_eigenvalues_eigenvectors(self, adj_matrices, k, smallest):
+        """point_mamba.py:717-761: L = I - D^-1 A (deg + 1e-6) of the symmetrised adjacency, eigh(UPLO='L') ->
+        (top_k_eigenvalues (B,k), top_k_eigenvectors (B,G,k), eigenvalues (B,G), eigenvectors (B,G,G))."""
+        return ops.eig_from_adjacency(adj_matrices, k, smallest, "laplacian", "add1e-6")
+
+    def calc_top_k_eigenvalues_eigenvectors_symmetric(self, adj_matrices, k, smallest):
+        """point_mamba.py:764-814: I - D^-1/2 A D^-1/2; k + 1 pairs are taken and the first one is dropped."""
+        return ops.eig_from_adjacency(adj_matrices, k, smallest, "sym", "add1e-6")
 
     def sort_points_by_fiedler(self, points, fiedler_vector):
         """point_mamba.py:817-826: rows of ``points`` (B,G,C) in ascending order of ``fiedler_vector`` (B,G)."""

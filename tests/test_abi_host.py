@@ -42,7 +42,7 @@ def test_invalid_arguments_fail_without_gpu(lib):
     rc = lib.sim_selective_scan_fwd(None, 0, None, 0, None, None, 0, None, 0, None, None, 0, None, None, 0, None,
                                     1, 8, 64, 8, 1, 0, 0, None)
     assert rc == -1 and b"d_state" in lib.sim_last_error_string()
-    assert lib.sim_selective_scan_checkpoint_bytes(32, 512, 768) == 32 * 32 * 768 * 16 * 4
+    assert lib.sim_selective_scan_checkpoint_bytes(32, 512, 768) == 32 * 64 * 768 * 16 * 4  # a state every 8 steps
     rc = lib.sim_spectral_eig(None, 1, 2, 1, 1.0, 0, 1, None, None, None, None, None, None, 0, None)
     assert rc == -1
     assert lib.sim_spectral_eig_workspace_bytes(4, 128, 4) == 0      # fits shared memory

@@ -171,15 +171,14 @@ def test_cuda_spectral_matches_reference(lib, ref_spec, variant):
     from si_mamba_b200 import ops
     n_checked = n_total = 0
     for c in ref_spec:
-        if c["builder"] == "centers" and c["alpha"] == 0:
-            continue  # sigma-weighted branch (:647): not a configuration of any shipped yaml, not built
+        sigma_mode = c["builder"] == "centers" and c["alpha"] == 0  # sigma-weighted branch of create_graph_from_centers (:647)
         if variant == "sym" and not c["symmetric"]:
             continue
         matrix = "sym" if variant == "sym" else "laplacian"
         eps_mode = "clamp1e-12" if variant == "batched" else "add1e-6"
         for smallest in (True, False):
             out = ops.spectral_eig(c["centre"].cuda(), c["knn"], c["alpha"], c["symmetric"], c["self_loop"],
-                                   c["binary"], 4, smallest, matrix, eps_mode, want_adjacency=True)
+                                   c["binary"], 4, smallest, matrix, eps_mode, want_adjacency=True, sigma_mode=sigma_mode)
             A, R = out["adjacency"].cpu(), c["adj"]
             assert torch.equal(A != 0, R != 0)
             if c["binary"]:
@@ -596,3 +595,40 @@ def test_cuda_hlt_cls_forward_matches_reference(lib, ref_mod, monkeypatch):
         logits = m(f["pts"].cuda(), hlt_noise=f["noise"]).cpu()
     err = (logits - f["logits"]).abs().max() / f["logits"].abs().max()
     assert err < 2e-3, err
+
+
+@pytest.mark.gpu
+def test_cuda_eig_helpers_match_reference(lib, ref_spec):
+    """PointMamba.calc_top_k_eigenvalues_eigenvectors{,_symmetric}(adj, k, smallest) - the reference's 4-tuple from a given
+    adjacency (:717-814): top-k values against the reference's own output, the full decomposition against fp64 eigh of the
+    operator the reference hands to torch.linalg.eigh, and create_graph_from_centers with self.alpha == 0."""
+    import types
+    from si_mamba_b200 import point_mamba as pmm
+    n = 0
+    for c in ref_spec:
+        adj = c["adj"].cuda()
+        for variant, fn, matrix in (("loop", pmm.PointMamba.calc_top_k_eigenvalues_eigenvectors, "laplacian"),
+                                    ("sym", pmm.PointMamba.calc_top_k_eigenvalues_eigenvectors_symmetric, "sym")):
+            if variant == "sym" and not c["symmetric"]:
+                continue
+            for smallest in (True, False):
+                vals, vecs, all_vals, all_vecs = fn(None, adj, 4, smallest)
+                rvals = c[f"{variant}_vals_{int(smallest)}"]
+                assert (vals.cpu() - rvals).abs().max() <= 2e-5
+                assert vecs.shape == (adj.shape[0], adj.shape[1], 4)
+                S = spectral.laplacian_operator(c["adj"], matrix, "add1e-6").double()
+                ev, evec = torch.linalg.eigh(S)
+                assert all_vals.shape == ev.shape and all_vecs.shape == evec.shape
+                assert (all_vals.cpu().double() - ev).abs().max() <= 2e-5
+                # every returned column is an eigenvector of the operator: || S v - lambda v || small
+                V = all_vecs.cpu().double()
+                res = (S @ V - V * all_vals.cpu().double()[:, None, :]).norm(dim=1)
+                assert res.max() < 5e-5
+                n += 1
+        if c["builder"] == "centers":
+            me = types.SimpleNamespace(alpha=c["alpha"])
+            A = pmm.PointMamba.create_graph_from_centers(me, c["centre"].cuda(), c["knn"], c["alpha"], c["symmetric"],
+                                                         c["self_loop"], c["binary"]).cpu()
+            assert torch.equal(A != 0, c["adj"] != 0)
+            assert torch.allclose(A, c["adj"], rtol=2e-6, atol=1e-12)
+    assert n >= 8
