@@ -66,6 +66,17 @@ int sim_fps(const float* xyz, int B, int N, int G, int32_t* idx, float* center, 
 int sim_knn_group(const float* xyz, const float* center, int B, int N, int G, int M, int32_t* idx, float* nbr,
                   float* nbr_org, sim_stream_t stream);
 
+/* sim_fps / sim_knn_group with a choice of distance arithmetic.  flags = 0 is the contract above: ((dx*dx)+(dy*dy))+(dz*dz),
+ * every product and sum rounded to fp32 on its own.  SIM_DIST_FMA selects fma(dz,dz, fma(dy,dy, dx*dx)) - what nvcc's default
+ * -fmad=true makes of the `dist2 += diff * diff` loops in pytorch3d's sample_farthest_points / knn_points device code.
+ * Distances differ in the last bit, so near-tied candidates can swap: a maintainer pinning bit-exact indices against a
+ * real pytorch3d build picks the flag that build agrees with (both are tested against their own oracle; the wheel is not
+ * available to this repo). */
+enum sim_distance_flags { SIM_DIST_FMA = 1 };
+int sim_fps_ex(const float* xyz, int B, int N, int G, int32_t* idx, float* center, int flags, sim_stream_t stream);
+int sim_knn_group_ex(const float* xyz, const float* center, int B, int N, int G, int M, int32_t* idx, float* nbr,
+                     float* nbr_org, int flags, sim_stream_t stream);
+
 /* a-3 + a-4 + a-5  centres -> kNN graph -> Laplacian -> k extremal eigenpairs -> argsort.
  * Replaces create_graph_from_* (models/point_mamba.py:620-715), calc_top_k_eigenvalues_eigenvectors
  * (:717-761, :3001-3050, symmetric :764-814) and the torch.sort of sort_points_by_fiedler (:817-826).

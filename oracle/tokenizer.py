@@ -19,16 +19,23 @@ from __future__ import annotations
 import torch
 
 
-def sqdist(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """Squared L2 between broadcastable (...,3) fp32 tensors, fixed op order, no FMA."""
+def sqdist(a: torch.Tensor, b: torch.Tensor, fma: bool = False) -> torch.Tensor:
+    """Squared L2 between broadcastable (...,3) fp32 tensors, fixed op order.  ``fma=False``: no FMA (the contract).
+    ``fma=True``: fma(dz, dz, fma(dy, dy, dx*dx)) - what nvcc's default contraction makes of pytorch3d's
+    ``dist2 += diff * diff`` device loops; each fused step is evaluated in fp64 (the product of two fp32 values is exact
+    there) and rounded to fp32 once."""
     dx = a[..., 0] - b[..., 0]
     dy = a[..., 1] - b[..., 1]
     dz = a[..., 2] - b[..., 2]
+    if fma:
+        t = (dx * dx).double()
+        t = (dy.double() * dy.double() + t).float().double()
+        return (dz.double() * dz.double() + t).float()
     # separate torch ops => each product / sum is rounded to fp32 on its own
     return (dx * dx + dy * dy) + dz * dz
 
 
-def fps(xyz: torch.Tensor, num_group: int) -> torch.Tensor:
+def fps(xyz: torch.Tensor, num_group: int, fma: bool = False) -> torch.Tensor:
     """Farthest point sampling, pytorch3d semantics (call site point_mamba.py:93).
 
     xyz (B,N,3) fp32 -> idx (B,G) int64.  Start index 0, min-dist init +inf.
@@ -41,7 +48,7 @@ def fps(xyz: torch.Tensor, num_group: int) -> torch.Tensor:
     ar = torch.arange(B)
     for j in range(1, num_group):
         p = xyz[ar, last]  # (B,3)
-        d = sqdist(xyz, p[:, None, :])
+        d = sqdist(xyz, p[:, None, :], fma)
         min_d = torch.minimum(min_d, d)
         # first arg-max: torch.max over dim returns the first maximal index on CPU
         mx = min_d.max(dim=1, keepdim=True).values
@@ -51,7 +58,7 @@ def fps(xyz: torch.Tensor, num_group: int) -> torch.Tensor:
     return idx
 
 
-def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int):
+def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, fma: bool = False):
     """kNN grouping (point_mamba.py:96-110).
 
     Returns (idx sorted ascending by point index (B,G,M) int64,
@@ -62,7 +69,7 @@ def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int):
     """
     B, N, _ = xyz.shape
     G = center.shape[1]
-    d = sqdist(center[:, :, None, :], xyz[:, None, :, :])  # (B,G,N)
+    d = sqdist(center[:, :, None, :], xyz[:, None, :, :], fma)  # (B,G,N)
     # lexicographic (distance, index): stable sort on distance keeps index order
     order = torch.sort(d, dim=-1, stable=True).indices[..., :group_size]
     idx = torch.sort(order, dim=-1).values

@@ -22,6 +22,8 @@ EIG_SMALLEST = 1 << 3
 LAP_SYMMETRIC = 1 << 4
 LAP_EPS_CLAMP = 1 << 5
 EIG_CANONICAL_SIGN = 1 << 6
+# sim_distance_flags
+DIST_FMA = 1
 
 _p, _i, _l, _f, _sz = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
 
@@ -31,6 +33,8 @@ SIGNATURES = {
     "sim_last_error_string": (C.c_char_p, []),
     "sim_fps": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "sim_knn_group": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "sim_fps_ex": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
+    "sim_knn_group_ex": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "sim_spectral_eig_workspace_bytes": (_sz, [_i, _i, _i]),
     "sim_spectral_eig": (_i, [_p, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sim_spectral_eig_ex": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),

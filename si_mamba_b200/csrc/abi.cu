@@ -46,6 +46,16 @@ int sim_knn_group(const float* xyz, const float* center, int B, int N, int G, in
   return sim::knn_group(xyz, center, B, N, G, M, idx, nbr, nbr_org, static_cast<cudaStream_t>(stream));
 }
 
+int sim_fps_ex(const float* xyz, int B, int N, int G, int32_t* idx, float* center, int flags, sim_stream_t stream) {
+  return sim::fps(xyz, B, N, G, idx, center, static_cast<cudaStream_t>(stream), 0, (flags & SIM_DIST_FMA) != 0);
+}
+
+int sim_knn_group_ex(const float* xyz, const float* center, int B, int N, int G, int M, int32_t* idx, float* nbr,
+                     float* nbr_org, int flags, sim_stream_t stream) {
+  return sim::knn_group(xyz, center, B, N, G, M, idx, nbr, nbr_org, static_cast<cudaStream_t>(stream),
+                        (flags & SIM_DIST_FMA) != 0);
+}
+
 size_t sim_spectral_eig_workspace_bytes(int B, int G, int k) { return sim::spectral_workspace_bytes(B, G, k); }
 
 int sim_spectral_eig(const float* center, int B, int G, int k_nn, float alpha, int flags, int k, float* eigvals,

@@ -6,8 +6,8 @@
 namespace sim {
 
 // implemented in the kernel translation units
-int fps(const float*, int, int, int, int*, float*, cudaStream_t, int pointnet2 = 0);
-int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t);
+int fps(const float*, int, int, int, int*, float*, cudaStream_t, int pointnet2 = 0, int fma = 0);
+int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t, int fma = 0);
 int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
                   int, int, cudaStream_t, void* planes = nullptr, long plane = 0);
 int order_gather_fwd(const void*, const void*, const int*, void*, void*, int, int, int, int, int, int, cudaStream_t);

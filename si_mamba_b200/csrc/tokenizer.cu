@@ -18,8 +18,13 @@
 
 namespace sim {
 
-__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+// fma = 0 (default contract): every product and sum rounded on its own.  fma = 1: the contraction a CUDA compiler makes
+// of `dist2 = 0; for d: dist2 += diff * diff` (pytorch3d's sample_farthest_points / knn_points device loops built with
+// the default -fmad=true): fma(dz, dz, fma(dy, dy, dx * dx)).  Which one the reference's wheel used cannot be checked
+// here (the wheel is absent), so both conventions are built and tested against their own oracle (include/simamba.h).
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz, int fma = 0) {
   const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  if (fma) return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
@@ -31,7 +36,7 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
 // (index mod bs_up, bs_up = upstream block size) and then the lowest index - `key` below orders exactly that way.
 template <int NT, int PPT, bool PN2>
 __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, int N, int G, int* __restrict__ idx,
-                                                 float* __restrict__ center, int bs_up) {
+                                                 float* __restrict__ center, int bs_up, int fma) {
   extern __shared__ float s_xyz[];  // N*3
   constexpr int NW = NT / 32;
   __shared__ unsigned s_bits[2][NW];
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, 
           best_idx = key;
         }
       } else {
-        const float d = sqdist3(px[j], py[j], pz[j], wx, wy, wz);
+        const float d = sqdist3(px[j], py[j], pz[j], wx, wy, wz, fma);
         md[j] = fminf(md[j], d);
         const unsigned bits = __float_as_uint(md[j]);
         if (i < N && (best_idx == 0xffffffffu || bits > best_bits)) {  // strict >: keeps the lowest own index
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(NT) fps_kernel(const float* __restrict__ xyz, 
   }
 }
 
-int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStream_t stream, int pointnet2) {
+int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStream_t stream, int pointnet2, int fma) {
   SIM_REQUIRE(B > 0 && N > 0 && G > 0 && G <= N, SIM_ERR_INVALID, "fps: need 0 < G <= N (G=%d N=%d)", G, N);
   SIM_REQUIRE(xyz && idx && center, SIM_ERR_INVALID, "fps: null tensor");
   const size_t smem = (size_t)N * 3 * sizeof(float);
@@ -120,12 +125,12 @@ int fps(const float* xyz, int B, int N, int G, int* idx, float* center, cudaStre
       auto kern = fps_kernel<NT, PPT, true>;                                                            \
       static SmemAttrCache attr; /* per device, grow-only, set by the first (warm-up) call */             \
       if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                   \
-      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up);                                     \
+      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up, fma);                                \
     } else {                                                                                            \
       auto kern = fps_kernel<NT, PPT, false>;                                                           \
       static SmemAttrCache attr;                                                                        \
       if (smem + 2048 > 48 * 1024) ensure_dyn_smem(kern, smem, attr);                                   \
-      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up);                                     \
+      kern<<<B, NT, smem, stream>>>(xyz, N, G, idx, center, bs_up, fma);                                \
     }                                                                                                   \
   } while (0)
   if (N <= 512)
@@ -151,7 +156,8 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) knn_group_kernel(const float* __restrict__ xyz,
                                                                const float* __restrict__ center, int N, int G,
                                                                int M, int* __restrict__ idx_out,
-                                                               float* __restrict__ nbr, float* __restrict__ nbr_org) {
+                                                               float* __restrict__ nbr, float* __restrict__ nbr_org,
+                                                               int fma) {
   extern __shared__ float sm[];
   float* s_xyz = sm;                                              // N*3
   unsigned* s_d = reinterpret_cast<unsigned*>(sm + (size_t)N * 3);  // WARPS * N distance bit patterns
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32) knn_group_kernel(const float* __re
               cz = center[((long)b * G + g) * 3 + 2];
   unsigned* d = s_d + (size_t)warp * N;
   for (int i = lane; i < N; i += 32)
-    d[i] = __float_as_uint(sqdist3(cx, cy, cz, s_xyz[3 * i], s_xyz[3 * i + 1], s_xyz[3 * i + 2]));
+    d[i] = __float_as_uint(sqdist3(cx, cy, cz, s_xyz[3 * i], s_xyz[3 * i + 1], s_xyz[3 * i + 2], fma));
   __syncwarp();
   // T = M-th smallest bit pattern: the largest v with #{d < v} < M (distances are >= 0, so bit 31 is clear)
   unsigned T = 0;
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32) knn_group_kernel(const float* __re
 }
 
 int knn_group(const float* xyz, const float* center, int B, int N, int G, int M, int* idx, float* nbr,
-              float* nbr_org, cudaStream_t stream) {
+              float* nbr_org, cudaStream_t stream, int fma) {
   SIM_REQUIRE(B > 0 && N > 0 && G > 0 && M > 0 && M <= N, SIM_ERR_INVALID, "knn_group: need 0 < M <= N");
   SIM_REQUIRE(xyz && center && idx, SIM_ERR_INVALID, "knn_group: null tensor");
   constexpr int WARPS = 8;
@@ -220,7 +226,7 @@ int knn_group(const float* xyz, const float* center, int B, int N, int G, int M,
   static SmemAttrCache attr;  // per device, grow-only, set by the first (warm-up) call
   if (smem > 48 * 1024) ensure_dyn_smem(kern, smem, attr);
   const int grid = B * ((G + WARPS - 1) / WARPS);
-  kern<<<grid, WARPS * 32, smem, stream>>>(xyz, center, N, G, M, idx, nbr, nbr_org);
+  kern<<<grid, WARPS * 32, smem, stream>>>(xyz, center, N, G, M, idx, nbr, nbr_org, fma);
   return check_launch("knn_group");
 }
 

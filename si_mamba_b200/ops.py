@@ -75,14 +75,23 @@ def sample_farthest_points(points: torch.Tensor, K: int):
     return center, idx.long()
 
 
-def fps(xyz: torch.Tensor, num_group: int):
+# Distance arithmetic of FPS / kNN (include/simamba.h, sim_distance_flags): False = separately rounded products and sums
+# (the documented contract), True = the FMA contraction of pytorch3d's device loops.  A process-wide default so a
+# maintainer can flip the whole model with one line; every call can override it.
+DIST_FMA = __import__("os").environ.get("SIM_DIST_FMA", "0") == "1"
+
+
+def fps(xyz: torch.Tensor, num_group: int, fma: Optional[bool] = None):
     """-> (center (B,G,3) fp32, idx (B,G) int32).  models/point_mamba.py:93."""
     _cuda(xyz)
     xyz = xyz.float().contiguous()
     B, N, _ = xyz.shape
     idx = torch.empty(B, num_group, dtype=torch.int32, device=xyz.device)
     center = torch.empty(B, num_group, 3, dtype=torch.float32, device=xyz.device)
-    _lib.call("sim_fps", _p(xyz), B, N, num_group, _p(idx), _p(center), _stream())
+    if DIST_FMA if fma is None else fma:
+        _lib.call("sim_fps_ex", _p(xyz), B, N, num_group, _p(idx), _p(center), _lib.DIST_FMA, _stream())
+    else:
+        _lib.call("sim_fps", _p(xyz), B, N, num_group, _p(idx), _p(center), _stream())
     return center, idx
 
 
@@ -98,7 +107,8 @@ def fps_pointnet2(data: torch.Tensor, number: int, return_idx: bool = False):
     return (out, idx) if return_idx else out
 
 
-def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, want_org: bool = True):
+def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, want_org: bool = True,
+              fma: Optional[bool] = None):
     """-> (idx (B,G,M) int32 ascending, neighborhood centred, neighborhood_org).  point_mamba.py:96-110."""
     _cuda(xyz, center)
     xyz = xyz.float().contiguous()
@@ -108,7 +118,11 @@ def knn_group(xyz: torch.Tensor, center: torch.Tensor, group_size: int, want_org
     idx = torch.empty(B, G, group_size, dtype=torch.int32, device=xyz.device)
     nbr = torch.empty(B, G, group_size, 3, dtype=torch.float32, device=xyz.device)
     org = torch.empty_like(nbr) if want_org else None
-    _lib.call("sim_knn_group", _p(xyz), _p(center), B, N, G, group_size, _p(idx), _p(nbr), _p(org), _stream())
+    if DIST_FMA if fma is None else fma:
+        _lib.call("sim_knn_group_ex", _p(xyz), _p(center), B, N, G, group_size, _p(idx), _p(nbr), _p(org), _lib.DIST_FMA,
+                  _stream())
+    else:
+        _lib.call("sim_knn_group", _p(xyz), _p(center), B, N, G, group_size, _p(idx), _p(nbr), _p(org), _stream())
     return idx, nbr, org
 
 

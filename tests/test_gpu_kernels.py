@@ -48,6 +48,24 @@ def test_tokenizer_vs_oracle(ops, B, N, G, M, kind):
         assert torch.equal(nbr.cpu(), ref_nbr) and torch.equal(org.cpu(), ref_org)
 
 
+@pytest.mark.parametrize("B,N,G,M,kind", [(4, 1024, 64, 32, "surface"), (2, 2048, 128, 32, "duplicates"), (2, 100, 7, 5, "ball")])
+def test_tokenizer_fma_convention_vs_oracle(ops, B, N, G, M, kind):
+    """SIM_DIST_FMA (sim_fps_ex / sim_knn_group_ex): the FMA-contracted distance pytorch3d's device loops most plausibly
+    compute, bit-exact against the oracle evaluated with the same contraction; the two conventions really differ in the
+    last bit of some distances (otherwise the flag would test nothing)."""
+    xyz = tokenizer.synthetic_clouds(B, N, 300 + N + G, kind)
+    fidx = tokenizer.fps(xyz, G, fma=True)
+    center, idx = ops.fps(dev(xyz), G, fma=True)
+    assert torch.equal(idx.cpu().long(), fidx)
+    ref_idx, ref_nbr, ref_org = tokenizer.knn_group(xyz, center.cpu(), M, fma=True)
+    kidx, nbr, org = ops.knn_group(dev(xyz), center, M, fma=True)
+    assert torch.equal(kidx.cpu().long(), ref_idx)
+    assert torch.equal(nbr.cpu(), ref_nbr) and torch.equal(org.cpu(), ref_org)
+    d0 = tokenizer.sqdist(xyz[:, :, None, :], xyz[:, None, :64, :])
+    d1 = tokenizer.sqdist(xyz[:, :, None, :], xyz[:, None, :64, :], fma=True)
+    assert not torch.equal(d0, d1) and torch.allclose(d0, d1, rtol=3e-7, atol=0)
+
+
 def test_fps_all_points_identical(ops):
     xyz = torch.zeros(1, 64, 3)
     xyz[0, :, 0] = 0.25
