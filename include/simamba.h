@@ -249,6 +249,19 @@ int sim_chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, flo
 int sim_chamfer_l2_bwd(const float* x, const float* y, const int32_t* idx_x, const int32_t* idx_y, const float* gloss,
                        long R, int P, int Q, float* dx, float* dy, sim_stream_t stream);
 
+/* a-10  bf16 projection GEMM (hand-written TMA + tcgen05 + TMEM kernel, csrc/gemm_bf16.cu): the in_proj / x_proj /
+ * dt_proj / out_proj products of Mamba.forward (models/block.py:72) under bf16 autocast (tools/runner_pretrain.py:243)
+ * and the dgrad / wgrad GEMMs of their backward, read in place from row-major tensors:
+ *   Y[M,N] = op(A) . op(B)^T, bf16 operands, fp32 accumulation in tensor memory;
+ *   a_mn = 0: A is (M,K) with row stride lda;  a_mn = 1: A is (K,M) with row stride lda (contraction index = row);
+ *   b_mn = 0: B is (N,K) with row stride ldb;  b_mn = 1: B is (K,N) with row stride ldb;
+ *   forward  Y = X W^T : (X,0, W,0);   dgrad dX = dY W : (dY,0, W,1);   wgrad dW = dY^T X : (dY,1, X,1).
+ *   out_bf16 = 1: Y bf16, else fp32 (row stride ldy, N and ldy multiples of 4).  splits > 1: split-K, every CTA ADDS its
+ *   partial tile to a caller-zeroed fp32 Y; splits = 0 chooses a split that fills the SMs (weight gradients).
+ * Operand bases 16-byte aligned, lda / ldb multiples of 8 elements; M, N, K arbitrary (tiles are zero-filled). */
+int sim_gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
+                  int M, int N, int K, int splits, sim_stream_t stream);
+
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
  * elements, row stride ldo); the weights are split once per model, activations by their producer.

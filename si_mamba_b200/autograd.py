@@ -102,6 +102,9 @@ _CONV_XPROJ = __import__("os").environ.get("SIM_CONV_XPROJ", "0") != "0"  # caus
 # split-K both fills the SMs and keeps each tensor-core accumulation chain short (6e-7 against fp64, cuBLAS SGEMM 8e-7).
 _TRAIN_X3 = __import__("os").environ.get("SIM_TRAIN_X3", "1") != "0"
 _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-split tcgen05 kernel) | cublas (ablation)
+# bf16 (autocast) projections - inference, training forward, dgrad and wgrad - on the hand-written tcgen05 bf16 kernel
+# (csrc/gemm_bf16.cu, operands read in place, MN-major for the backward); "cublas" keeps F.linear as the ablation switch
+_BF16_GEMM = __import__("os").environ.get("SIM_BF16_GEMM", "own")
 
 
 class _SplitCols(torch.autograd.Function):
@@ -144,7 +147,13 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     need_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in (hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_proj_b, A_log, D,
                                   out_proj_w))
-    if need_grad:
+    own_bf16 = (act == torch.bfloat16 and _BF16_GEMM != "cublas" and not isinstance(hidden, ops.Split3) and hidden.is_cuda
+                and all(w.shape[1] % 8 == 0 and w.shape[0] % 4 == 0 for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w)))
+    if need_grad and own_bf16:
+        # LinearBF16 takes the fp32 master weights themselves (one cast per call) and returns their gradients in fp32
+        w_in, w_x, w_dt, w_out = in_proj_w, x_proj_w, dt_proj_w, out_proj_w
+        A = -torch.exp(A_log.float())
+    elif need_grad:
         w_in, w_x, w_dt, w_out = (w.to(act) for w in (in_proj_w, x_proj_w, dt_proj_w, out_proj_w))
         A = -torch.exp(A_log.float())
     else:
@@ -154,7 +163,7 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     # fp32 inference: the four projections run on the tensor cores with fp32-accurate 3 x bf16 operand splitting.
     # x3: hand-written TMA + tcgen05 kernel on pre-split planes (weights split once and cached, 3.7x cuBLAS SGEMM on
     # in_proj); cublas: F.linear (SIMT SGEMM), kept as the ablation switch.
-    linear = F.linear
+    linear = ops.linear_bf16 if own_bf16 else F.linear
     x3 = False
     if not need_grad and act == torch.float32 and hidden.is_cuda and _FP32_GEMM != "cublas":
         x3 = d_inner % 64 == 0  # every producer below then emits the split operand of the next projection itself

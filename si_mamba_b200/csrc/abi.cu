@@ -107,6 +107,11 @@ int sim_spectral_eig_ex(const float* center, const float* adjacency_in, const fl
   return sim::spectral_eig(P, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int sim_gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
+                  int M, int N, int K, int splits, sim_stream_t stream) {
+  return sim::gemm_bf16(A, lda, a_mn, B, ldb, b_mn, Y, ldy, out_bf16, M, N, K, splits, static_cast<cudaStream_t>(stream));
+}
+
 int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream) {
   return sim::pairwise_dist_mean(center, B, G, partial, sigma, static_cast<cudaStream_t>(stream));
 }

@@ -68,6 +68,8 @@ struct ScanBwdParams {
   int softplus;
 };
 int selective_scan_bwd(const ScanBwdParams&, int, cudaStream_t);
+int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
+              int N, int K, int splits, cudaStream_t stream);
 int causal_conv1d_bwd(const void*, long, const float*, const float*, const void*, long, void*, long, float*, float*,
                       int, int, int, int, int, int, cudaStream_t);
 

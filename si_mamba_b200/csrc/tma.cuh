@@ -19,6 +19,16 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapFloatOOBfill);
 
 static inline PFN_tmapEncodeTiled tmap_encode_fn() {
+  // cuTensorMapEncodeTiled is a driver call and needs a context bound to the CALLING thread (CUDA_ERROR_INVALID_CONTEXT
+  // otherwise).  A thread that has only been told its device through cudaGetDevice - PyTorch's autograd worker when one of
+  // these kernels is the first thing its backward runs - has none yet: cudaSetDevice binds the primary context (no stream
+  // operation, so it is legal during graph capture).
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    bound = true;
+  }
   static PFN_tmapEncodeTiled fn = nullptr;  // benign race: every thread resolves the same pointer
   if (!fn) {
     void* p = nullptr;
@@ -66,6 +76,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// global -> shared, 2-D tile, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
 

@@ -628,6 +628,80 @@ def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torc
     return out
 
 
+def _gemm_operand(t: torch.Tensor) -> torch.Tensor:
+    """2-D bf16 operand the TMA unit can read in place: unit inner stride, 16-byte aligned base and row stride."""
+    assert t.dim() == 2 and t.dtype == torch.bfloat16
+    if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+        if t.stride(0) % 8 != 0:  # odd widths (never on the SI-Mamba shapes): pad the row pitch
+            p = torch.zeros(t.shape[0], (t.shape[1] + 7) // 8 * 8, dtype=t.dtype, device=t.device)
+            p[:, :t.shape[1]] = t
+            t = p[:, :t.shape[1]]
+    return t
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False,
+              out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None, splits: int = 1) -> torch.Tensor:
+    """Y = op(a) @ op(b).T on the tcgen05 bf16 kernel (sim_gemm_bf16).  a: (M,K), or (K,M) when ``a_mn``; b: (N,K), or (K,N)
+    when ``b_mn`` - row-major views with a uniform row stride are read in place.  ``splits`` = 0: automatic split-K into an
+    fp32 result (weight gradients)."""
+    _cuda(a, b, out)
+    a, b = _gemm_operand(a), _gemm_operand(b)
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    assert K == Kb, f"contraction sizes differ: {K} vs {Kb}"
+    if splits != 1:
+        out_dtype = torch.float32
+    if out is None:
+        out = (torch.zeros if splits != 1 else torch.empty)(M, N, dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    _lib.call("sim_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out), out.stride(0),
+              int(out.dtype == torch.bfloat16), M, N, K, int(splits), _stream())
+    return out
+
+
+class LinearBF16(torch.autograd.Function):
+    """y = x @ w.T for the bf16 (autocast) mixer on the hand-written tcgen05 kernel: x (..., K) bf16, w (N, K) - an fp32
+    parameter is cast once per call - -> (..., N) bf16.  Backward: dX = dY @ W and dW = dY^T @ X read dY, W and X in place
+    (MN-major operands), dW with split-K in fp32 - the dtype of the master weight's gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        wb = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        K = w.shape[1]
+        x2 = x.reshape(-1, K) if x.is_contiguous() or x.dim() == 2 else _as_rows(x)
+        ctx.save_for_backward(x2, wb)
+        ctx.x_shape, ctx.w_dtype = x.shape, w.dtype
+        return gemm_bf16(x2, wb).view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb = ctx.saved_tensors
+        N, K = wb.shape
+        dy2 = dy.reshape(-1, N)
+        if dy2.dtype != torch.bfloat16:
+            dy2 = dy2.to(torch.bfloat16)
+        dy2 = _gemm_operand(dy2)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_bf16(dy2, wb, b_mn=True).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm_bf16(dy2, x2, a_mn=True, b_mn=True, splits=0)
+            if ctx.w_dtype != torch.float32:
+                dw = dw.to(ctx.w_dtype)
+        return dx, dw
+
+
+def linear_bf16(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Differentiable y = x @ w.T on the tcgen05 bf16 kernel (see LinearBF16); plain forward when no graph is needed."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return LinearBF16.apply(x, w)
+    wb = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+    K = w.shape[1]
+    x2 = x.reshape(-1, K) if x.is_contiguous() or x.dim() == 2 else _as_rows(x)
+    return gemm_bf16(x2, wb).view(*x.shape[:-1], w.shape[0])
+
+
 class LinearX3(torch.autograd.Function):
     """y = x @ w.T for fp32 TRAINING on the tcgen05 split-plane GEMM (the reference's fp32 runs do all three GEMMs of a
     Linear as SIMT SGEMMs): forward, dX = dY @ W and dW = dY^T @ X each split their two operands into bf16 planes

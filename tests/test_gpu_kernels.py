@@ -581,3 +581,53 @@ def test_mlp3_relu_rows(ops, rows, d0, d1, d2, d3):
     y0 = ops.mlp3_relu_rows(x, ws[0], None, ws[1], None, ws[2], None)
     h = torch.relu(torch.relu(x.double() @ ws[0].double()) @ ws[1].double()) @ ws[2].double()
     assert (y0.double() - h).abs().max().item() < 1e-5 * max(1.0, h.abs().max().item())
+
+
+# ----------------------------------------------------------------------------- a-10 bf16 GEMM on tensor cores (autocast configs)
+@pytest.mark.parametrize("M,N,K", [(16384, 1536, 384), (16384, 56, 768), (16384, 768, 24), (16384, 384, 768),
+                                   (100, 64, 36), (7, 384, 128), (300, 256, 40), (4096, 24, 768), (520, 200, 1000)])
+def test_gemm_bf16_all_layouts(ops, M, N, K):
+    """sim_gemm_bf16 (hand-written tcgen05 kernel) in its three uses - forward (K-major x K-major), dgrad (K-major x
+    MN-major), wgrad (MN-major x MN-major, automatic split-K) - and the fourth combination, against fp64 products of the
+    same bf16 operands; bf16 and fp32 outputs; operands that are column slices of wider buffers."""
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = K + 8 * (K % 3)  # exercise row strides wider than the logical width
+    xw = torch.randn(M, ld, generator=g).to(torch.bfloat16)
+    x = xw[:, :K]
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    ref = x.double() @ w.double().t()
+    scale = ref.abs().max()
+    xd, wd = dev(xw)[:, :K], dev(w)
+    y = ops.gemm_bf16(xd, wd)                                      # forward
+    assert y.dtype == torch.bfloat16 and (y.cpu().double() - ref).abs().max() / scale < 6e-3
+    y32 = ops.gemm_bf16(xd, wd, out_dtype=torch.float32)
+    assert (y32.cpu().double() - ref).abs().max() / scale < 2e-5
+    yt = ops.gemm_bf16(xd, dev(w.t().contiguous()), b_mn=True, out_dtype=torch.float32)   # B given as (K, N)
+    assert (yt.cpu().double() - ref).abs().max() / scale < 2e-5
+    xt = dev(x.t().contiguous())                                   # A given as (K, M)
+    y3 = ops.gemm_bf16(xt, dev(w.t().contiguous()), a_mn=True, b_mn=True, out_dtype=torch.float32)
+    assert (y3.cpu().double() - ref).abs().max() / scale < 2e-5
+    y4 = ops.gemm_bf16(xt, wd, a_mn=True, out_dtype=torch.float32)
+    assert (y4.cpu().double() - ref).abs().max() / scale < 2e-5
+    y5 = ops.gemm_bf16(xt, dev(w.t().contiguous()), a_mn=True, b_mn=True, splits=0)        # split-K (wgrad form)
+    assert y5.dtype == torch.float32 and (y5.cpu().double() - ref).abs().max() / scale < 2e-5
+
+
+def test_linear_bf16_autograd(ops):
+    """LinearBF16: forward / dX / dW of a projection on the bf16 kernel vs autograd of the fp32 product of the same bf16
+    operands (x_proj shape with its 56-wide rows, and dt_proj reading the first 24 columns of those rows in place)."""
+    g = torch.Generator().manual_seed(5)
+    for (M, N, K, ldx) in ((4096, 56, 768, 768), (4096, 768, 24, 56), (2048, 1536, 384, 384)):
+        xb = torch.randn(M, ldx, generator=g).to(torch.bfloat16)
+        w = torch.randn(N, K, generator=g) * K ** -0.5
+        dy = torch.randn(M, N, generator=g).to(torch.bfloat16)
+        xr = xb[:, :K].float().requires_grad_(True)
+        wr = w.to(torch.bfloat16).float().requires_grad_(True)
+        (xr @ wr.t()).backward(dy.float())
+        xc = dev(xb).requires_grad_(True)
+        wc = dev(w).requires_grad_(True)
+        y = ops.linear_bf16(xc[:, :K], wc)
+        y.backward(dev(dy))
+        assert rel_err(y.detach().cpu().float(), (xr @ wr.t()).detach()) < 6e-3
+        assert wc.grad.dtype == torch.float32 and rel_err(wc.grad.cpu(), wr.grad) < 1e-4
+        assert rel_err(xc.grad.cpu().float()[:, :K], xr.grad) < 6e-3
