@@ -222,6 +222,10 @@ int sim_fps_pointnet2(const float* xyz, int B, int N, int npoint, int32_t* idx, 
  *                     BatchNorm folded into W / b by the caller; weights TRANSPOSED (in, out) fp32, widths d1, d2, d3 <= 256,
  *                     biases may be NULL. */
 int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype, sim_stream_t stream);
+/* a-2  y[p,c] = act(b[c] + <w[c,:], x[p,:]>) for 3-D points: x (rows,3), w (C,3), b (C) or NULL, y (rows,C) fp32, C % 4 == 0;
+ * act 0 = none, 1 = ReLU (Encoder.first_conv[0..2] with eval BatchNorm folded, models/point_mamba.py:47-49), 2 = GELU (erf;
+ * pos_embed[0..1], :470-474). */
+int sim_point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, sim_stream_t stream);
 int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, sim_stream_t stream);
 int sim_layernorm_mean(const float* x, const float* gamma, const float* beta, float* out, int B, int L, int C, float eps,
                        sim_stream_t stream);
@@ -261,6 +265,14 @@ int sim_chamfer_l2_bwd(const float* x, const float* y, const int32_t* idx_x, con
  * Operand bases 16-byte aligned, lda / ldb multiples of 8 elements; M, N, K arbitrary (tiles are zero-filled). */
 int sim_gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
                   int M, int N, int K, int splits, sim_stream_t stream);
+
+/* a-2  the same kernel on fp32 operands consumed as TF32 (tcgen05 kind::tf32), with an optional + bias[N] and ReLU
+ * epilogue: the 1x1 convolutions of Encoder.forward (models/point_mamba.py:59-73) written as row-major GEMMs on the
+ * (B*G*M, C) point matrix, at the precision the reference's Conv1d layers run at (torch default cudnn.allow_tf32 = True);
+ * K-major operands only (a_mn = b_mn = 0: 32-bit MN-major tiles need another swizzle atom and are not built).
+ * lda / ldb multiples of 4 elements. */
+int sim_gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
+                  int M, int N, int K, int splits, const float* bias, int relu, sim_stream_t stream);
 
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane

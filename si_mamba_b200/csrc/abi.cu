@@ -112,6 +112,12 @@ int sim_gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, in
   return sim::gemm_bf16(A, lda, a_mn, B, ldb, b_mn, Y, ldy, out_bf16, M, N, K, splits, static_cast<cudaStream_t>(stream));
 }
 
+int sim_gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
+                  int M, int N, int K, int splits, const float* bias, int relu, sim_stream_t stream) {
+  return sim::gemm_tf32(A, lda, a_mn, B, ldb, b_mn, Y, ldy, out_bf16, M, N, K, splits, bias, relu,
+                        static_cast<cudaStream_t>(stream));
+}
+
 int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream) {
   return sim::pairwise_dist_mean(center, B, G, partial, sigma, static_cast<cudaStream_t>(stream));
 }
@@ -351,6 +357,10 @@ int sim_group_max(const void* x, void* out, long groups, int M, int C, int dtype
 
 int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, sim_stream_t stream) {
   return sim::group_bias_relu(x, gvec, rows, M, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sim_point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, sim_stream_t stream) {
+  return sim::point_linear3(x, w, b, y, rows, C, act, static_cast<cudaStream_t>(stream));
 }
 
 int sim_mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1,

@@ -31,13 +31,20 @@ namespace sim {
 namespace {
 
 constexpr int kBM = 128;  // output rows per CTA == TMEM lanes
-constexpr int kBK = 64;   // contraction elements per pipeline stage (one 128-byte swizzle span of bf16)
-constexpr int kUK = 16;   // K of one tcgen05.mma.kind::f16
+// A pipeline stage holds one 128-byte swizzle span of contraction per row: 64 bf16 or 32 fp32 (TF32) elements, consumed by
+// four tcgen05.mma of 32 bytes of K each (K = 16 for kind::f16, K = 8 for kind::tf32).  In bytes the two element types share
+// every tile size and descriptor; TF32 = false / true selects the element size, the MMA kind and the operand formats.
+template <bool TF32>
+struct El {
+  static constexpr int ES = TF32 ? 4 : 2;     // bytes per element
+  static constexpr int BK = 128 / ES;         // contraction elements per stage == columns of one MN-major chunk
+  static constexpr int UK = 32 / ES;          // K of one MMA
+};
 
 template <int BN, int NSTAGE_>
 struct Cfg {
-  static constexpr int A_TILE = kBM * kBK * 2;
-  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int A_TILE = kBM * 128;
+  static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = A_TILE + B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int STG_LD = 36;  // padded row stride (floats) of the epilogue staging tile
@@ -60,16 +67,27 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -105,23 +123,38 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t smem_addr, uint3
   return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((chunk_bytes >> 4) & 0x3fffu) << 16) |
          ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor: D fp32 (bits [4,6) = 1), A and B bf16 (bits [7,10), [10,13) = 1), a_major bit 15, b_major bit 16
-// (0 = K-major, 1 = MN-major), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+// Instruction descriptor: D fp32 (bits [4,6) = 1), A and B format in bits [7,10), [10,13) (1 = bf16, 2 = tf32), a_major bit
+// 15, b_major bit 16 (0 = K-major, 1 = MN-major), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t idesc_tc(int M, int N, bool a_mn, bool b_mn, bool tf32) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// optional epilogue: + bias[column], ReLU
+struct Epi {
+  const float* bias;
+  int relu;
+};
+__device__ __forceinline__ float4 apply_epi(float4 o, const Epi& e, int gn) {
+  if (e.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(e.bias + gn);
+    o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+  }
+  if (e.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+  return o;
 }
 
 struct Tmaps {
   CUtensorMap a, b;
 };
 
-template <int BN, int NSTAGE_, bool A_MN, bool B_MN>
+template <int BN, int NSTAGE_, bool A_MN, bool B_MN, bool TF32>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ Tmaps tm, void* __restrict__ Yv, long ldd, int M, int N, int K, int n_tiles,
-                     int out_bf16, int kb_per_split) {
+                     int out_bf16, int kb_per_split, const Epi epi) {
   using C = Cfg<BN, NSTAGE_>;
   constexpr int NSTAGE = C::NSTAGE;
+  constexpr int kBK = El<TF32>::BK, kUK = El<TF32>::UK;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
@@ -165,13 +198,13 @@ __global__ void __launch_bounds__(192, 1)
         mbar_arrive_expect_tx(&full[s], C::STAGE);
         if constexpr (A_MN) {  // map dims (output rows [contiguous], contraction rows): one copy per 64-column chunk
 #pragma unroll
-          for (int c = 0; c < kBM / 64; ++c) tma_load_2d(st + c * 64 * 128, &tm.a, m0 + c * 64, k0, &full[s]);
+          for (int c = 0; c < kBM / kBK; ++c) tma_load_2d(st + c * kBK * 128, &tm.a, m0 + c * kBK, k0, &full[s]);
         } else {               // map dims (contraction [contiguous], output rows)
           tma_load_2d(st, &tm.a, k0, m0, &full[s]);
         }
         if constexpr (B_MN) {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(st + C::A_TILE + c * 64 * 128, &tm.b, n0 + c * 64, k0, &full[s]);
+          for (int c = 0; c < BN / kBK; ++c) tma_load_2d(st + C::A_TILE + c * kBK * 128, &tm.b, n0 + c * kBK, k0, &full[s]);
         } else {
           tma_load_2d(st + C::A_TILE, &tm.b, k0, n0, &full[s]);
         }
@@ -179,7 +212,7 @@ __global__ void __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = idesc_tc(kBM, BN, A_MN, B_MN, TF32);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % NSTAGE;
         mbar_wait(&full[s], (kb / NSTAGE) & 1);
@@ -189,9 +222,9 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
         for (int k = 0; k < kBK / kUK; ++k) {
           // K-major: 16 contraction elements = 32 bytes further along the swizzled row; MN-major: 16 contraction rows
-          const uint64_t da = A_MN ? desc_mnmajor_sw128(a0 + k * kUK * 128, 64 * 128) : desc_kmajor_sw128(a0 + k * kUK * 2);
-          const uint64_t db = B_MN ? desc_mnmajor_sw128(b0 + k * kUK * 128, 64 * 128) : desc_kmajor_sw128(b0 + k * kUK * 2);
-          umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+          const uint64_t da = A_MN ? desc_mnmajor_sw128(a0 + k * kUK * 128, kBK * 128) : desc_kmajor_sw128(a0 + k * 32);
+          const uint64_t db = B_MN ? desc_mnmajor_sw128(b0 + k * kUK * 128, kBK * 128) : desc_kmajor_sw128(b0 + k * 32);
+          umma<TF32>(tmem_d, da, db, idesc, (kb | k) != 0);
         }
         umma_commit(&empty[s]);
       }
@@ -219,7 +252,7 @@ __global__ void __launch_bounds__(192, 1)
         const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
         const int gm = m0 + quad * 32 + row, gn = n0 + c * 32 + col;
         if (gm < M && gn < N) {
-          const float4 o = *reinterpret_cast<const float4*>(stg + row * C::STG_LD + col);
+          const float4 o = apply_epi(*reinterpret_cast<const float4*>(stg + row * C::STG_LD + col), epi, gn);
           if (out_bf16) {
             const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
             uint2 pk;
@@ -252,8 +285,8 @@ __global__ void __launch_bounds__(192, 1)
 // first TMA round trip and an un-overlapped epilogue per tile: 3.05 ms against cuBLAS' 2.39 ms on the bf16 C1 forward.
 template <int BN, int NSTAGE_>
 struct PCfg {
-  static constexpr int A_TILE = kBM * kBK * 2;
-  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int A_TILE = kBM * 128;
+  static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = A_TILE + B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int NEPI = 8;
@@ -266,12 +299,13 @@ struct PCfg {
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN, int NSTAGE_, bool A_MN, bool B_MN>
+template <int BN, int NSTAGE_, bool A_MN, bool B_MN, bool TF32>
 __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
     gemm_bf16_persistent_kernel(const __grid_constant__ Tmaps tm, void* __restrict__ Yv, long ldd, int M, int N, int K,
-                                int n_tiles, int total_tiles, int out_bf16) {
+                                int n_tiles, int total_tiles, int out_bf16, const Epi epi) {
   using C = PCfg<BN, NSTAGE_>;
   constexpr int NSTAGE = C::NSTAGE, CW = C::CW;
+  constexpr int kBK = El<TF32>::BK, kUK = El<TF32>::UK;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);
@@ -318,13 +352,13 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
           mbar_arrive_expect_tx(&full[s], C::STAGE);
           if constexpr (A_MN) {
 #pragma unroll
-            for (int c = 0; c < kBM / 64; ++c) tma_load_2d(st + c * 64 * 128, &tm.a, m0 + c * 64, k0, &full[s]);
+            for (int c = 0; c < kBM / kBK; ++c) tma_load_2d(st + c * kBK * 128, &tm.a, m0 + c * kBK, k0, &full[s]);
           } else {
             tma_load_2d(st, &tm.a, k0, m0, &full[s]);
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(st + C::A_TILE + c * 64 * 128, &tm.b, n0 + c * 64, k0, &full[s]);
+            for (int c = 0; c < BN / kBK; ++c) tma_load_2d(st + C::A_TILE + c * kBK * 128, &tm.b, n0 + c * kBK, k0, &full[s]);
           } else {
             tma_load_2d(st + C::A_TILE, &tm.b, k0, n0, &full[s]);
           }
@@ -333,7 +367,7 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = idesc_tc(kBM, BN, A_MN, B_MN, TF32);
       int it = 0, i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
         const int buf = i & 1;
@@ -349,9 +383,9 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
           const uint32_t b0 = a0 + C::A_TILE;
 #pragma unroll
           for (int k = 0; k < kBK / kUK; ++k) {
-            const uint64_t da = A_MN ? desc_mnmajor_sw128(a0 + k * kUK * 128, 64 * 128) : desc_kmajor_sw128(a0 + k * kUK * 2);
-            const uint64_t db = B_MN ? desc_mnmajor_sw128(b0 + k * kUK * 128, 64 * 128) : desc_kmajor_sw128(b0 + k * kUK * 2);
-            umma_bf16(tmem_d + buf * BN, da, db, idesc, (kb | k) != 0);
+            const uint64_t da = A_MN ? desc_mnmajor_sw128(a0 + k * kUK * 128, kBK * 128) : desc_kmajor_sw128(a0 + k * 32);
+            const uint64_t db = B_MN ? desc_mnmajor_sw128(b0 + k * kUK * 128, kBK * 128) : desc_kmajor_sw128(b0 + k * 32);
+            umma<TF32>(tmem_d + buf * BN, da, db, idesc, (kb | k) != 0);
           }
           umma_commit(&empty[s]);
         }
@@ -386,7 +420,7 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
           const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
           const int gm = m0 + quad * 32 + row, gn = n0 + cb + col;
           if (gm < M && gn < N) {
-            const float4 o = *reinterpret_cast<const float4*>(stg + row * C::STG_LD + col);
+            const float4 o = apply_epi(*reinterpret_cast<const float4*>(stg + row * C::STG_LD + col), epi, gn);
             if (out_bf16) {
               const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
               uint2 pk;
@@ -413,100 +447,109 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
   }
 }
 
-// 2-D bf16 tensor map with SWIZZLE_128B: dims (inner [contiguous], outer), outer stride ld elements, box (64, box_outer)
-int make_tmap_2d(CUtensorMap* m, const void* base, long inner, long outer, long ld, int box_outer) {
+// 2-D tensor map with SWIZZLE_128B: dims (inner [contiguous], outer), outer stride ld elements, box (128 bytes, box_outer)
+int make_tmap_2d(CUtensorMap* m, const void* base, long inner, long outer, long ld, int box_outer, bool tf32) {
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SIM_ERR_CUDA;
   }
+  const int es = tf32 ? 4 : 2;
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (bf16 2-D) failed with CUresult %d (inner=%ld outer=%ld ld=%ld box=%d)", (int)r, inner,
-              outer, ld, box_outer);
+    set_error("cuTensorMapEncodeTiled (2-D operand) failed with CUresult %d (inner=%ld outer=%ld ld=%ld box=%d es=%d)", (int)r,
+              inner, outer, ld, box_outer, es);
     return SIM_ERR_CUDA;
   }
   return SIM_OK;
 }
 
-template <int BN, int NSTAGE, bool A_MN, bool B_MN>
-int launch(const Tmaps& tm, void* Y, long ldd, int M, int N, int K, int out_bf16, int splits, cudaStream_t stream) {
+struct Problem {
+  Tmaps tm;
+  void* Y;
+  long ldd;
+  int M, N, K, out_bf16, splits;
+  Epi epi;
+};
+
+template <int BN, int NSTAGE, bool A_MN, bool B_MN, bool TF32>
+int launch(const Problem& q, cudaStream_t stream) {
   using C = Cfg<BN, NSTAGE>;
-  auto kern = gemm_bf16_kernel<BN, NSTAGE, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, NSTAGE, A_MN, B_MN, TF32>;
   static SmemAttrCache attr;
-  if (ensure_dyn_smem(kern, C::SMEM, attr) != cudaSuccess) return check_launch("gemm_bf16 attr");
-  const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + kBM - 1) / kBM;
-  const int nk_all = (K + kBK - 1) / kBK;
-  const int kb_per_split = (nk_all + splits - 1) / splits;
+  if (ensure_dyn_smem(kern, C::SMEM, attr) != cudaSuccess) return check_launch("gemm_tc attr");
+  const int n_tiles = (q.N + BN - 1) / BN;
+  const int m_tiles = (q.M + kBM - 1) / kBM;
+  const int nk_all = (q.K + El<TF32>::BK - 1) / El<TF32>::BK;
+  const int kb_per_split = (nk_all + q.splits - 1) / q.splits;
   const int ny = (nk_all + kb_per_split - 1) / kb_per_split;
-  kern<<<dim3(m_tiles * n_tiles, ny), 192, C::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, out_bf16, kb_per_split);
-  return check_launch("gemm_bf16");
+  kern<<<dim3(m_tiles * n_tiles, ny), 192, C::SMEM, stream>>>(q.tm, q.Y, q.ldd, q.M, q.N, q.K, n_tiles, q.out_bf16, kb_per_split,
+                                                               q.epi);
+  return check_launch("gemm_tc");
 }
 
-template <int BN, int NSTAGE, bool A_MN, bool B_MN>
-int launch_persistent(const Tmaps& tm, void* Y, long ldd, int M, int N, int K, int out_bf16, cudaStream_t stream) {
+template <int BN, int NSTAGE, bool A_MN, bool B_MN, bool TF32>
+int launch_persistent(const Problem& q, cudaStream_t stream) {
   using C = PCfg<BN, NSTAGE>;
-  auto kern = gemm_bf16_persistent_kernel<BN, NSTAGE, A_MN, B_MN>;
+  auto kern = gemm_bf16_persistent_kernel<BN, NSTAGE, A_MN, B_MN, TF32>;
   static SmemAttrCache attr;
-  if (ensure_dyn_smem(kern, C::SMEM, attr) != cudaSuccess) return check_launch("gemm_bf16_persistent attr");
-  const int n_tiles = (N + BN - 1) / BN;
-  const int total = ((M + kBM - 1) / kBM) * n_tiles;
+  if (ensure_dyn_smem(kern, C::SMEM, attr) != cudaSuccess) return check_launch("gemm_tc_persistent attr");
+  const int n_tiles = (q.N + BN - 1) / BN;
+  const int total = ((q.M + kBM - 1) / kBM) * n_tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static int sm_count[64] = {};
   if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   if (sm_count[dev & 63] > 0) sms = sm_count[dev & 63];
-  kern<<<std::min(total, sms), C::NT, C::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total, out_bf16);
-  return check_launch("gemm_bf16_persistent");
+  kern<<<std::min(total, sms), C::NT, C::SMEM, stream>>>(q.tm, q.Y, q.ldd, q.M, q.N, q.K, n_tiles, total, q.out_bf16, q.epi);
+  return check_launch("gemm_tc_persistent");
 }
 
-template <bool A_MN, bool B_MN>
-int dispatch(const Tmaps& tm, void* Y, long ldd, int M, int N, int K, int out_bf16, int splits, int bn, cudaStream_t stream) {
+template <bool A_MN, bool B_MN, bool TF32>
+int dispatch(const Problem& q, int bn, cudaStream_t stream) {
   static const int persist = [] { const char* e = getenv("SIM_GEMM_BF16_PERSIST"); return e ? atoi(e) : 1; }();
-  if (splits == 1 && persist) {
+  if (q.splits == 1 && persist) {
     switch (bn) {
-      case 64: return launch_persistent<64, 6, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, stream);
-      case 128: return launch_persistent<128, 5, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, stream);
-      case 192: return launch_persistent<192, 4, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, stream);
-      default: return launch_persistent<256, 3, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, stream);
+      case 64: return launch_persistent<64, 6, A_MN, B_MN, TF32>(q, stream);
+      case 128: return launch_persistent<128, 5, A_MN, B_MN, TF32>(q, stream);
+      case 192: return launch_persistent<192, 4, A_MN, B_MN, TF32>(q, stream);
+      default: return launch_persistent<256, 3, A_MN, B_MN, TF32>(q, stream);
     }
   }
   switch (bn) {
-    case 64: return launch<64, 6, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, splits, stream);
-    case 128: return launch<128, 5, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, splits, stream);
-    default: return launch<256, 4, A_MN, B_MN>(tm, Y, ldd, M, N, K, out_bf16, splits, stream);
+    case 64: return launch<64, 6, A_MN, B_MN, TF32>(q, stream);
+    case 128: return launch<128, 5, A_MN, B_MN, TF32>(q, stream);
+    default: return launch<256, 4, A_MN, B_MN, TF32>(q, stream);
   }
 }
 
-}  // namespace
-
-// Y[M,N] = op(A) . op(B)^T with bf16 operands and fp32 accumulation.
-//   a_mn = 0: A is (M, K) row-major with row stride lda (K-major);  a_mn = 1: A is (K, M) row-major (MN-major)
-//   b_mn = 0: B is (N, K) row-major with row stride ldb (K-major);  b_mn = 1: B is (K, N) row-major (MN-major)
-//   out_bf16: Y bf16 (row stride ldd), else fp32.  splits > 1: split-K, partial tiles are ADDED to a zeroed fp32 Y.
-int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
-              int N, int K, int splits, cudaStream_t stream) {
-  SIM_REQUIRE(A && B && Y && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_bf16: empty problem / null tensor");
-  SIM_REQUIRE(aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0, SIM_ERR_ALIGN,
-              "gemm_bf16: TMA needs 16-byte aligned operand bases and row strides (lda=%ld ldb=%ld)", lda, ldb);
-  SIM_REQUIRE(N % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & (out_bf16 ? 7u : 15u)) == 0, SIM_ERR_ALIGN,
-              "gemm_bf16: the epilogue stores 4 columns at a time (N=%d ldd=%ld)", N, ldd);
+template <bool TF32>
+int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
+             int N, int K, int splits, const float* bias, int relu, cudaStream_t stream) {
+  constexpr int ES = El<TF32>::ES, BK = El<TF32>::BK;
+  SIM_REQUIRE(A && B && Y && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_tc: empty problem / null tensor");
+  SIM_REQUIRE(!TF32 || (!a_mn && !b_mn), SIM_ERR_INVALID, "gemm_tf32: only K-major operands ((M,K) and (N,K) row-major) are built");
+  SIM_REQUIRE(aligned16(A) && aligned16(B) && (lda * ES) % 16 == 0 && (ldb * ES) % 16 == 0, SIM_ERR_ALIGN,
+              "gemm_tc: TMA needs 16-byte aligned operand bases and row strides (lda=%ld ldb=%ld)", lda, ldb);
+  SIM_REQUIRE(N % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & (out_bf16 ? 7u : 15u)) == 0 &&
+                  (!bias || aligned16(bias)),
+              SIM_ERR_ALIGN, "gemm_tc: the epilogue stores 4 columns at a time (N=%d ldd=%ld)", N, ldd);
   const int m_tiles = (M + kBM - 1) / kBM;
   if (splits <= 0) {
-    // automatic split-K (weight gradients: few output tiles, a contraction over every token): about two waves of CTAs, at
-    // least four 64-deep k-blocks per CTA.  The caller zeroes the fp32 output.
+    // automatic split-K (weight gradients: few output tiles, a contraction over every token): at most two full waves of
+    // CTAs, at least four k-blocks per CTA.  The caller zeroes the fp32 output.
     const long tiles = (long)m_tiles * ((N + 127) / 128);
-    const int nk_all = (K + kBK - 1) / kBK;
-    splits = (int)std::max<long>(1, std::min<long>(296 / tiles, nk_all / 4));  // at most two full waves of CTAs
+    const int nk_all = (K + BK - 1) / BK;
+    splits = (int)std::max<long>(1, std::min<long>(296 / tiles, nk_all / 4));
   }
-  SIM_REQUIRE(splits == 1 || !out_bf16, SIM_ERR_INVALID, "gemm_bf16: split-K accumulates into an fp32 output");
+  SIM_REQUIRE(splits == 1 || (!out_bf16 && !bias && !relu), SIM_ERR_INVALID,
+              "gemm_tc: split-K accumulates into an fp32 output and has no bias / ReLU epilogue");
   int bn = 64;
   if (N > 64) {
     long best = -1;
@@ -519,16 +562,40 @@ int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_
       if (best < 0 || cost < best) best = cost, bn = cand;
     }
   }
-  Tmaps tm;
+  Problem q;
+  q.Y = Y, q.ldd = ldd, q.M = M, q.N = N, q.K = K, q.out_bf16 = out_bf16, q.splits = splits;
+  q.epi.bias = bias, q.epi.relu = relu;
   int rc;
-  if (a_mn) rc = make_tmap_2d(&tm.a, A, M, K, lda, kBK); else rc = make_tmap_2d(&tm.a, A, K, M, lda, kBM);
+  if (a_mn) rc = make_tmap_2d(&q.tm.a, A, M, K, lda, BK, TF32); else rc = make_tmap_2d(&q.tm.a, A, K, M, lda, kBM, TF32);
   if (rc) return rc;
-  if (b_mn) rc = make_tmap_2d(&tm.b, B, N, K, ldb, kBK); else rc = make_tmap_2d(&tm.b, B, K, N, ldb, bn);
+  if (b_mn) rc = make_tmap_2d(&q.tm.b, B, N, K, ldb, BK, TF32); else rc = make_tmap_2d(&q.tm.b, B, K, N, ldb, bn, TF32);
   if (rc) return rc;
-  if (a_mn) return b_mn ? dispatch<true, true>(tm, Y, ldd, M, N, K, out_bf16, splits, bn, stream)
-                        : dispatch<true, false>(tm, Y, ldd, M, N, K, out_bf16, splits, bn, stream);
-  return b_mn ? dispatch<false, true>(tm, Y, ldd, M, N, K, out_bf16, splits, bn, stream)
-              : dispatch<false, false>(tm, Y, ldd, M, N, K, out_bf16, splits, bn, stream);
+  if constexpr (TF32) {
+    // 32-bit MN-major operands need the SWIZZLE_128B_BASE32B atom (a different tile layout and TMA swizzle mode); the TF32
+    // uses of this kernel (inference convolutions of the Encoder) are K-major on both sides, so only that form is built
+    return dispatch<false, false, true>(q, bn, stream);
+  } else {
+    if (a_mn) return b_mn ? dispatch<true, true, false>(q, bn, stream) : dispatch<true, false, false>(q, bn, stream);
+    return b_mn ? dispatch<false, true, false>(q, bn, stream) : dispatch<false, false, false>(q, bn, stream);
+  }
+}
+
+}  // namespace
+
+// Y[M,N] = op(A) . op(B)^T (+ bias[N], ReLU) on the tensor cores, fp32 accumulation.
+//   a_mn = 0: A is (M, K) row-major with row stride lda (K-major);  a_mn = 1: A is (K, M) row-major (MN-major)
+//   b_mn = 0: B is (N, K) row-major with row stride ldb (K-major);  b_mn = 1: B is (K, N) row-major (MN-major)
+//   out_bf16: Y bf16 (row stride ldd), else fp32.  splits > 1: split-K, partial tiles are ADDED to a zeroed fp32 Y.
+// gemm_bf16: bf16 operands (kind::f16).  gemm_tf32: fp32 operands consumed as TF32 (kind::tf32 reads the upper 19 bits) -
+// the precision the reference's Conv1d layers run at under torch's default cudnn.allow_tf32 = True.
+int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
+              int N, int K, int splits, cudaStream_t stream) {
+  return gemm_any<false>(A, lda, a_mn, B, ldb, b_mn, Y, ldd, out_bf16, M, N, K, splits, nullptr, 0, stream);
+}
+
+int gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
+              int N, int K, int splits, const float* bias, int relu, cudaStream_t stream) {
+  return gemm_any<true>(A, lda, a_mn, B, ldb, b_mn, Y, ldd, out_bf16, M, N, K, splits, bias, relu, stream);
 }
 
 }  // namespace sim

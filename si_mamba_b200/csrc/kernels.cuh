@@ -70,6 +70,8 @@ struct ScanBwdParams {
 int selective_scan_bwd(const ScanBwdParams&, int, cudaStream_t);
 int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
               int N, int K, int splits, cudaStream_t stream);
+int gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
+              int N, int K, int splits, const float* bias, int relu, cudaStream_t stream);
 int causal_conv1d_bwd(const void*, long, const float*, const float*, const void*, long, void*, long, float*, float*,
                       int, int, int, int, int, int, cudaStream_t);
 
@@ -121,6 +123,7 @@ int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, c
                       float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream);
 int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream);
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream);
+int point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, cudaStream_t stream);
 int mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1, const float* w2t,
                    const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y, long ldy,
                    cudaStream_t stream);

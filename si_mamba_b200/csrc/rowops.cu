@@ -9,6 +9,8 @@
 //   a-17  MAE token restore                       models/point_mamba.py:3147-3197
 // One warp moves one row with 16-byte vector accesses; rows are C <= 1024*... floats.
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace sim {
@@ -386,6 +388,50 @@ int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cu
     group_max_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
                                                               static_cast<__nv_bfloat16*>(out), groups, M, C);
   return check_launch("group_max");
+}
+
+// y[p, c] = act(b[c] + w[c,0] x[p,0] + w[c,1] x[p,1] + w[c,2] x[p,2]): the 3 -> C first layer of the Encoder (Conv1d(3, 128, 1)
+// with eval-mode BatchNorm folded in, + ReLU; models/point_mamba.py:47-49) and of pos_embed (Linear(3, 128) + GELU, :470-474).
+// K = 3 is no GEMM: a thread computes four adjacent channels of one point with three FMAs each; the output write is the cost.
+template <int ACT>
+__global__ void __launch_bounds__(256) point_linear3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float* __restrict__ y, long rows,
+                                                            int C) {
+  extern __shared__ float s_w[];  // [C][4]: w0, w1, w2, bias
+  for (int i = threadIdx.x; i < C; i += 256) {
+    s_w[4 * i] = w[3 * i], s_w[4 * i + 1] = w[3 * i + 1], s_w[4 * i + 2] = w[3 * i + 2];
+    s_w[4 * i + 3] = b ? b[i] : 0.f;
+  }
+  __syncthreads();
+  const int cq = C / 4;
+  for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < rows * cq; e += (long)gridDim.x * 256) {
+    const long p = e / cq;
+    const int c = (int)(e % cq) * 4;
+    const float px = x[3 * p], py = x[3 * p + 1], pz = x[3 * p + 2];
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 wv = *reinterpret_cast<const float4*>(s_w + 4 * (c + i));
+      float v = fmaf(wv.z, pz, fmaf(wv.y, py, fmaf(wv.x, px, wv.w)));
+      if (ACT == 1) v = fmaxf(v, 0.f);
+      if (ACT == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() (erf form)
+      o[i] = v;
+    }
+    *reinterpret_cast<float4*>(y + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, cudaStream_t stream) {
+  SIM_REQUIRE(x && w && y && rows > 0 && C > 0 && C % 4 == 0 && C <= 2048 && act >= 0 && act <= 2, SIM_ERR_INVALID,
+              "point_linear3: bad arguments");
+  SIM_REQUIRE(aligned16(y), SIM_ERR_ALIGN, "point_linear3: the output must be 16-byte aligned");
+  const long work = rows * (C / 4);
+  const int grid = (int)std::min<long>((work + 255) / 256, 148L * 8);
+  const size_t smem = (size_t)C * 16;
+  if (act == 0) point_linear3_kernel<0><<<grid, 256, smem, stream>>>(x, w, b, y, rows, C);
+  else if (act == 1) point_linear3_kernel<1><<<grid, 256, smem, stream>>>(x, w, b, y, rows, C);
+  else point_linear3_kernel<2><<<grid, 256, smem, stream>>>(x, w, b, y, rows, C);
+  return check_launch("point_linear3");
 }
 
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream) {

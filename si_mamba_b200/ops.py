@@ -266,7 +266,7 @@ def order_gather(x: torch.Tensor, perm: torch.Tensor, reverse: bool = True,
 def order_gather_add(x: torch.Tensor, x2: torch.Tensor, perm: torch.Tensor, reverse: bool = True) -> torch.Tensor:
     """Inference fast path: gather(x)+gather(x2) in one pass (tokens + pos, point_mamba.py:250)."""
     _cuda(x, x2, perm)
-    x, x2, perm = x.contiguous(), x2.contiguous(), perm.contiguous()
+    x, x2, perm = x.contiguous(), x2.to(x.dtype).contiguous(), perm.contiguous()
     B, G, Cc = x.shape
     k = perm.shape[1]
     T = (2 if reverse else 1) * k * G
@@ -658,6 +658,37 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     _lib.call("sim_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out), out.stride(0),
               int(out.dtype == torch.bfloat16), M, N, K, int(splits), _stream())
     return out
+
+
+def gemm_tf32(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+              relu: bool = False, out: Optional[torch.Tensor] = None, splits: int = 1) -> torch.Tensor:
+    """fp32 Y = op(a) @ op(b).T (+ bias, ReLU) with the operands consumed as TF32 on the tcgen05 kernel (sim_gemm_tf32): the
+    Encoder's 1x1 convolutions at the precision torch's default cudnn.allow_tf32 = True gives the reference's Conv1d."""
+    _cuda(a, b, bias, out)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+
+    def operand(t):
+        return t if (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0) else t.contiguous()
+    a, b = operand(a), operand(b)
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    assert K == Kb and (a.stride(0) % 4 == 0) and (b.stride(0) % 4 == 0)
+    if out is None:
+        out = (torch.zeros if splits != 1 else torch.empty)(M, N, dtype=torch.float32, device=a.device)
+    _lib.call("sim_gemm_tf32", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out), out.stride(0), 0, M, N, K,
+              int(splits), _p(_f32c(bias)), int(relu), _stream())
+    return out
+
+
+def point_linear3(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: str = "none") -> torch.Tensor:
+    """y = act(x @ w.T + b) for 3-D points: x (rows, 3), w (C, 3) -> (rows, C) fp32; act in none | relu | gelu (erf)."""
+    _cuda(x, w, b)
+    x, w = _f32c(x), _f32c(w)
+    rows, C = x.shape[0], w.shape[0]
+    assert x.shape[1] == 3 and w.shape[1] == 3
+    y = torch.empty(rows, C, dtype=torch.float32, device=x.device)
+    _lib.call("sim_point_linear3", _p(x), _p(w), _p(_f32c(b)), _p(y), rows, C, {"none": 0, "relu": 1, "gelu": 2}[act], _stream())
+    return y
 
 
 class LinearBF16(torch.autograd.Function):

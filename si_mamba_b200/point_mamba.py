@@ -81,6 +81,22 @@ def _conv_linear(x, w, b=None):
     return _ConvLinear.apply(x, w, b)
 
 
+def _own_linear(x, w, b=None, tf32=None):
+    """Inference F.linear(x (rows, K), w (N, K), b) on the hand-written tcgen05 kernels: TF32 operands with the bias in the
+    epilogue (``tf32`` = None follows torch.backends.cudnn.allow_tf32, the switch of the convolutions these GEMMs stand
+    for), else fp32-accurate on three bf16 planes of each operand (weights split once and cached)."""
+    from .autograd import _CACHE
+    if tf32 is None:
+        tf32 = torch.backends.cudnn.allow_tf32
+    if tf32:
+        return ops.gemm_tf32(x, w.detach(), bias=None if b is None else b.detach())
+    K = w.shape[1]
+    planes = _CACHE.get(w, "x3", lambda t: ops.split3(t.float().contiguous())) if isinstance(w, nn.Parameter) \
+        else ops.split3(w.detach().float().contiguous())
+    y = ops.linear_split3(ops.split3(x), planes, K)
+    return y if b is None else y.add_(b.detach())
+
+
 class Encoder(nn.Module):
     """Per-patch mini-PointNet (models/point_mamba.py:42-73); dense contractions stay on cuDNN / cuBLAS."""
 
@@ -104,28 +120,26 @@ class Encoder(nn.Module):
         return _CACHE.get_multi(conv.weight, "bn_fold", deps, fold)
 
     def _forward_eval(self, point_groups):
-        """Inference form of forward(): the same arithmetic written as row-major GEMMs on the (B*G*M, C) point
-        matrix with BatchNorm folded into the weights, and the `cat([global, local])` conv split into a per-point
-        and a per-patch GEMM (W3 = [W3_global | W3_local]) so the global half is computed once per patch instead of
-        once per point.  These GEMMs ARE the reference's convolutions, so they follow the cuDNN TF32 policy."""
+        """Inference form of forward() on own kernels only: the same arithmetic written as row-major GEMMs on the
+        (B*G*M, C) point matrix with BatchNorm folded into the weights, and the `cat([global, local])` conv split into a
+        per-point and a per-patch GEMM (W3 = [W3_global | W3_local]) so the global half is computed once per patch instead
+        of once per point.  Conv1d(3, 128) + BN + ReLU is a 3-FMA row kernel (sim_point_linear3); the other convolutions run
+        on the hand-written tcgen05 kernel: as TF32 with the bias in its epilogue (sim_gemm_tf32) when
+        torch.backends.cudnn.allow_tf32 is on - these GEMMs ARE the reference's convolutions, so they follow cuDNN's
+        switch, True by default - and fp32-accurate on three bf16 planes (sim_gemm_bf16x3) when it is off."""
         bs, g, n, _ = point_groups.shape
-        BG, P = bs * g, bs * g * n
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-        try:
-            x = point_groups.reshape(P, 3)
-            w1, b1 = self._fold_bn(self.first_conv[0], self.first_conv[1])
-            h = F.relu(F.linear(x, w1, b1))
-            f = F.linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)          # (P, 256)
-            w3, b3 = self._fold_bn(self.second_conv[0], self.second_conv[1])
-            c_loc = f.shape[-1]
-            # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
-            fg = ops.group_max(f, n)                                                            # (BG, 256)
-            h2 = ops.group_bias_relu_(F.linear(f, w3[:, c_loc:]), F.linear(fg, w3[:, :c_loc], b3), n)
-            o = F.linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)    # (P, C)
-            return ops.group_max(o, n).view(bs, g, self.encoder_channel)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        P = bs * g * n
+        x = point_groups.reshape(P, 3)
+        w1, b1 = self._fold_bn(self.first_conv[0], self.first_conv[1])
+        h = ops.point_linear3(x, w1, b1, "relu")                                                # (P, 128)
+        f = _own_linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)         # (P, 256)
+        w3, b3 = self._fold_bn(self.second_conv[0], self.second_conv[1])
+        c_loc = f.shape[-1]
+        # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
+        fg = ops.group_max(f, n)                                                                # (BG, 256)
+        h2 = ops.group_bias_relu_(_own_linear(f, w3[:, c_loc:], None), _own_linear(fg, w3[:, :c_loc], b3), n)
+        o = _own_linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)      # (P, C)
+        return ops.group_max(o, n).view(bs, g, self.encoder_channel)
 
     def _forward_rows(self, point_groups):
         """Differentiable form of forward() on the (B*G*M, C) point matrix: the 1x1 convolutions as row-major linears
@@ -365,6 +379,19 @@ class PointMamba(nn.Module):
         w1t, b1, w2t, b2, w3t, b3 = _CACHE.get_multi(h[0].weight, "head_fold", deps, fold)
         return ops.mlp3_relu_rows(f.contiguous(), w1t, b1, w2t, b2, w3t, b3)
 
+    def _pos_embed(self, center):
+        """pos_embed (models/point_mamba.py:470-474, 847): Linear(3, 128) + GELU + Linear(128, C).  Inference in fp32 runs on
+        own kernels - a 3-FMA row kernel with the GELU, then the tcgen05 GEMM (fp32-accurate unless
+        torch.backends.cuda.matmul.allow_tf32 is on, the switch nn.Linear follows); otherwise nn.Sequential."""
+        pe = self.pos_embed
+        if (self.training or torch.is_grad_enabled() or not center.is_cuda or center.dtype != torch.float32
+                or torch.is_autocast_enabled() or len(pe) != 3 or pe[0].in_features != 3 or not isinstance(pe[1], nn.GELU)
+                or getattr(pe[1], "approximate", "none") != "none"):
+            return pe(center)
+        h = ops.point_linear3(center.reshape(-1, 3), pe[0].weight, pe[0].bias, "gelu")
+        out = _own_linear(h, pe[2].weight, pe[2].bias, tf32=torch.backends.cuda.matmul.allow_tf32)
+        return out.view(*center.shape[:-1], pe[2].out_features)
+
     def spectral_order(self, center):
         """centres -> dict(vals, vecs, perm, inv_perm): graph + Laplacian + eigensolver + argsort in one kernel
         (replaces create_graph_* + calc_top_k_eigenvalues_eigenvectors* + the sorts, point_mamba.py:872-898)."""
@@ -423,7 +450,7 @@ class PointMamba(nn.Module):
             with torch.cuda.stream(side):
                 spec = self.spectral_order(center)
         group_input_tokens = self.encoder(neighborhood)
-        pos = self.pos_embed(center)
+        pos = self._pos_embed(center)
         if spec is not None:
             cur.wait_stream(side)
             for t in spec.values():

@@ -631,3 +631,31 @@ def test_linear_bf16_autograd(ops):
         assert rel_err(y.detach().cpu().float(), (xr @ wr.t()).detach()) < 6e-3
         assert wc.grad.dtype == torch.float32 and rel_err(wc.grad.cpu(), wr.grad) < 1e-4
         assert rel_err(xc.grad.cpu().float()[:, :K], xr.grad) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(65536, 256, 128), (2048, 512, 256), (4096, 384, 512), (100, 64, 36), (300, 200, 40)])
+def test_gemm_tf32_bias_relu(ops, M, N, K):
+    """sim_gemm_tf32 (tcgen05 kind::tf32 on fp32 operands, bias + ReLU epilogue) vs the fp64 product of the operands
+    truncated to TF32 (the unit reads the upper 19 bits); split-K; MN-major operands are rejected."""
+    g = torch.Generator().manual_seed(M + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * K ** -0.5, torch.randn(N, generator=g)
+    trunc = lambda t: (t.view(torch.int32) & ~0x1fff).view(torch.float32)
+    ref = trunc(x).double() @ trunc(w).double().t()
+    scale = ref.abs().max()
+    y = ops.gemm_tf32(dev(x), dev(w))
+    assert (y.cpu().double() - ref).abs().max() / scale < 2e-5
+    assert (y.cpu().double() - x.double() @ w.double().t()).abs().max() / scale < 3e-3   # TF32 vs exact
+    yb = ops.gemm_tf32(dev(x), dev(w), bias=dev(b), relu=True)
+    assert (yb.cpu().double() - torch.relu(ref + b.double())).abs().max() / scale < 2e-5
+    y4 = ops.gemm_tf32(dev(x), dev(w), splits=0)
+    assert (y4.cpu().double() - ref).abs().max() / scale < 2e-5
+    with pytest.raises(Exception):
+        ops.gemm_tf32(dev(x), dev(w.t().contiguous()), b_mn=True)
+
+
+def test_point_linear3(ops):
+    g = torch.Generator().manual_seed(3)
+    x, w, b = torch.randn(5000, 3, generator=g), torch.randn(128, 3, generator=g), torch.randn(128, generator=g)
+    for act, fn in (("none", lambda t: t), ("relu", torch.relu), ("gelu", torch.nn.functional.gelu)):
+        y = ops.point_linear3(dev(x), dev(w), dev(b), act)
+        assert torch.allclose(y.cpu(), fn(torch.nn.functional.linear(x, w, b)), rtol=1e-5, atol=1e-5)
