@@ -287,6 +287,17 @@ int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_ou
 
 /* Producers that emit the split operand directly (fp32 activations), so no separate split pass is needed:
  * LayerNorm output -> in_proj, conv output (fp32 u for the scan AND planes for x_proj), scan output -> out_proj. */
+/* a-9 with DropPath folded in (training; models/block.py:59 `residual = self.drop_path(hidden_states) + residual`, timm
+ * drop_path = x / keep * mask per sample): res_out = row_scale[row / rows_per_sample] * x + res_in, y = LN(res_out).
+ * row_scale (samples) f32 = mask_b / keep_prob, or NULL (then identical to sim_add_layernorm without x2).
+ * sim_add_layernorm_bwd_dx: sim_add_layernorm_bwd that also writes dx = row_scale * dres in x's dtype (dtype_dx; the
+ * gradient of the x operand), so the backward needs neither a cast nor the DropPath multiply; row_scale may be NULL. */
+int sim_add_layernorm_droppath(const void* x, const float* row_scale, int rows_per_sample, const float* res_in,
+                               const float* gamma, const float* beta, float* res_out, void* y, long rows, int C, float eps,
+                               int dtype_x, int dtype_y, sim_stream_t stream);
+int sim_add_layernorm_bwd_dx(const float* res, const void* dy, const float* dres_out, const float* gamma,
+                             const float* row_scale, int rows_per_sample, float* dres, void* dx, int dtype_dx, float* dgamma,
+                             float* dbeta, long rows, int C, float eps, int dtype_y, sim_stream_t stream);
 int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
                              float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
                              sim_stream_t stream);

@@ -34,9 +34,17 @@ class DropPath(nn.Module):
         mask = (keep + torch.rand(shape, dtype=x.dtype, device=x.device)).floor_()
         return x.div(keep) * mask
 
+    def sample_scale(self, x):
+        """The per-sample factor mask / keep of forward(), (B,) fp32, drawn exactly like forward() draws its mask (same
+        shape, dtype and generator state), for kernels that fold DropPath in."""
+        keep = 1.0 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+        mask = (keep + torch.rand(shape, dtype=x.dtype, device=x.device)).floor_()
+        return (mask.float() / keep).reshape(-1)
+
 
 def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor], want_residual: bool = True,
-                   split: bool = False):
+                   split: bool = False, row_scale: Optional[Tensor] = None):
     """(LayerNorm(hidden + residual), hidden + residual) through the CUDA kernel when no autograd graph is
     needed; plain torch ops (so autograd works) when training."""
     needs_grad = torch.is_grad_enabled() and (hidden.requires_grad or (residual is not None and residual.requires_grad)
@@ -49,7 +57,9 @@ def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor
         res = res.float() if res.dtype != torch.float32 else res
         return norm(res.to(dtype=norm.weight.dtype)), res
     if needs_grad:  # training: same forward kernel, backward through sim_add_layernorm_bwd
-        return ops.AddLayerNorm.apply(hidden, residual, norm.weight, norm.bias, norm.eps, _amp_dtype(hidden))
+        return ops.AddLayerNorm.apply(hidden, residual, norm.weight, norm.bias, norm.eps, _amp_dtype(hidden), row_scale)
+    if row_scale is not None:  # DropPath without a graph (train mode under no_grad): plain scaling, then the kernel
+        hidden = hidden * row_scale.view(-1, *([1] * (hidden.dim() - 1))).to(hidden.dtype)
     out_dtype = _amp_dtype(hidden)
     return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=out_dtype,
                              want_residual=want_residual, split=split and out_dtype == torch.float32)
@@ -70,9 +80,16 @@ class Block(nn.Module):
         # fp32 inference: LayerNorm writes the in_proj operand (three bf16 planes) directly, see autograd.wants_split3
         want = getattr(self.mixer, "wants_split3", None)
         split = bool(want and want(hidden_states))
-        # block.py:59: `drop_path(h) + residual if residual is not None else h` - the first block's input is never dropped
-        h = self.drop_path(hidden_states) if residual is not None else hidden_states
-        hidden_states, residual = fused_add_norm(self.norm, h, residual, split=split)
+        # block.py:59: `drop_path(h) + residual if residual is not None else h` - the first block's input is never dropped.
+        # The per-sample factor mask / keep goes into the add + LayerNorm kernels (forward and backward) as row_scale.
+        scale = None
+        h = hidden_states
+        if residual is not None and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0. and self.training:
+            if hidden_states.is_cuda and hidden_states.dim() == 3 and isinstance(self.norm, nn.LayerNorm):
+                scale = self.drop_path.sample_scale(hidden_states)
+            else:
+                h = self.drop_path(hidden_states)
+        hidden_states, residual = fused_add_norm(self.norm, h, residual, split=split, row_scale=scale)
         hidden_states = self.mixer(hidden_states, inference_params=inference_params)
         return hidden_states, residual
 

@@ -359,6 +359,20 @@ int sim_group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int 
   return sim::group_bias_relu(x, gvec, rows, M, C, dtype, static_cast<cudaStream_t>(stream));
 }
 
+int sim_add_layernorm_droppath(const void* x, const float* row_scale, int rows_per_sample, const float* res_in,
+                               const float* gamma, const float* beta, float* res_out, void* y, long rows, int C, float eps,
+                               int dtype_x, int dtype_y, sim_stream_t stream) {
+  return sim::add_layernorm(x, nullptr, res_in, gamma, beta, res_out, y, rows, C, eps, dtype_x, dtype_y,
+                            static_cast<cudaStream_t>(stream), nullptr, 0, row_scale, rows_per_sample);
+}
+
+int sim_add_layernorm_bwd_dx(const float* res, const void* dy, const float* dres_out, const float* gamma,
+                             const float* row_scale, int rows_per_sample, float* dres, void* dx, int dtype_dx, float* dgamma,
+                             float* dbeta, long rows, int C, float eps, int dtype_y, sim_stream_t stream) {
+  return sim::add_layernorm_bwd(res, dy, dres_out, gamma, dres, dgamma, dbeta, rows, C, eps, dtype_y,
+                                static_cast<cudaStream_t>(stream), dx, dtype_dx, row_scale, rows_per_sample);
+}
+
 int sim_point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, sim_stream_t stream) {
   return sim::point_linear3(x, w, b, y, rows, C, act, static_cast<cudaStream_t>(stream));
 }

@@ -9,7 +9,8 @@ namespace sim {
 int fps(const float*, int, int, int, int*, float*, cudaStream_t, int pointnet2 = 0, int fma = 0);
 int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t, int fma = 0);
 int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
-                  int, int, cudaStream_t, void* planes = nullptr, long plane = 0);
+                  int, int, cudaStream_t, void* planes = nullptr, long plane = 0, const float* row_scale = nullptr,
+                  int rows_per_sample = 0);
 int order_gather_fwd(const void*, const void*, const int*, void*, void*, int, int, int, int, int, int, cudaStream_t);
 int order_gather_bwd(const void*, const int*, void*, int, int, int, int, int, int, cudaStream_t);
 int gather_rows(const void*, const int*, const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -120,7 +121,8 @@ int chamfer_l2_fwd(const float* x, const float* y, long R, int P, int Q, float* 
 int chamfer_l2_bwd(const float* x, const float* y, const int* idx_x, const int* idx_y, const float* gloss, long R, int P,
                    int Q, float* dx, float* dy, cudaStream_t stream);
 int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, const float* gamma, float* dres,
-                      float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream);
+                      float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream,
+                      void* dx = nullptr, int dtype_dx = 0, const float* row_scale = nullptr, int rows_per_sample = 0);
 int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream);
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream);
 int point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, cudaStream_t stream);

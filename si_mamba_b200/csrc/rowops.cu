@@ -59,11 +59,14 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
                                                             const float* __restrict__ beta,
                                                             float* __restrict__ res_out, TY* __restrict__ y,
                                                             long rows, int C, float eps,
-                                                            __nv_bfloat16* __restrict__ planes, long plane) {
+                                                            __nv_bfloat16* __restrict__ planes, long plane,
+                                                            const float* __restrict__ row_scale, int rows_per_sample) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nv = C / 4;
+  // DropPath folded in (models/block.py:59, timm drop_path): x is scaled by mask_b / keep of its sample before the add
+  const float sc = row_scale ? row_scale[row / rows_per_sample] : 1.f;
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
     const int q = lane + 32 * i;
     if (q < nv) {
       float4 a = ld4<TX>(x + row * C + 4 * q);
+      if (row_scale) a.x *= sc, a.y *= sc, a.z *= sc, a.w *= sc;
       if (x2) {
         const float4 c = ld4<TX>(x2 + row * C + 4 * q);
         a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
@@ -114,7 +118,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
 
 int add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
                   float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
-                  cudaStream_t stream, void* planes, long plane) {
+                  cudaStream_t stream, void* planes, long plane, const float* row_scale, int rows_per_sample) {
+  SIM_REQUIRE(!row_scale || rows_per_sample > 0, SIM_ERR_INVALID, "add_layernorm: row_scale needs rows_per_sample > 0");
   SIM_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
               "add_layernorm: C must be a multiple of 4 and <= 1024 (got %d)", C);
   SIM_REQUIRE(x && gamma && beta && (y || planes), SIM_ERR_INVALID, "add_layernorm: null tensor");
@@ -128,7 +133,8 @@ int add_layernorm(const void* x, const void* x2, const float* res_in, const floa
   add_layernorm_kernel<TX, TY, MAXV><<<grid, 256, 0, stream>>>(static_cast<const TX*>(x),                    \
                                                                static_cast<const TX*>(x2), res_in, gamma,    \
                                                                beta, res_out, static_cast<TY*>(y), rows, C, eps,  \
-                                                               static_cast<__nv_bfloat16*>(planes), plane)
+                                                               static_cast<__nv_bfloat16*>(planes), plane, row_scale, \
+                                                               rows_per_sample)
 #define SIM_LN_MAXV(TX, TY)                     \
   if (C <= 384) {                               \
     SIM_LN_LAUNCH(TX, TY, 3);                   \
@@ -167,7 +173,9 @@ __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float* __r
                                                                 const float* __restrict__ dres_out,
                                                                 const float* __restrict__ gamma, float* __restrict__ dres,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                long rows, int C, float eps) {
+                                                                long rows, int C, float eps, void* __restrict__ dx,
+                                                                int dtype_dx, const float* __restrict__ row_scale,
+                                                                int rows_per_sample) {
   extern __shared__ float s_red[];  // 2 * C
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = C / 4;
@@ -229,6 +237,12 @@ __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float* __r
           o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
         }
         *reinterpret_cast<float4*>(dres + row * C + 4 * q) = o;
+        if (dx) {  // gradient of the x operand in its own dtype, with the DropPath scale of its sample
+          const float sc = row_scale ? row_scale[row / rows_per_sample] : 1.f;
+          o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+          if (dtype_dx == 0) st4<float>(static_cast<float*>(dx) + row * C + 4 * q, o);
+          else st4<__nv_bfloat16>(static_cast<__nv_bfloat16*>(dx) + row * C + 4 * q, o);
+        }
       }
     }
   }
@@ -250,7 +264,10 @@ __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float* __r
 }
 
 int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, const float* gamma, float* dres,
-                      float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream) {
+                      float* dgamma, float* dbeta, long rows, int C, float eps, int dtype_y, cudaStream_t stream, void* dx,
+                      int dtype_dx, const float* row_scale, int rows_per_sample) {
+  SIM_REQUIRE((!row_scale || (dx && rows_per_sample > 0)) && (!dx || (aligned16(dx) && (dtype_dx == 0 || dtype_dx == 1))),
+              SIM_ERR_INVALID, "add_layernorm_bwd: row_scale needs dx and rows_per_sample; dx must be aligned fp32 / bf16");
   SIM_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
               "add_layernorm_bwd: C must be a multiple of 4 and <= 1024 (got %d)", C);
   SIM_REQUIRE(res && dy && gamma && dres && dgamma && dbeta, SIM_ERR_INVALID, "add_layernorm_bwd: null tensor");
@@ -261,7 +278,8 @@ int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, c
   const size_t smem = (size_t)2 * C * sizeof(float);
 #define SIM_LNB_LAUNCH(TY, MAXV)                                                                                  \
   add_layernorm_bwd_kernel<TY, MAXV><<<grid, 256, smem, stream>>>(res, static_cast<const TY*>(dy), dres_out, gamma, \
-                                                                  dres, dgamma, dbeta, rows, C, eps)
+                                                                  dres, dgamma, dbeta, rows, C, eps, dx, dtype_dx,   \
+                                                                  row_scale, rows_per_sample)
 #define SIM_LNB_MAXV(TY)      \
   if (C <= 384) {             \
     SIM_LNB_LAUNCH(TY, 3);    \

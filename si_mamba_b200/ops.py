@@ -548,15 +548,30 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
 
 # ----------------------------------------------------------------------------- fp32 GEMM on tensor cores (a-10)
 class AddLayerNorm(torch.autograd.Function):
-    """(y, res) = (LayerNorm(x + residual), x + residual) with the residual stream in fp32: sim_add_layernorm forward,
-    sim_add_layernorm_bwd backward (statistics recomputed from ``res``, which autograd keeps alive anyway)."""
+    """(y, res) = (LayerNorm(s * x + residual), s * x + residual) with the residual stream in fp32: sim_add_layernorm
+    forward, sim_add_layernorm_bwd backward (statistics recomputed from ``res``, which autograd keeps alive anyway).
+    ``row_scale`` (B,) fp32 or None is the DropPath factor of each sample (mask / keep, block.py:59), applied to x inside
+    the kernels - forward and backward - instead of two elementwise passes each way."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, eps, out_dtype):
-        y, res = add_layernorm(x, residual, weight, bias, eps, out_dtype=out_dtype, want_residual=True)
-        ctx.save_for_backward(res, weight)
+    def forward(ctx, x, residual, weight, bias, eps, out_dtype, row_scale=None):
+        if row_scale is None:
+            y, res = add_layernorm(x, residual, weight, bias, eps, out_dtype=out_dtype, want_residual=True)
+        else:
+            _cuda(x, residual, weight, bias, row_scale)
+            x = x.contiguous()
+            C = x.shape[-1]
+            rows = x.numel() // C
+            assert x.dim() == 3 and row_scale.numel() == x.shape[0] and row_scale.dtype == torch.float32
+            res = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+            r_in = None if residual is None else residual.float().contiguous()
+            _lib.call("sim_add_layernorm_droppath", _p(x), _p(row_scale.contiguous()), x.shape[1], _p(r_in),
+                      _p(_f32c(weight)), _p(_f32c(bias)), _p(res), _p(y), rows, C, float(eps), _dt(x), _dt(y), _stream())
+        ctx.save_for_backward(res, weight, row_scale)
         ctx.eps = eps
         ctx.x_dtype = x.dtype
+        ctx.rows_per_sample = x.shape[1] if x.dim() == 3 else 0
         ctx.res_dtype = None if residual is None else residual.dtype
         ctx.wdtype = weight.dtype
         ctx.mark_non_differentiable()
@@ -564,20 +579,24 @@ class AddLayerNorm(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dres_out):
-        res, weight = ctx.saved_tensors
+        res, weight, row_scale = ctx.saved_tensors
         C = res.shape[-1]
         rows = res.numel() // C
         dy = dy.contiguous()
         if dres_out is not None:
             dres_out = dres_out.float().contiguous()
         dres = torch.empty_like(res)
-        dg = torch.zeros(C, dtype=torch.float32, device=res.device)
-        db = torch.zeros(C, dtype=torch.float32, device=res.device)
-        _lib.call("sim_add_layernorm_bwd", _p(res), _p(dy), _p(dres_out), _p(_f32c(weight)), _p(dres), _p(dg), _p(db),
-                  rows, C, float(ctx.eps), _dt(dy), _stream())
-        dx = dres if ctx.x_dtype == torch.float32 else dres.to(ctx.x_dtype)
+        stats = torch.zeros(2, C, dtype=torch.float32, device=res.device)  # dgamma | dbeta, one fill
+        dg, db = stats[0], stats[1]
+        need_dx = row_scale is not None or ctx.x_dtype != torch.float32
+        dx = torch.empty(res.shape, dtype=ctx.x_dtype, device=res.device) if need_dx else None
+        _lib.call("sim_add_layernorm_bwd_dx", _p(res), _p(dy), _p(dres_out), _p(_f32c(weight)), _p(row_scale),
+                  int(ctx.rows_per_sample), _p(dres), _p(dx), 0 if dx is None else _dt(dx), _p(dg), _p(db), rows, C,
+                  float(ctx.eps), _dt(dy), _stream())
+        if dx is None:
+            dx = dres
         dr = None if ctx.res_dtype is None else (dres if ctx.res_dtype == torch.float32 else dres.to(ctx.res_dtype))
-        return dx, dr, dg.to(ctx.wdtype), db.to(ctx.wdtype), None, None
+        return dx, dr, dg.to(ctx.wdtype), db.to(ctx.wdtype), None, None, None
 
 
 class Split3:
@@ -964,11 +983,13 @@ def selective_scan_bwd_tm(u, delta, A, Bm, Cm, D, z, delta_bias, dout, checkpoin
     du = torch.empty(B, L, Dm, dtype=u.dtype, device=dev)
     ddelta = torch.empty_like(du)
     dz = torch.empty_like(du) if z is not None else None
-    dB = torch.zeros(B, L, N, dtype=torch.float32, device=dev)
-    dC = torch.zeros_like(dB)
-    dA = torch.zeros(Dm, N, dtype=torch.float32, device=dev)
-    dD = torch.zeros(Dm, dtype=torch.float32, device=dev) if D is not None else None
-    dbias = torch.zeros(Dm, dtype=torch.float32, device=dev) if delta_bias is not None else None
+    # the accumulated outputs share one zero-filled buffer (one fill instead of five)
+    nbc, na = B * L * N, Dm * N
+    acc = torch.zeros(2 * nbc + na + 2 * Dm, dtype=torch.float32, device=dev)
+    dB, dC = acc[:nbc].view(B, L, N), acc[nbc:2 * nbc].view(B, L, N)
+    dA = acc[2 * nbc:2 * nbc + na].view(Dm, N)
+    dD = acc[2 * nbc + na:2 * nbc + na + Dm] if D is not None else None
+    dbias = acc[2 * nbc + na + Dm:] if delta_bias is not None else None
     _lib.call("sim_selective_scan_bwd", _p(u), _tm(u), _p(delta), _tm(delta), _p(_f32c(A)), _p(Bm), _tm(Bm), _p(Cm),
               _tm(Cm), _p(_f32c(D)), _p(z), 0 if z is None else _tm(z), _p(_f32c(delta_bias)), _p(dout), _tm(dout),
               _p(checkpoints), _p(du), _tm(du), _p(ddelta), _tm(ddelta), _p(dz), 0 if dz is None else _tm(dz),

@@ -121,6 +121,7 @@ def test_gradsync_single_process_flat_views_and_clip():
     sync.finish()
     assert sync.prune_unused() == 2  # unused.weight / unused.bias never receive a gradient
     assert m.unused.weight.grad is None and m.fc.weight.grad is not None
+    assert m.fc.weight.grad.data_ptr() == sync.flat[sync._offs[m.fc.weight]:].data_ptr()
     ref = _Tiny()
     ref.load_state_dict(m.state_dict())
     ref(x).pow(2).sum().backward()
@@ -133,11 +134,12 @@ def test_gradsync_single_process_flat_views_and_clip():
     for p, q in zip(m.parameters(), ref.parameters()):
         if q.grad is not None:
             assert torch.allclose(p.grad, q.grad, atol=1e-7)
-    sync.zero_grad()
-    assert float(m.fc.weight.grad.abs().sum()) == 0.0
-    m(x).pow(2).sum().backward()   # second step accumulates into the same views
+    sync.begin_step()
+    assert m.fc.weight.grad is None
+    m(x).pow(2).sum().backward()   # second step: fresh gradients, packed into the same flat slices by finish()
     sync.finish()
     assert m.fc.weight.grad.data_ptr() == sync.flat[sync._offs[m.fc.weight]:].data_ptr()
+    assert m.unused.weight.grad is None
 
 
 def _free_port():
@@ -155,7 +157,7 @@ def _worker(rank, world, port, q):
     sync = train.GradSync(m, bucket_mb=1e-4)
     xs = torch.randn(2, 6, 4, generator=torch.Generator().manual_seed(5))
     for step in range(2):  # the second step runs with the unused parameters pruned
-        sync.zero_grad()
+        sync.begin_step()
         m(xs[rank]).pow(2).sum().backward()
         sync.finish()
         if step == 0:
