@@ -242,10 +242,26 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
     {
       const int col = tid % GP, jg = tid / GP, njg = NT / GP;
       if (col < n) {
-        double acc = 0.0;
+        // four independent partial sums: the loads of a column walk (L2-resident workspace for G > 128) overlap instead of
+        // waiting on one another through a single fp64 dependency chain
+        constexpr int U = IN_SMEM ? 4 : 8;  // loads in flight per thread
+        double acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = 0.0;
         const double* Ac = Mat + (size_t)o * G + o + col;
-        for (int j = jg; j < n; j += njg) acc = fma(Ac[(size_t)j * G], s_v[j], acc);
-        s_part[jg * GP + col] = acc;
+        int j = jg;
+        for (; j + (U - 1) * njg < n; j += U * njg) {
+          double x[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) x[u] = Ac[(size_t)(j + u * njg) * G];
+#pragma unroll
+          for (int u = 0; u < U; ++u) acc[u] = fma(x[u], s_v[j + u * njg], acc[u]);
+        }
+        for (; j < n; j += njg) acc[0] = fma(Ac[(size_t)j * G], s_v[j], acc[0]);
+        double tot = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) tot += acc[u];
+        s_part[jg * GP + col] = tot;
       }
     }
     __syncthreads();
@@ -266,7 +282,18 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const SpectralParams P) {
       const int col = tid % GP, ig = tid / GP, nig = NT / GP;
       if (col < n) {
         const double vc = s_v[col], wc = s_w[col];
-        for (int i = ig; i < n; i += nig) {
+        constexpr int U = IN_SMEM ? 4 : 8;  // rows in flight per thread
+        int i = ig;
+        for (; i + (U - 1) * nig < n; i += U * nig) {
+          double* a = Mat + (size_t)(o + i) * G + o + col;
+          const size_t st = (size_t)nig * G;
+          double x[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) x[u] = a[u * st];
+#pragma unroll
+          for (int u = 0; u < U; ++u) a[u * st] = x[u] - (s_v[i + u * nig] * wc + s_w[i + u * nig] * vc);
+        }
+        for (; i < n; i += nig) {
           double* a = Mat + (size_t)(o + i) * G + o + col;
           *a = *a - (s_v[i] * wc + s_w[i] * vc);
         }
@@ -520,7 +547,7 @@ static size_t spectral_smem_bytes(int G, int k, int NT, bool in_smem) {
 size_t spectral_workspace_bytes(int B, int G, int k) {
   if (G <= 0 || B <= 0) return 0;
   const int NT = G <= 64 ? 256 : 512;
-  if (spectral_smem_bytes(G, k, NT, true) <= 227 * 1024) return 0;
+  if (spectral_smem_bytes(G, k, NT, true) <= 227 * 1024) return 0;  // (the workspace path itself runs 1024 threads)
   return (size_t)B * G * G * 12 + 256;
 }
 
@@ -531,8 +558,11 @@ int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cuda
               SIM_ERR_INVALID, "spectral_eig: k must be in [1, 8] and first + k <= G (got k=%d first=%d)", P.k, P.first);
   SIM_REQUIRE(P.adj_in || (P.k_nn >= 1 && P.k_nn + 1 <= P.G), SIM_ERR_INVALID, "spectral_eig: k_nn+1 must be <= G");
   SIM_REQUIRE((P.center || P.adj_in) && P.eigvals && P.eigvecs && P.perm, SIM_ERR_INVALID, "spectral_eig: null tensor");
-  const int NT = P.G <= 64 ? 256 : 512;
+  int NT = P.G <= 64 ? 256 : 512;
   const bool in_smem = spectral_smem_bytes(P.G, P.k, NT, true) <= 227 * 1024;
+  // matrix in the L2-resident workspace (G > 128): one CTA per cloud is latency-bound on its column / row walks, so it runs
+  // 1024 threads (twice the loads in flight; 9.1 -> see profiles/r02_sweep_c5.jsonl)
+  if (!in_smem) NT = 1024;
   const size_t smem = spectral_smem_bytes(P.G, P.k, NT, in_smem);
   P.lu_alias = spectral_lu_alias(P.G, P.k, in_smem) ? 1 : 0;
   if (!in_smem) {
@@ -551,10 +581,12 @@ int spectral_eig(SpectralParams P, void* workspace, size_t workspace_bytes, cuda
       return check_launch("spectral_eig attr");                                                     \
     kern<<<P.B, NT_, smem, stream>>>(P);                                                            \
   } while (0)
-  if (NT == 256) {
-    if (in_smem) SIM_SPEC_LAUNCH(256, true); else SIM_SPEC_LAUNCH(256, false);
+  if (NT == 1024) {
+    SIM_SPEC_LAUNCH(1024, false);
+  } else if (NT == 256) {
+    SIM_SPEC_LAUNCH(256, true);
   } else {
-    if (in_smem) SIM_SPEC_LAUNCH(512, true); else SIM_SPEC_LAUNCH(512, false);
+    SIM_SPEC_LAUNCH(512, true);
   }
 #undef SIM_SPEC_LAUNCH
   return check_launch("spectral_eig");

@@ -29,8 +29,9 @@ def main():
     torch.cuda.set_device(local)
     out = (lambda d: print(json.dumps(d), flush=True)) if rank == 0 else (lambda d: None)
     out(dict(device=torch.cuda.get_device_name(local), hbm_peak_gbs=HBM, world=int(os.environ.get("WORLD_SIZE", 1))))
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     # ---- spectral ordering
-    for G in (64, 128, 256, 512):
+    for G in ((64, 128, 256, 512) if only in (None, "spectral") else ()):
         for B in ((1, 32, 256) if quick else (1, 32, 256, 4096)):
             if G >= 256 and B > 256:
                 continue  # > 1 s of eigensolver work and GBs of workspace: outside the sweep's budget
@@ -40,7 +41,7 @@ def main():
             out(dict(kernel="spectral_eig", G=G, B=B, us=round(t * 1e6, 1), clouds_per_s=round(B / t, 1)))
     # ---- selective scan
     D = 768
-    for dtype in (torch.float32, torch.bfloat16):
+    for dtype in ((torch.float32, torch.bfloat16) if only in (None, "scan") else ()):
         es = 4 if dtype == torch.float32 else 2
         for L in (64, 256, 1024, 4096):
             for B in ((1, 32, 256) if quick else (1, 8, 32, 256, 1024, 4096)):
