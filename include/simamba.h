@@ -338,6 +338,9 @@ int sim_selective_scan_fwd_fused_dt(const void* u, long ld_u, const void* x_dbl,
                                     long plane, int batch, int L, int D, int N, int delta_softplus, int dtype,
                                     sim_stream_t stream);
 int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
+/* the three planes of the TRANSPOSE: x (rows,K) f32 (row stride ld) -> out[q][k][r] (row stride ldo >= rows, plane stride
+ * `plane`): the K-major operands of the dgrad / wgrad GEMMs of an fp32 Linear (W^T, dY^T, X^T) in one pass */
+int sim_split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
                     int M, int N, int K, sim_stream_t stream);
 

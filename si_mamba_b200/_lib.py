@@ -39,6 +39,7 @@ SIGNATURES = {
     "sim_spectral_eig": (_i, [_p, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sim_spectral_eig_ex": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sim_pairwise_dist_mean": (_i, [_p, _i, _i, _p, _p, _p]),
+    "sim_split3_bf16_t": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
     "sim_gemm_bf16": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _i, _p]),
     "sim_add_layernorm_droppath": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _l, _i, _f, _i, _i, _p]),
     "sim_add_layernorm_bwd_dx": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _l, _i, _f, _i, _p]),

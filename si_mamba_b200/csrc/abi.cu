@@ -393,6 +393,10 @@ int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ld
   return sim::split3_bf16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
 }
 
+int sim_split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
+  return sim::split3_bf16_t(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
+}
+
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
                     int M, int N, int K, sim_stream_t stream) {
   return sim::gemm_bf16x3(Xs, ldx, xplane, Ws, ldw, wplane, Y, ldd, M, N, K, static_cast<cudaStream_t>(stream));

@@ -702,6 +702,43 @@ int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, l
   return check_launch("split3_bf16");
 }
 
+// The three planes of the TRANSPOSE of x (rows, K) -> out[q][k][r]: the operands of the dgrad / wgrad GEMMs of an fp32
+// Linear (dX = dY W needs W^T, dW = dY^T X needs dY^T and X^T as K-major operands).  One pass through a 32 x 32 shared-memory
+// tile - reads coalesced along K, writes coalesced along rows - instead of a transposing copy followed by sim_split3_bf16.
+__global__ void __launch_bounds__(256) split3_t_kernel(const float* __restrict__ x, long ld, int rows, int K,
+                                                       __nv_bfloat16* __restrict__ out, long ldo, long plane) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, k = k0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && k < K) ? x[(long)r * ld + k] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty + 8 * i, r = r0 + tx;
+    if (k < K && r < rows) {
+      const float f = tile[tx][ty + 8 * i];
+      const __nv_bfloat16 p0 = __float2bfloat16_rn(f);
+      const float r1 = f - __bfloat162float(p0);
+      const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+      __nv_bfloat16* o = out + (long)k * ldo + r;
+      o[0] = p0, o[plane] = p1, o[2 * plane] = p2;
+    }
+  }
+}
+
+int split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream) {
+  SIM_REQUIRE(x && out && rows > 0 && K > 0 && ldo >= rows, SIM_ERR_INVALID, "split3_bf16_t: bad arguments");
+  const dim3 grid((K + 31) / 32, (rows + 31) / 32);
+  SIM_REQUIRE(grid.y <= 65535, SIM_ERR_INVALID, "split3_bf16_t: more than 2 M rows");
+  split3_t_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, K, static_cast<__nv_bfloat16*>(out), ldo, plane);
+  return check_launch("split3_bf16_t");
+}
+
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
   SIM_REQUIRE(!po || (N <= 64 && po_cols % 4 == 0 && po_cols <= N + 3 && po_ld % 4 == 0 && po_plane % 4 == 0 &&

@@ -136,6 +136,7 @@ int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wp
                      const float* conv_w = nullptr, const float* conv_b = nullptr, float* U = nullptr, long ldu = 0,
                      int batch = 0, int L = 0);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
+int split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream, void* po = nullptr, int po_cols = 0, long po_ld = 0, long po_plane = 0);
 

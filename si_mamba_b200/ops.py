@@ -635,6 +635,18 @@ def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
+def split3_t(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (rows, K) -> planes of the transpose (3, K, rows_p) bf16, rows_p = rows rounded up to 8 (zero padded): one
+    kernel instead of ``split3(x.t().contiguous())``."""
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    rp = (rows + 7) // 8 * 8
+    out = (torch.zeros if rp != rows else torch.empty)(3, K, rp, dtype=torch.bfloat16, device=x.device)
+    _lib.call("sim_split3_bf16_t", _p(x), x.stride(0), rows, K, _p(out), out.stride(1), out.stride(0), _stream())
+    return out
+
+
 def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y (rows, N) fp32 = x @ w.T from pre-split planes xs (3, rows, >=K), ws (3, N, >=K) (tcgen05 kernel)."""
     _cuda(xs, ws)
@@ -773,11 +785,13 @@ class LinearX3(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = linear_split3(split3(dy2), split3(w.t().contiguous()), N).view(x.shape)
+            dx = linear_split3(split3(dy2), split3_t(w if w.stride(1) == 1 else w.contiguous()), N).view(x.shape)
         if ctx.needs_input_grad[1]:
             x2 = x.reshape(-1, K)
+            if x2.stride(1) != 1:
+                x2 = x2.contiguous()
             M = x2.shape[0]
-            dw = linear_split3(split3(dy2.t().contiguous()), split3(x2.t().contiguous()), M)
+            dw = linear_split3(split3_t(dy2), split3_t(x2), M)  # transposed operands split in one pass each
         return dx, dw
 
 
