@@ -573,8 +573,8 @@ def run_train(args):
 
     for d, s in zip(statics, host_sets[0]):
         d.copy_(s)
-    optimizer, scheduler = train.build_opti_sche(model, ocfg, capturable=True)
     sync = train.GradSync(model, bucket_mb=1e9 if args.no_overlap else args.bucket_mb)
+    optimizer, scheduler = train.build_opti_sche(model, ocfg, capturable=True, sync=sync)  # FlatAdamW: one kernel per step
     n0 = _lib.launches()
     step = train.TrainStep(model, optimizer, loss_fn, grad_clip=10.0, autocast_dtype=autocast, graph=not args.no_graph,
                            sync=sync)

@@ -287,6 +287,14 @@ int sim_add_layernorm_bwd(const float* res, const void* dy, const float* dres_ou
 
 /* Producers that emit the split operand directly (fp32 activations), so no separate split pass is needed:
  * LayerNorm output -> in_proj, conv output (fp32 u for the scan AND planes for x_proj), scan output -> out_proj. */
+/* 8f-4  torch.optim.AdamW (tools/builder.py:74, part_segmentation/main.py:201) over flat buffers of n floats (n % 4 == 0):
+ * p, g, m = exp_avg, v = exp_avg_sq, wd = per-element weight decay (< 0: leave the element alone).  lr, step (the number
+ * of steps taken so far, incremented by the call) and grad_scale (NULL = 1; the clip_grad_norm_ coefficient) are DEVICE
+ * scalars, so the update can be captured in a CUDA graph:  g' = g * grad_scale;  p *= 1 - lr wd;  m = b1 m + (1 - b1) g';
+ * v = b2 v + (1 - b2) g'^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),  t = step + 1. */
+int sim_adamw_flat(float* p, const float* g, float* m, float* v, const float* wd, long n, const float* lr, float* step,
+                   const float* grad_scale, float beta1, float beta2, float eps, sim_stream_t stream);
+
 /* a-9 with DropPath folded in (training; models/block.py:59 `residual = self.drop_path(hidden_states) + residual`, timm
  * drop_path = x / keep * mask per sample): res_out = row_scale[row / rows_per_sample] * x + res_in, y = LN(res_out).
  * row_scale (samples) f32 = mask_b / keep_prob, or NULL (then identical to sim_add_layernorm without x2).

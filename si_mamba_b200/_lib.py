@@ -43,6 +43,7 @@ SIGNATURES = {
     "sim_gemm_bf16": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _i, _p]),
     "sim_add_layernorm_droppath": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _l, _i, _f, _i, _i, _p]),
     "sim_add_layernorm_bwd_dx": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _l, _i, _f, _i, _p]),
+    "sim_adamw_flat": (_i, [_p, _p, _p, _p, _p, _l, _p, _p, _p, _f, _f, _f, _p]),
     "sim_point_linear3": (_i, [_p, _p, _p, _p, _l, _i, _i, _p]),
     "sim_gemm_tf32": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
     "sim_argsort_rows": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),

@@ -373,6 +373,11 @@ int sim_add_layernorm_bwd_dx(const float* res, const void* dy, const float* dres
                                 static_cast<cudaStream_t>(stream), dx, dtype_dx, row_scale, rows_per_sample);
 }
 
+int sim_adamw_flat(float* p, const float* g, float* m, float* v, const float* wd, long n, const float* lr, float* step,
+                   const float* grad_scale, float beta1, float beta2, float eps, sim_stream_t stream) {
+  return sim::adamw_flat(p, g, m, v, wd, n, lr, step, grad_scale, beta1, beta2, eps, static_cast<cudaStream_t>(stream));
+}
+
 int sim_point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, sim_stream_t stream) {
   return sim::point_linear3(x, w, b, y, rows, C, act, static_cast<cudaStream_t>(stream));
 }

@@ -125,6 +125,8 @@ int add_layernorm_bwd(const float* res, const void* dy, const float* dres_out, c
                       void* dx = nullptr, int dtype_dx = 0, const float* row_scale = nullptr, int rows_per_sample = 0);
 int group_max(const void* x, void* out, long groups, int M, int C, int dtype, cudaStream_t stream);
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream);
+int adamw_flat(float* p, const float* g, float* m, float* v, const float* wd, long n, const float* lr, float* step,
+               const float* grad_scale, float beta1, float beta2, float eps, cudaStream_t stream);
 int point_linear3(const float* x, const float* w, const float* b, float* y, long rows, int C, int act, cudaStream_t stream);
 int mlp3_relu_rows(const float* x, long ldx, long rows, int d0, const float* w1t, const float* b1, int d1, const float* w2t,
                    const float* b2, int d2, const float* w3t, const float* b3, int d3, float* y, long ldy,

@@ -452,6 +452,60 @@ int point_linear3(const float* x, const float* w, const float* b, float* y, long
   return check_launch("point_linear3");
 }
 
+// ----------------------------------------------------------------------------- flat AdamW (trainer plumbing)
+// torch.optim.AdamW (tools/builder.py:74, part_segmentation/main.py:201) over ONE flat parameter / gradient / moment buffer:
+//   g = grad * grad_scale (the clip_grad_norm_ coefficient, optional);  p *= 1 - lr wd;  m = b1 m + (1 - b1) g;
+//   v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),  t = *step + 1.
+// wd[i] < 0 marks slots the optimizer must not touch (padding, parameters without a gradient).  lr, step and grad_scale
+// are device scalars, so the launch can live in a CUDA graph; torch's capturable multi-tensor AdamW issues ~700 scalar
+// kernels per step for the same update (1.5 - 2.5 ms of a 9 - 22 ms step, profiles/r02_launches_c4.md).
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         const float* __restrict__ wd, long n, const float* __restrict__ lr_p,
+                                                         const float* __restrict__ step_p, const float* __restrict__ gs_p,
+                                                         float b1, float b2, float eps) {
+  const float lr = *lr_p, t = *step_p + 1.f;
+  const float gs = gs_p ? *gs_p : 1.f;
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (long)gridDim.x * 256 * 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wd + i);
+    float4 p4 = *reinterpret_cast<float4*>(p + i);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    float* pp = &p4.x;
+    float* mm = &m4.x;
+    float* vv = &v4.x;
+    const float* gg = &g4.x;
+    const float* ww = &w4.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ww[k] < 0.f) continue;
+      const float gk = gg[k] * gs;
+      float pk = pp[k] * (1.f - lr * ww[k]);
+      const float mk = b1 * mm[k] + (1.f - b1) * gk;
+      const float vk = b2 * vv[k] + (1.f - b2) * gk * gk;
+      pk -= step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+      pp[k] = pk, mm[k] = mk, vv[k] = vk;
+    }
+    *reinterpret_cast<float4*>(p + i) = p4;
+    *reinterpret_cast<float4*>(m + i) = m4;
+    *reinterpret_cast<float4*>(v + i) = v4;
+  }
+}
+__global__ void adamw_step_incr_kernel(float* step) { *step += 1.f; }
+
+int adamw_flat(float* p, const float* g, float* m, float* v, const float* wd, long n, const float* lr, float* step,
+               const float* grad_scale, float beta1, float beta2, float eps, cudaStream_t stream) {
+  SIM_REQUIRE(p && g && m && v && wd && lr && step && n > 0 && n % 4 == 0, SIM_ERR_INVALID, "adamw_flat: bad arguments (n %% 4)");
+  SIM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && aligned16(wd), SIM_ERR_ALIGN,
+              "adamw_flat: buffers must be 16-byte aligned");
+  const int grid = (int)std::min<long>((n / 4 + 255) / 256, 148L * 8);
+  adamw_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, wd, n, lr, step, grad_scale, beta1, beta2, eps);
+  adamw_step_incr_kernel<<<1, 1, 0, stream>>>(step);
+  return check_launch("adamw_flat");
+}
+
 int group_bias_relu(void* x, const void* gvec, long rows, int M, int C, int dtype, cudaStream_t stream) {
   SIM_REQUIRE(x && gvec && rows > 0 && M > 0 && C > 0 && C % 4 == 0 && rows % M == 0, SIM_ERR_INVALID,
               "group_bias_relu: bad arguments");
