@@ -284,16 +284,23 @@ def test_feature_propagation_matches_reference(ref_mod):
 def test_cuda_modules_match_reference(lib, ref_mod):
     """Drop-in check: the reference's own state dicts load (strict) into the product's Encoder /
     PointNetFeaturePropagation / Block, and their CUDA forward reproduces what the reference modules returned.
-    Encoder tolerance 2e-3 relative: its 1x1 convolutions run on TF32 tensor cores under torch's default conv policy,
-    like the reference's cuDNN path."""
+    The Encoder runs on own kernels only (3 -> 128 row kernel + tcgen05 GEMMs): with cuDNN's TF32 switch off its
+    convolutions are fp32-accurate split-plane GEMMs and match the reference (run in fp32 on the CPU) to 1e-4; with the
+    switch on (torch's default, the policy of the reference's Conv1d layers) they run as TF32 and match to 2e-3."""
     from si_mamba_b200 import block as blk, point_mamba as pmod, seg as smod
     e = ref_mod["encoder"]
     enc = pmod.Encoder(384).cuda().eval()
     enc.load_state_dict(_f32(e["sd"]), strict=True)
-    with torch.no_grad():
-        out = enc(e["groups"].cuda()).cpu()
     scale = e["tokens"].abs().max()
-    assert (out - e["tokens"]).abs().max() <= 2e-3 * scale, (out - e["tokens"]).abs().max() / scale
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        for tf32, tol in ((False, 1e-4), (True, 2e-3)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                out = enc(e["groups"].cuda()).cpu()
+            assert (out - e["tokens"]).abs().max() <= tol * scale, (tf32, (out - e["tokens"]).abs().max() / scale)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
 
     f = ref_mod["feature_propagation"]
     fp = smod.PointNetFeaturePropagation(in_channel=40, mlp=[32, 24]).cuda().eval()
