@@ -140,7 +140,9 @@ int sim_causal_conv1d_fwd(const void* x, long ld_x, const float* w, const float*
 /* a-11  selective scan forward.  Replaces mamba-ssm selective_scan_fn inside Mamba.forward
  * (models/block.py:72); semantics of selective_scan_ref.  u, delta, z, out (batch*L, D) token-major;
  * Bm, Cm (batch*L, N) token-major; A (D,N) f32; Dvec, delta_bias (D) f32 or NULL; z may be NULL.
- * N must be 16.  variant: 0 = auto, else states per thread (2, 4, 8, 16). */
+ * N must be 16.  variant: 0 = auto, else states per thread (2, 4, 8, 16).
+ * delta_softplus: bit 0 = apply softplus to delta + delta_bias; bit 1 (inference, also in sim_selective_scan_fwd_split3) =
+ * `z` already holds the gate silu(z) (written by sim_gemm_planes act_mode 1), the kernel multiplies by it as is. */
 int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_delta, const float* A,
                            const void* Bm, long ld_B, const void* Cm, long ld_C, const float* Dvec, const void* z,
                            long ld_z, const float* delta_bias, void* out, long ld_out, float* checkpoints, int batch,
@@ -351,6 +353,22 @@ int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ld
 int sim_split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
                     int M, int N, int K, sim_stream_t stream);
+
+/* a-10  the plane GEMM with a choice of operand format and an optional activation fused into its epilogue (inference).
+ * np = 3: three bf16 planes per operand (sim_split3_bf16), six products - any fp32 operand;
+ * np = 2: two fp16 planes x0 = fp16(x), x1' = fp16(2^11 (x - x0)) (sim_split2_f16 / sim_add_layernorm_split2h), three
+ *         products: half the tensor-core work at fp32-GEMM accuracy, valid for |x|, |w| < 65504 - used for in_proj, whose
+ *         operand is a LayerNorm output (models/block.py:56-58) bounded by sqrt(C) max|gamma| + max|beta|.
+ * act_mode 0: none.  1: columns >= act_col0 leave as silu(v) - in_proj hands the scan the gate silu(z) instead of z
+ * (Mamba.forward -> selective_scan_fn(..., z=z), models/block.py:72; pair with bit 1 of sim_selective_scan_fwd's
+ * delta_softplus).  2: every column leaves as softplus(v + act_bias[col]) - dt_proj hands the scan dt itself (then call the
+ * scan with delta_bias = NULL, delta_softplus = 0).  Same device arithmetic as the scan's own pre-pass: bit-identical. */
+int sim_gemm_planes(int np, const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
+                    int M, int N, int K, int act_mode, int act_col0, const float* act_bias, sim_stream_t stream);
+int sim_split2_f16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream);
+int sim_add_layernorm_split2h(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                              float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
+                              sim_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,9 @@ SIGNATURES = {
     "sim_mlp3_relu_rows": (_i, [_p, _l, _l, _i, _p, _p, _i, _p, _p, _i, _p, _p, _i, _p, _l, _p]),
     "sim_layernorm_mean": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "sim_split3_bf16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
+    "sim_split2_f16": (_i, [_p, _l, _i, _i, _p, _l, _l, _p]),
+    "sim_gemm_planes": (_i, [_i, _p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _i, _i, _p, _p]),
+    "sim_add_layernorm_split2h": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _i, _p]),
     "sim_gemm_bf16x3": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _p]),
     "sim_causal_conv1d_bwd": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }

@@ -107,6 +107,39 @@ _FP32_GEMM = __import__("os").environ.get("SIM_FP32_GEMM", "x3")  # x3 (pre-spli
 _BF16_GEMM = __import__("os").environ.get("SIM_BF16_GEMM", "own")
 
 
+# fp32 inference, in_proj on two fp16 planes (three tensor-core products instead of six, csrc/gemm_split3.cu NP = 2): its
+# operand is a LayerNorm output, bounded by sqrt(C) max|gamma| + max|beta|, so the fp16 range (65504) can be checked once
+# per parameter version on the host (inproj_f16_ok).  SIM_INPROJ_F16X2=0 keeps the three bf16 planes (ablation).
+_INPROJ_F16 = __import__("os").environ.get("SIM_INPROJ_F16X2", "1") != "0"
+# fp32 inference: activations the scan would evaluate on its XU pipe (the unit that bounds it) are applied by
+# the GEMM epilogue that produces the operand instead.  "z": in_proj writes silu(z) (free inside a tensor-bound kernel);
+# "zdt": dt_proj also writes softplus(delta + bias); "0": the scan does both itself (ablation).  Bit-identical results.
+_HOIST_ACT = __import__("os").environ.get("SIM_HOIST_ACT", "z")
+
+
+def inproj_f16_ok(norm_w: torch.Tensor, norm_b: torch.Tensor, in_proj_w: torch.Tensor) -> bool:
+    """True when LayerNorm(gamma = norm_w, beta = norm_b) outputs and in_proj_w are provably inside the fp16 range (with a
+    2x margin), so in_proj may take two fp16 planes.  One host read per parameter version; while a CUDA graph is being
+    captured an uncached answer is "no" (bf16 planes are always valid)."""
+    if not _INPROJ_F16 or _OVERLAP_Z:
+        return False
+    C = norm_w.numel()
+
+    def check():
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        bound = float(C) ** 0.5 * norm_w.detach().abs().max() + norm_b.detach().abs().max()
+        return bool((bound < 3.0e4).item() and (in_proj_w.detach().abs().max() < 3.0e4).item())
+
+    ok = _CACHE.get_multi(norm_w, "f16ok", (norm_w, norm_b, in_proj_w), check)
+    if ok is None:  # asked during capture before any eager forward: do not cache the refusal
+        per = _CACHE._d.get(norm_w)
+        if per is not None:
+            per.pop("f16ok", None)
+        return False
+    return ok
+
+
 class _SplitCols(torch.autograd.Function):
     """x (..., sum(sizes)) -> views x[..., a:b] per size; the backward writes the pieces' gradients side by side with
     one torch.cat (autograd's own SliceBackward allocates a zero tensor of the full shape per slice and then adds them:
@@ -174,6 +207,7 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
             and _FP32_GEMM != "cublas" and d_inner % 8 == 0 and hidden.shape[-1] % 8 == 0 and dt_rank % 4 == 0):
         linear = ops.linear_x3_train  # fp32 training: forward, dX and dW GEMMs on the split-plane tensor-core kernel
     join_z = None
+    hoist_z = False
     if x3 and _OVERLAP_Z:
         # in_proj as two GEMMs: the x half on this stream, the z half (only needed by the scan) on a side stream where it
         # runs next to the HBM-bound conv and the small x_proj / dt_proj GEMMs; a fork / join that CUDA graphs capture
@@ -188,6 +222,14 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         with torch.cuda.stream(side):
             z = ops.linear_split3(hs.planes, wp[:, d_inner:], K).view(*hs.shape[:-1], d_inner)
         join_z = (cur, side, z)
+    elif x3 and isinstance(hidden, ops.Split3):
+        # in_proj from the planes the Block's add + LayerNorm wrote (two fp16 planes where inproj_f16_ok, else three bf16);
+        # with the hoist its epilogue turns the z half into the gate silu(z) the scan multiplies by
+        hoist_z = _HOIST_ACT in ("z", "zdt") and not _FUSE_DT
+        f16 = hidden.planes.dtype == torch.float16
+        wp = _CACHE.get(in_proj_w, "x2h", ops.split2h) if f16 else _CACHE.get(in_proj_w, "x3", ops.split3)
+        xz = ops.linear_f32_x3(hidden, wp, in_proj_w.shape[1], act="silu_from" if hoist_z else None, act_col0=d_inner)
+        x, z = xz[..., :d_inner], xz[..., d_inner:]
     else:
         xz = linear(hidden if isinstance(hidden, ops.Split3) else hidden.to(act), w_in)  # (B, L, 2*d_inner)
         if need_grad:
@@ -209,6 +251,7 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     else:
         u = u_op = ops.causal_conv1d_tm(x, conv_w, conv_b, silu=True)
     dt_planes = None
+    dt_final = False
     if u_op is None:
         x_dbl, dt_planes = x_dbl_f, dt_planes_f
     elif x3 and _XPROJ_F32A and not isinstance(u_op, ops.Split3) and dt_rank <= 32 and 32 <= x_proj_w.shape[0] <= 64:
@@ -236,7 +279,11 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
                            lambda t: ops.split3(F.pad(t.float(), (0, 32 - t.shape[1])).contiguous()))
         if dt_planes is None:
             dt_planes = ops.split3(x_dbl[..., :32])
-        dt = ops.linear_split3(dt_planes, wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
+        if _HOIST_ACT == "zdt" and dt_proj_b is not None:  # dt = softplus(delta + bias) leaves the GEMM's epilogue
+            dt = ops.linear_split3(dt_planes, wdt32, 32, act="softplus_bias", bias=dt_proj_b).view(*x_dbl.shape[:-1], d_inner)
+            dt_final = True
+        else:
+            dt = ops.linear_split3(dt_planes, wdt32, 32).view(*x_dbl.shape[:-1], d_inner)
         Bm = x_dbl[..., dt_rank:dt_rank + d_state]
         Cm = x_dbl[..., dt_rank + d_state:]
     elif need_grad and x_dbl.shape[-1] == dt_rank + 2 * d_state:
@@ -254,5 +301,6 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
     if need_grad:
         y = ops.SelectiveScanTM.apply(u, dt, A, Bm, Cm, D, z, dt_proj_b, True)
     else:
-        y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, dt_proj_b, delta_softplus=True, split=x3)
+        y = ops.selective_scan_tm(u, dt, A, Bm, Cm, D, z, None if dt_final else dt_proj_b, delta_softplus=not dt_final,
+                                  split=x3, z_gate=hoist_z)
     return linear(y, w_out)

@@ -62,7 +62,7 @@ def fused_add_norm(norm: nn.LayerNorm, hidden: Tensor, residual: Optional[Tensor
         hidden = hidden * row_scale.view(-1, *([1] * (hidden.dim() - 1))).to(hidden.dtype)
     out_dtype = _amp_dtype(hidden)
     return ops.add_layernorm(hidden, residual, norm.weight, norm.bias, norm.eps, out_dtype=out_dtype,
-                             want_residual=want_residual, split=split and out_dtype == torch.float32)
+                             want_residual=want_residual, split=split if out_dtype == torch.float32 else False)
 
 
 class Block(nn.Module):
@@ -80,6 +80,10 @@ class Block(nn.Module):
         # fp32 inference: LayerNorm writes the in_proj operand (three bf16 planes) directly, see autograd.wants_split3
         want = getattr(self.mixer, "wants_split3", None)
         split = bool(want and want(hidden_states))
+        if split and isinstance(self.norm, nn.LayerNorm) and self.norm.bias is not None:
+            from .autograd import inproj_f16_ok
+            if inproj_f16_ok(self.norm.weight, self.norm.bias, self.mixer.in_proj.weight):
+                split = "f16x2"  # bounded operand: two fp16 planes, half the tensor-core work of in_proj
         # block.py:59: `drop_path(h) + residual if residual is not None else h` - the first block's input is never dropped.
         # The per-sample factor mask / keep goes into the add + LayerNorm kernels (forward and backward) as row_scale.
         scale = None

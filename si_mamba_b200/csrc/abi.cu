@@ -167,7 +167,7 @@ int sim_selective_scan_fwd(const void* u, long ld_u, const void* delta, long ld_
   p.u = u, p.delta = delta, p.z = z, p.Bm = Bm, p.Cm = Cm, p.out = out;
   p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
   p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_out = ld_out;
-  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus & 1, p.z_gate = (delta_softplus >> 1) & 1;
   p.ckpt = checkpoints;
   return sim::selective_scan_fwd(p, dtype, variant, static_cast<cudaStream_t>(stream));
 }
@@ -184,7 +184,7 @@ int sim_selective_scan_fwd_split3(const void* u, long ld_u, const void* delta, l
   p.u = u, p.delta = delta, p.z = z, p.Bm = Bm, p.Cm = Cm, p.out = nullptr;
   p.A = A, p.Dv = Dvec, p.dbias = delta_bias;
   p.ld_u = ld_u, p.ld_delta = ld_delta, p.ld_z = ld_z, p.ld_B = ld_B, p.ld_C = ld_C, p.ld_out = 0;
-  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus;
+  p.batch = batch, p.L = L, p.D = D, p.softplus = delta_softplus & 1, p.z_gate = (delta_softplus >> 1) & 1;
   p.ckpt = nullptr;
   p.out_planes = out_planes, p.ld_planes = ld_planes, p.plane = plane;
   return sim::selective_scan_fwd(p, 0, 0, static_cast<cudaStream_t>(stream));
@@ -215,6 +215,13 @@ int sim_add_layernorm_split3(const void* x, const void* x2, const float* res_in,
                              sim_stream_t stream) {
   return sim::add_layernorm(x, x2, res_in, gamma, beta, res_out, nullptr, rows, C, eps, dtype_x, 0,
                             static_cast<cudaStream_t>(stream), planes, plane);
+}
+
+int sim_add_layernorm_split2h(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
+                              float* res_out, void* planes, long plane, long rows, int C, float eps, int dtype_x,
+                              sim_stream_t stream) {
+  return sim::add_layernorm(x, x2, res_in, gamma, beta, res_out, nullptr, rows, C, eps, dtype_x, 0,
+                            static_cast<cudaStream_t>(stream), planes, plane, nullptr, 0, 1);
 }
 
 int sim_causal_conv1d_fwd_split3(const float* x, long ld_x, const float* w, const float* bias, float* y, long ld_y,
@@ -400,6 +407,16 @@ int sim_split3_bf16(const float* x, long ld, int rows, int K, void* out, long ld
 
 int sim_split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
   return sim::split3_bf16_t(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
+}
+
+int sim_split2_f16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, sim_stream_t stream) {
+  return sim::split2_f16(x, ld, rows, K, out, ldo, plane, static_cast<cudaStream_t>(stream));
+}
+
+int sim_gemm_planes(int np, const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
+                    int M, int N, int K, int act_mode, int act_col0, const float* act_bias, sim_stream_t stream) {
+  return sim::gemm_planes(np, Xs, ldx, xplane, Ws, ldw, wplane, Y, ldd, M, N, K, static_cast<cudaStream_t>(stream), nullptr, 0,
+                          0, 0, act_mode, act_col0, act_bias);
 }
 
 int sim_gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,

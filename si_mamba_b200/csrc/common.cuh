@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -177,6 +178,21 @@ __device__ __forceinline__ void split3_store4(__nv_bfloat16* dst, long plane, fl
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(dst + k * plane) = *reinterpret_cast<const uint2*>(q[k]);
+}
+
+// x = x0 + 2^-11 x1' as two fp16 values: x0 = fp16(x) (11 significant bits), x1' = fp16(2^11 (x - x0)) - the residual is
+// exact in fp32, the scaling keeps it out of the fp16 subnormal range for |x| down to 2^-14.  Operand format of the NP = 2
+// kernels of gemm_split3.cu; valid for |x| < 65504.  Four adjacent elements -> one 8-byte store per plane.
+__device__ __forceinline__ void split2h_store4(__half* dst, long plane, float4 v) {
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __half q[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    q[0][j] = __float2half_rn(f[j]);
+    q[1][j] = __float2half_rn((f[j] - __half2float(q[0][j])) * 2048.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) *reinterpret_cast<uint2*>(dst + k * plane) = *reinterpret_cast<const uint2*>(q[k]);
 }
 
 }  // namespace sim

@@ -35,11 +35,13 @@ constexpr int kBM = 128;  // rows of X per CTA == TMEM lanes
 constexpr int kBK = 32;   // K elements per pipeline stage = one 64-byte swizzle row of bf16
 constexpr int kUK = 16;   // K of one tcgen05.mma.kind::f16
 
-template <int BN, int NSTAGE_>
+// NP = operand planes: 3 = bf16 planes, six products (any fp32 operand); 2 = fp16 planes hi + 2^11 lo, three products
+// (operands whose magnitude is bounded below the fp16 range, see the header comment of gemm_planes below)
+template <int BN, int NSTAGE_, int NP = 3>
 struct GemmCfg {
   static constexpr int A_TILE = kBM * kBK * 2;
   static constexpr int B_TILE = BN * kBK * 2;
-  static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
+  static constexpr int STAGE = NP * A_TILE + NP * B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int MINB = (NSTAGE_ * STAGE + 2304) * 2 <= 232448 && 4 * BN <= 512 && BN != 192 ? 2 : 1;  // CTAs per SM
   static constexpr int STG_LD = 36;  // padded row stride (floats) of the epilogue staging tile: 16-B aligned, conflict-free
@@ -110,16 +112,55 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// A / B element format field of the instruction descriptor: 0 = fp16, 1 = bf16
+__host__ __device__ constexpr uint32_t umma_idesc_planes(int M, int N, int np) {
+  return np == 3 ? umma_idesc_bf16(M, N) : ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24));
+}
+// (X plane, W plane) pairs, smallest contributions first; the LAST pair is the leading product (accumulator 0)
+template <int NP>
+struct PlaneProducts;
+template <>
+struct PlaneProducts<3> {
+  static constexpr int N = 6;
+  __host__ __device__ static constexpr int pa(int q) { return q == 0 ? 0 : q == 1 ? 2 : q == 2 ? 1 : q == 3 ? 0 : q == 4 ? 1 : 0; }
+  __host__ __device__ static constexpr int pb(int q) { return q == 0 ? 2 : q == 1 ? 0 : q == 2 ? 1 : q == 3 ? 1 : q == 4 ? 0 : 0; }
+  static constexpr float LOW = 1.f;  // weight of the correction accumulator in the epilogue
+};
+template <>
+struct PlaneProducts<2> {  // x = x0 + 2^-11 x1', w = w0 + 2^-11 w1': x0.w1' + x1'.w0 carry 2^11, x1'.w1' (2^-22) is dropped
+  static constexpr int N = 3;
+  __host__ __device__ static constexpr int pa(int q) { return q == 1 ? 1 : 0; }
+  __host__ __device__ static constexpr int pb(int q) { return q == 0 ? 1 : 0; }
+  static constexpr float LOW = 1.f / 2048.f;
+};
+
+// Optional activation fused into the epilogue (inference): the producer of an activation applies what its only
+// consumer, the scan, would otherwise evaluate on the XU pipe that bounds it:
+//   mode 1: columns >= col0 -> silu(v)           (in_proj: the z half leaves as the gate silu(z))
+//   mode 2: every column   -> softplus(v + bias)  (dt_proj: delta leaves as dt = softplus(delta + dt_proj.bias))
+// Same device functions as the scan's own pre-pass (common.cuh), so both paths agree bit for bit.
+struct EpiAct {
+  int mode;
+  int col0;
+  const float* bias;
+};
+__device__ __forceinline__ float epi_act(float v, int col, int N, const EpiAct& a) {
+  if (a.mode == 1) return col >= a.col0 ? silu_f(v) : v;
+  if (a.mode == 2) return softplus_f(v + (col < N ? a.bias[col] : 0.f));
+  return v;
+}
+
 struct GemmTmaps {
   CUtensorMap x, w;
 };
 
-template <int BN, int NSTAGE_>
-__global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
+template <int BN, int NSTAGE_, int NP>
+__global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_, NP>::MINB) gemm_split3_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y,
                                                              long ldd, int M, int N, int K, int n_tiles,
                                                              __nv_bfloat16* __restrict__ po, int po_cols, long po_ld,
-                                                             long po_plane, int kb_per_split) {
-  using Cfg = GemmCfg<BN, NSTAGE_>;
+                                                             long po_plane, int kb_per_split, const EpiAct act) {
+  using Cfg = GemmCfg<BN, NSTAGE_, NP>;
+  using PP = PlaneProducts<NP>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
   // swizzled tiles: align the carve-up to 1024 bytes of the shared ADDRESS space
@@ -167,29 +208,26 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
         unsigned char* st = smem + s * Cfg::STAGE;
         mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
         tma_load_3d(st, &tm.x, (kb0 + kb) * kBK, m0, 0, &full[s]);
-        tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, (kb0 + kb) * kBK, n0, 0, &full[s]);
+        tma_load_3d(st + NP * Cfg::A_TILE, &tm.w, (kb0 + kb) * kBK, n0, 0, &full[s]);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      // (X plane, W plane) pairs, smallest contributions first
-      constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
-      constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+      constexpr uint32_t idesc = umma_idesc_planes(kBM, BN, NP);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % NSTAGE;
         mbar_wait(&full[s], (kb / NSTAGE) & 1);
         tc_fence_after();
         const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
-        const uint32_t b0 = a0 + 3 * Cfg::A_TILE;
+        const uint32_t b0 = a0 + NP * Cfg::A_TILE;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
+        for (int q = 0; q < PP::N; ++q) {
 #pragma unroll
           for (int k = 0; k < kBK / kUK; ++k) {
-            const uint64_t da = umma_desc_sw64(a0 + PA[q] * Cfg::A_TILE + k * kUK * 2);
-            const uint64_t db = umma_desc_sw64(b0 + PB[q] * Cfg::B_TILE + k * kUK * 2);
-            umma_bf16(tmem_d + (q == 5 ? 0 : BN), da, db, idesc, q == 5 ? (kb | k) != 0 : (kb | q | k) != 0);
+            const uint64_t da = umma_desc_sw64(a0 + PP::pa(q) * Cfg::A_TILE + k * kUK * 2);
+            const uint64_t db = umma_desc_sw64(b0 + PP::pb(q) * Cfg::B_TILE + k * kUK * 2);
+            umma_bf16(tmem_d + (q == PP::N - 1 ? 0 : BN), da, db, idesc, q == PP::N - 1 ? (kb | k) != 0 : (kb | q | k) != 0);
           }
         }
         umma_commit(&empty[s]);  // stage s may be refilled once these MMAs have read it
@@ -209,7 +247,11 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + BN + c * 32, sm);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += sm[i];
+      for (int i = 0; i < 32; ++i) v[i] = NP == 3 ? v[i] + sm[i] : fmaf(sm[i], 1.f / 2048.f, v[i]);
+      if (act.mode) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = epi_act(v[i], n0 + c * 32 + i, N, act);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -246,11 +288,11 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_>::MINB) gemm_split3_k
 // epilogue warps (two per TMEM lane quadrant, half of the tile's columns each) first drain both accumulators into
 // registers (BN / 2 fp32 values per thread), release the accumulators to the MMA warp, and only then do the slow part
 // (staging + global stores) while the next tile's MMAs are already running.
-template <int BN, int NSTAGE_>
+template <int BN, int NSTAGE_, int NP = 3>
 struct GemmPCfg {
   static constexpr int A_TILE = kBM * kBK * 2;
   static constexpr int B_TILE = BN * kBK * 2;
-  static constexpr int STAGE = 3 * A_TILE + 3 * B_TILE;
+  static constexpr int STAGE = NP * A_TILE + NP * B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int NEPI = 8;                      // epilogue warps
   static constexpr int NT = 64 + 32 * NEPI;
@@ -262,11 +304,12 @@ struct GemmPCfg {
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN, int NSTAGE_>
-__global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
+template <int BN, int NSTAGE_, int NP>
+__global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
     gemm_split3_persistent_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y, long ldd, int M, int N, int K,
-                                  int n_tiles, int total_tiles) {
-  using Cfg = GemmPCfg<BN, NSTAGE_>;
+                                  int n_tiles, int total_tiles, const EpiAct act) {
+  using Cfg = GemmPCfg<BN, NSTAGE_, NP>;
+  using PP = PlaneProducts<NP>;
   constexpr int NSTAGE = Cfg::NSTAGE, CW = Cfg::CW;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
@@ -310,15 +353,13 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
           unsigned char* st = smem + s * Cfg::STAGE;
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
           tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
-          tma_load_3d(st + 3 * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+          tma_load_3d(st + NP * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
-      constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+      constexpr uint32_t idesc = umma_idesc_planes(kBM, BN, NP);
       int it = 0, i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
         if (i >= 1) {  // the epilogue warps have drained the previous tile's accumulators
@@ -330,14 +371,14 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
           mbar_wait(&full[s], (it / NSTAGE) & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
-          const uint32_t b0 = a0 + 3 * Cfg::A_TILE;
+          const uint32_t b0 = a0 + NP * Cfg::A_TILE;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
+          for (int q = 0; q < PP::N; ++q) {
 #pragma unroll
             for (int k = 0; k < kBK / kUK; ++k) {
-              const uint64_t da = umma_desc_sw64(a0 + PA[q] * Cfg::A_TILE + k * kUK * 2);
-              const uint64_t db = umma_desc_sw64(b0 + PB[q] * Cfg::B_TILE + k * kUK * 2);
-              umma_bf16(tmem_d + (q == 5 ? 0 : BN), da, db, idesc, q == 5 ? (kb | k) != 0 : (kb | q | k) != 0);
+              const uint64_t da = umma_desc_sw64(a0 + PP::pa(q) * Cfg::A_TILE + k * kUK * 2);
+              const uint64_t db = umma_desc_sw64(b0 + PP::pb(q) * Cfg::B_TILE + k * kUK * 2);
+              umma_bf16(tmem_d + (q == PP::N - 1 ? 0 : BN), da, db, idesc, q == PP::N - 1 ? (kb | k) != 0 : (kb | q | k) != 0);
             }
           }
           umma_commit(&empty[s]);
@@ -362,7 +403,7 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + col, v[c]);
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + BN + col, sm);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[c][e] += sm[e];
+        for (int e = 0; e < 32; ++e) v[c][e] = NP == 3 ? v[c][e] + sm[e] : fmaf(sm[e], 1.f / 2048.f, v[c][e]);
       }
       tc_fence_before();
       __syncwarp();
@@ -371,6 +412,10 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_>::NT, 1)
       for (int c = 0; c < CW / 32; ++c) {
         const int nc = n0 + half * CW + c * 32;
         if (nc >= N) break;
+        if (act.mode) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[c][e] = epi_act(v[c][e], nc + e, N, act);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           *reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + 4 * e) =
@@ -603,17 +648,17 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
 }
 
 // 3-D map over the three bf16 planes of a row-major (rows, K) operand: dims (K, rows, 3), 64-byte swizzle.
-int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows) {
+int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows, int np = 3) {
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SIM_ERR_CUDA;
   }
-  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)np};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 3u};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, (cuuint32_t)np};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = enc(m, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -624,11 +669,11 @@ int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld,
   return SIM_OK;
 }
 
-template <int BN, int NSTAGE>
+template <int BN, int NSTAGE, int NP = 3>
 int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream, void* po = nullptr,
-                int po_cols = 0, long po_ld = 0, long po_plane = 0) {
-  using Cfg = GemmCfg<BN, NSTAGE>;
-  auto kern = gemm_split3_kernel<BN, NSTAGE>;
+                int po_cols = 0, long po_ld = 0, long po_plane = 0, EpiAct act = EpiAct{0, 0, nullptr}) {
+  using Cfg = GemmCfg<BN, NSTAGE, NP>;
+  auto kern = gemm_split3_kernel<BN, NSTAGE, NP>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 attr");
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
@@ -637,7 +682,7 @@ int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cu
   const int nk = (K + kBK - 1) / kBK, tiles = m_tiles * n_tiles;
   int splits = 1, kps = nk;
   static const int splitk = [] { const char* e = getenv("SIM_GEMM_SPLITK"); return e ? atoi(e) : 1; }();
-  if (splitk && !po && tiles * 2 <= 148 && nk >= 32) {
+  if (splitk && !po && !act.mode && tiles * 2 <= 148 && nk >= 32) {
     splits = std::min((148 + tiles - 1) / tiles, nk / 8);
     kps = (nk + splits - 1) / splits;
     splits = (nk + kps - 1) / kps;
@@ -645,14 +690,15 @@ int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cu
   if (splits > 1 && cudaMemset2DAsync(Y, (size_t)ldd * 4, 0, (size_t)N * 4, M, stream) != cudaSuccess)
     return check_launch("gemm_split3 memset");
   kern<<<dim3(tiles, splits), 192, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, static_cast<__nv_bfloat16*>(po),
-                                                        po_cols, po_ld, po_plane, kps);
+                                                        po_cols, po_ld, po_plane, kps, act);
   return check_launch("gemm_split3");
 }
 
-template <int BN, int NSTAGE>
-int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmPCfg<BN, NSTAGE>;
-  auto kern = gemm_split3_persistent_kernel<BN, NSTAGE>;
+template <int BN, int NSTAGE, int NP = 3>
+int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream,
+                           EpiAct act = EpiAct{0, 0, nullptr}) {
+  using Cfg = GemmPCfg<BN, NSTAGE, NP>;
+  auto kern = gemm_split3_persistent_kernel<BN, NSTAGE, NP>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 persistent attr");
   static int sm_count[64] = {};
@@ -662,7 +708,7 @@ int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
   const int total = m_tiles * n_tiles;
   const int grid = total < sm_count[dev & 63] ? total : sm_count[dev & 63];
-  kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total);
+  kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total, act);
   return check_launch("gemm_split3 persistent");
 }
 
@@ -689,7 +735,30 @@ __global__ void split3_kernel(const float* __restrict__ x, long ld, int rows, in
   }
 }
 
+// x = x0 + 2^-11 x1' as two fp16 planes (operand format of the NP = 2 kernels; split2h_store4, common.cuh)
+__global__ void split2h_kernel(const float* __restrict__ x, long ld, int rows, int K, __half* __restrict__ out, long ldo,
+                               long plane) {
+  const int kq = K / 4;
+  const long n = (long)rows * kq;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / kq;
+    const int c = (int)(i % kq) * 4;
+    split2h_store4(out + r * ldo + c, plane, *reinterpret_cast<const float4*>(x + r * ld + c));
+  }
+}
+
 }  // namespace
+
+int split2_f16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream) {
+  SIM_REQUIRE(x && out && rows > 0 && K > 0, SIM_ERR_INVALID, "split2_f16: empty problem / null tensor");
+  SIM_REQUIRE(K % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && plane % 4 == 0 && aligned16(x) &&
+                  (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+              SIM_ERR_ALIGN, "split2_f16: K, strides must be multiples of 4 and bases 16-byte aligned");
+  const long n = (long)rows * (K / 4);
+  const int grid = (int)((n + 255) / 256 < 148L * 16 ? (n + 255) / 256 : 148L * 16);
+  split2h_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, K, static_cast<__half*>(out), ldo, plane);
+  return check_launch("split2_f16");
+}
 
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream) {
   SIM_REQUIRE(x && out && rows > 0 && K > 0, SIM_ERR_INVALID, "split3_bf16: empty problem / null tensor");
@@ -739,8 +808,22 @@ int split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo,
   return check_launch("split3_bf16_t");
 }
 
-int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
-                int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
+// Two operand formats (np):
+//   3: three bf16 planes, six products - exact for any fp32 operand (bf16 keeps the fp32 exponent range);
+//   2: two fp16 planes x0 = fp16(x), x1' = fp16(2^11 (x - x0)), three products x0.w0 + 2^-11 (x0.w1' + x1'.w0) with the
+//      scaled pair in the second TMEM accumulator: representation error 2^-22 per operand (measured 7e-8 of the result
+//      norm at K = 384, below the 3.5e-7 of an fp32 SGEMM's own accumulation) for HALF the tensor-core work, valid while
+//      |x|, |w| < 65504 - the host side selects it only where that bound is provable (in_proj: a LayerNorm output is
+//      bounded by sqrt(C) max|gamma| + max|beta|; the weights are checked when they are split).
+// act_mode / act_col0 / act_bias: optional epilogue activation (EpiAct), not combined with split-K or planes_out.
+int gemm_planes(int np, const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
+                int M, int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane, int act_mode,
+                int act_col0, const float* act_bias) {
+  SIM_REQUIRE(np == 3 || np == 2, SIM_ERR_INVALID, "gemm_planes: np must be 3 (bf16 planes) or 2 (fp16 planes)");
+  SIM_REQUIRE(act_mode >= 0 && act_mode <= 2 && (act_mode != 2 || act_bias) && (!act_mode || !po), SIM_ERR_INVALID,
+              "gemm_planes: epilogue activation 0 / 1 (silu from act_col0) / 2 (softplus(v + bias), bias required), no planes_out");
+  SIM_REQUIRE(np == 3 || !po, SIM_ERR_INVALID, "gemm_planes: planes_out is a bf16 x 3 feature");
+  const EpiAct act{act_mode, act_col0, act_bias};
   SIM_REQUIRE(!po || (N <= 64 && po_cols % 4 == 0 && po_cols <= N + 3 && po_ld % 4 == 0 && po_plane % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(po) & 7u) == 0),
               SIM_ERR_INVALID, "gemm_bf16x3: split-plane output is built for N <= 64 (x_proj) and 8-byte aligned planes");
@@ -772,20 +855,38 @@ int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw,
   if (K <= 2 * kBK && N > 64 && shallow_mode == 1) bn = 192;
   GemmTmaps tm;
   int rc;
+  if (np == 2) {
+    if (bn == 96) bn = 128;
+    if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM, 2))) return rc;
+    if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn, 2))) return rc;
+    switch (bn) {
+      case 64: return launch_gemm<64, 6, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+      case 128: return launch_gemm<128, 5, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+      case 192:
+        if ((long)m_tiles * ((N + 191) / 192) >= 148) return launch_gemm_persistent<192, 4, 2>(tm, Y, ldd, M, N, K, stream, act);
+        return launch_gemm<192, 4, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+      default: return launch_gemm<256, 4, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+    }
+  }
   if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
   if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn))) return rc;
   switch (bn) {
-    case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream, po, po_cols, po_ld, po_plane);
-    case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream)
-                                   : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream);
-    case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream);
+    case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream, po, po_cols, po_ld, po_plane, act);
+    case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act)
+                                   : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+    case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
     case 192: {
       static const int persist = [] { const char* e = getenv("SIM_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
-      if (persist && (long)m_tiles * ((N + 191) / 192) >= 148) return launch_gemm_persistent<192, 3>(tm, Y, ldd, M, N, K, stream);
-      return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream);
+      if (persist && (long)m_tiles * ((N + 191) / 192) >= 148) return launch_gemm_persistent<192, 3>(tm, Y, ldd, M, N, K, stream, act);
+      return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
     }
-    default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream);
+    default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
   }
+}
+
+int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
+                int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane) {
+  return gemm_planes(3, Xs, ldx, xplane, Ws, ldw, wplane, Y, ldd, M, N, K, stream, po, po_cols, po_ld, po_plane, 0, 0, nullptr);
 }
 
 int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M, int N,

@@ -10,7 +10,7 @@ int fps(const float*, int, int, int, int*, float*, cudaStream_t, int pointnet2 =
 int knn_group(const float*, const float*, int, int, int, int, int*, float*, float*, cudaStream_t, int fma = 0);
 int add_layernorm(const void*, const void*, const float*, const float*, const float*, float*, void*, long, int, float,
                   int, int, cudaStream_t, void* planes = nullptr, long plane = 0, const float* row_scale = nullptr,
-                  int rows_per_sample = 0);
+                  int rows_per_sample = 0, int plane_fmt = 0);  // plane_fmt: 0 = three bf16 planes, 1 = two fp16 planes
 int order_gather_fwd(const void*, const void*, const int*, void*, void*, int, int, int, int, int, int, cudaStream_t);
 int order_gather_bwd(const void*, const int*, void*, int, int, int, int, int, int, cudaStream_t);
 int gather_rows(const void*, const int*, const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -31,6 +31,7 @@ struct ScanParams {
   long ld_u, ld_delta, ld_z, ld_B, ld_C, ld_out;
   int batch, L, D;
   int softplus;
+  int z_gate = 0;  // 1: `z` already holds the gate silu(z) (applied by the in_proj epilogue, gemm_split3.cu EpiAct mode 1)
   float* ckpt;  // optional (batch, ceil(L/kScanCkpt), D, 16) fp32: state BEFORE every kScanCkpt-th step (for backward)
   // optional (fp32 activations, warp-specialised kernel): write the result as three bf16 planes instead of `out`
   // (operand format of gemm_split3.cu: out_proj consumes it directly); plane q at out_planes + q * plane elements
@@ -138,6 +139,10 @@ int gemm_f32a_bf16x3(const float* X, long ldx, const void* Ws, long ldw, long wp
                      const float* conv_w = nullptr, const float* conv_b = nullptr, float* U = nullptr, long ldu = 0,
                      int batch = 0, int L = 0);
 int split3_bf16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
+int split2_f16(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
+int gemm_planes(int np, const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd,
+                int M, int N, int K, cudaStream_t stream, void* po, int po_cols, long po_ld, long po_plane, int act_mode,
+                int act_col0, const float* act_bias);
 int split3_bf16_t(const float* x, long ld, int rows, int K, void* out, long ldo, long plane, cudaStream_t stream);
 int gemm_bf16x3(const void* Xs, long ldx, long xplane, const void* Ws, long ldw, long wplane, float* Y, long ldd, int M,
                 int N, int K, cudaStream_t stream, void* po = nullptr, int po_cols = 0, long po_ld = 0, long po_plane = 0);

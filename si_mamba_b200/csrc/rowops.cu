@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
                                                             float* __restrict__ res_out, TY* __restrict__ y,
                                                             long rows, int C, float eps,
                                                             __nv_bfloat16* __restrict__ planes, long plane,
-                                                            const float* __restrict__ row_scale, int rows_per_sample) {
+                                                            const float* __restrict__ row_scale, int rows_per_sample,
+                                                            int plane_fmt) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -111,14 +112,18 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const TX* __restrict
       o.z = (v[i].z - mean) * rstd * g.z + bb.z;
       o.w = (v[i].w - mean) * rstd * g.w + bb.w;
       if (y) st4<TY>(y + row * C + 4 * q, o);
-      if (planes) split3_store4(planes + row * C + 4 * q, plane, o);
+      if (planes) {
+        if (plane_fmt) split2h_store4(reinterpret_cast<__half*>(planes) + row * C + 4 * q, plane, o);
+        else split3_store4(planes + row * C + 4 * q, plane, o);
+      }
     }
   }
 }
 
 int add_layernorm(const void* x, const void* x2, const float* res_in, const float* gamma, const float* beta,
                   float* res_out, void* y, long rows, int C, float eps, int dtype_x, int dtype_y,
-                  cudaStream_t stream, void* planes, long plane, const float* row_scale, int rows_per_sample) {
+                  cudaStream_t stream, void* planes, long plane, const float* row_scale, int rows_per_sample,
+                  int plane_fmt) {
   SIM_REQUIRE(!row_scale || rows_per_sample > 0, SIM_ERR_INVALID, "add_layernorm: row_scale needs rows_per_sample > 0");
   SIM_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, SIM_ERR_INVALID,
               "add_layernorm: C must be a multiple of 4 and <= 1024 (got %d)", C);
@@ -134,7 +139,7 @@ int add_layernorm(const void* x, const void* x2, const float* res_in, const floa
                                                                static_cast<const TX*>(x2), res_in, gamma,    \
                                                                beta, res_out, static_cast<TY*>(y), rows, C, eps,  \
                                                                static_cast<__nv_bfloat16*>(planes), plane, row_scale, \
-                                                               rows_per_sample)
+                                                               rows_per_sample, plane_fmt)
 #define SIM_LN_MAXV(TX, TY)                     \
   if (C <= 384) {                               \
     SIM_LN_LAUNCH(TX, TY, 3);                   \

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(Cfg::NT) selective_scan_fwd_kernel(const __gri
       float4 gv = make_float4(1.f, 1.f, 1.f, 1.f);
       if (has_z && !(Cfg::DBG & 2)) {
         const float4 zv = lds4<T>(sz + r * CH + cc);
-        gv = make_float4(silu_f(zv.x), silu_f(zv.y), silu_f(zv.z), silu_f(zv.w));
+        gv = p.z_gate ? zv : make_float4(silu_f(zv.x), silu_f(zv.y), silu_f(zv.z), silu_f(zv.w));
       }
       *reinterpret_cast<float4*>(w_g + r * CHP + cc) = gv;
     }
@@ -328,6 +328,8 @@ int selective_scan_fwd(const ScanParams& p, int dtype, int variant, cudaStream_t
   SIM_REQUIRE(p.batch > 0 && p.L > 0 && p.D > 0, SIM_ERR_INVALID, "selective_scan_fwd: empty problem");
   SIM_REQUIRE(p.u && p.delta && (p.wdt || (p.Bm && p.Cm)) && (p.out || p.out_planes) && p.A, SIM_ERR_INVALID,
               "selective_scan_fwd: null tensor");
+  SIM_REQUIRE(!p.z_gate || (p.z && !p.ckpt), SIM_ERR_INVALID,
+              "selective_scan_fwd: the pre-gated z flag is an inference feature (needs z, no checkpoints: the backward differentiates silu)");
   SIM_REQUIRE(!p.wdt || (p.D % 64 == 0 && aligned16(p.wdt) && !p.ckpt), SIM_ERR_INVALID,
               "selective_scan_fwd: fused dt_proj needs D %% 64 == 0, 16-byte aligned weight planes and no checkpoints");
   if (p.wdt) variant = 5900;

@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_fwd_ws_kern
           float4 gv = make_float4(1.f, 1.f, 1.f, 1.f);
           if (has_z) {
             const float4 zv = lds4<T>(sz + r * CH + cc);
-            if constexpr (Cfg::EP) gv = silu4_poly(zv);
+            if (p.z_gate) gv = zv;  // the in_proj epilogue already applied silu (gemm_split3.cu, EpiAct mode 1)
+            else if constexpr (Cfg::EP) gv = silu4_poly(zv);
             else gv = make_float4(silu_f(zv.x), silu_f(zv.y), silu_f(zv.z), silu_f(zv.w));
           }
           gate[par][i] = gv;

@@ -523,7 +523,8 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
                   eps: float = 1e-5, x2: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
                   want_residual: bool = True, split: bool = False):
     """res = x (+ x2) (+ residual) in fp32;  y = LayerNorm(res).  -> (y, res or None).  Forward only.
-    ``split``: y is returned as a Split3 (three bf16 planes of the fp32 result) for linear_split3."""
+    ``split``: y is returned as a Split3 for linear_split3 - True: three bf16 planes of the fp32 result, "f16x2": two
+    fp16 planes (see split2h)."""
     _cuda(x, residual, weight, bias, x2)
     x = x.contiguous()
     Cc = x.shape[-1]
@@ -536,8 +537,13 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], weight: tor
         x2 = x2.to(x.dtype).contiguous()
     if split:
         assert Cc % 8 == 0
-        planes = torch.empty(3, rows, Cc, dtype=torch.bfloat16, device=x.device)
-        _lib.call("sim_add_layernorm_split3", _p(x), _p(x2), _p(residual), _p(_f32c(weight)), _p(_f32c(bias)),
+        if split == "f16x2":  # two fp16 planes (hi, 2^11 lo): the caller has checked that |y| stays inside the fp16 range
+            planes = torch.empty(2, rows, Cc, dtype=torch.float16, device=x.device)
+            entry = "sim_add_layernorm_split2h"
+        else:
+            planes = torch.empty(3, rows, Cc, dtype=torch.bfloat16, device=x.device)
+            entry = "sim_add_layernorm_split3"
+        _lib.call(entry, _p(x), _p(x2), _p(residual), _p(_f32c(weight)), _p(_f32c(bias)),
                   _p(res_out), _p(planes), planes.stride(0), rows, Cc, float(eps), _dt(x), _stream())
         return Split3(planes, x.shape), res_out
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
@@ -600,9 +606,10 @@ class AddLayerNorm(torch.autograd.Function):
 
 
 class Split3:
-    """An fp32 activation (..., K) carried as three bf16 planes (3, rows, K): the operand format of the tcgen05
-    projection GEMM (csrc/gemm_split3.cu).  Produced by add_layernorm / causal_conv1d_tm / selective_scan_tm with
-    ``split=True`` or by split3(); consumed by linear_split3."""
+    """An fp32 activation (..., K) carried as three bf16 planes (3, rows, K) - or, where its magnitude is provably
+    inside the fp16 range, two fp16 planes (2, rows, K) -: the operand formats of the tcgen05 projection GEMM
+    (csrc/gemm_split3.cu).  Produced by add_layernorm / causal_conv1d_tm / selective_scan_tm with ``split`` or by
+    split3() / split2h(); consumed by linear_split3."""
 
     __slots__ = ("planes", "shape")
 
@@ -635,6 +642,19 @@ def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
+def split2h(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (..., K) -> (2, rows, Kp) fp16 planes with x = p0 + 2^-11 p1 to 2^-22 relative (p0 = fp16(x), p1 =
+    fp16(2^11 (x - p0))), Kp = K rounded up to 8.  Only for operands with |x| < 65504 (callers check)."""
+    _cuda(x)
+    assert x.dtype == torch.float32
+    K = x.shape[-1]
+    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else _as_rows(x)
+    rows, Kp = x2.shape[0], (K + 7) // 8 * 8
+    out = (torch.zeros if Kp != K else torch.empty)(2, rows, Kp, dtype=torch.float16, device=x.device)
+    _lib.call("sim_split2_f16", _p(x2), x2.stride(0), rows, K, _p(out), out.stride(1), out.stride(0), _stream())
+    return out
+
+
 def split3_t(x: torch.Tensor) -> torch.Tensor:
     """fp32 (rows, K) -> planes of the transpose (3, K, rows_p) bf16, rows_p = rows rounded up to 8 (zero padded): one
     kernel instead of ``split3(x.t().contiguous())``."""
@@ -647,15 +667,27 @@ def split3_t(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y (rows, N) fp32 = x @ w.T from pre-split planes xs (3, rows, >=K), ws (3, N, >=K) (tcgen05 kernel)."""
-    _cuda(xs, ws)
-    assert xs.dtype == torch.bfloat16 and ws.dtype == torch.bfloat16 and xs.stride(2) == 1 and ws.stride(2) == 1
+_EPI_ACT = {None: 0, "silu_from": 1, "softplus_bias": 2}
+
+
+def linear_split3(xs: torch.Tensor, ws: torch.Tensor, K: int, out: Optional[torch.Tensor] = None, act: Optional[str] = None,
+                  act_col0: int = 0, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y (rows, N) fp32 = x @ w.T from pre-split planes (tcgen05 kernel): xs (3, rows, >=K), ws (3, N, >=K) bf16, or
+    xs (2, rows, >=K), ws (2, N, >=K) fp16 (split2h).  ``act`` (inference): "silu_from" - columns >= act_col0 leave as
+    silu(y); "softplus_bias" - every column leaves as softplus(y + bias) (sim_gemm_planes)."""
+    _cuda(xs, ws, bias)
+    assert xs.dtype == ws.dtype and xs.dtype in (torch.bfloat16, torch.float16) and xs.stride(2) == 1 and ws.stride(2) == 1
+    np_ = 3 if xs.dtype == torch.bfloat16 else 2
+    assert xs.shape[0] == np_ and ws.shape[0] == np_
     M, N = xs.shape[1], ws.shape[1]
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=xs.device)
-    _lib.call("sim_gemm_bf16x3", _p(xs), xs.stride(1), xs.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out),
-              out.stride(0), M, N, K, _stream())
+    if np_ == 3 and act is None:
+        _lib.call("sim_gemm_bf16x3", _p(xs), xs.stride(1), xs.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out),
+                  out.stride(0), M, N, K, _stream())
+    else:
+        _lib.call("sim_gemm_planes", np_, _p(xs), xs.stride(1), xs.stride(0), _p(ws), ws.stride(1), ws.stride(0), _p(out),
+                  out.stride(0), M, N, K, _EPI_ACT[act], int(act_col0), _p(_f32c(bias)), _stream())
     return out
 
 
@@ -844,11 +876,15 @@ def conv_xproj_f32(x: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch
     return u, x_dbl, planes
 
 
-def linear_f32_x3(x, weight_planes: torch.Tensor, K: int) -> torch.Tensor:
-    """y = x @ W.T (fp32-accurate) with W given as split planes (see split3); x is a Split3 from its producer, or an
-    fp32 tensor that is split here."""
-    xs = x.planes if isinstance(x, Split3) else split3(x)
-    y = linear_split3(xs, weight_planes, K)
+def linear_f32_x3(x, weight_planes: torch.Tensor, K: int, act: Optional[str] = None, act_col0: int = 0,
+                  bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ W.T (fp32-accurate) with W given as split planes (see split3 / split2h); x is a Split3 from its producer,
+    or an fp32 tensor that is split here (in the weight planes' format)."""
+    if isinstance(x, Split3):
+        xs = x.planes
+    else:
+        xs = split3(x) if weight_planes.dtype == torch.bfloat16 else split2h(x)
+    y = linear_split3(xs, weight_planes, K, act=act, act_col0=act_col0, bias=bias)
     return y.view(*x.shape[:-1], weight_planes.shape[1])
 
 
@@ -924,10 +960,12 @@ def causal_conv1d_fn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
 # ----------------------------------------------------------------------------- selective scan (a-11)
 def selective_scan_tm(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False,
                       out: Optional[torch.Tensor] = None, variant: int = 0,
-                      checkpoints: Optional[torch.Tensor] = None, split: bool = False):
+                      checkpoints: Optional[torch.Tensor] = None, split: bool = False, z_gate: bool = False):
     """Token-major selective scan (forward only).  u, delta, z (B,L,D); Bm, Cm (B,L,N) - all may be column slices of
     wider row-major buffers; A (D,N) fp32.  Returns out (B,L,D) in u's dtype.  ``checkpoints`` (fp32,
-    scan_checkpoint_shape) receives the tile-start states the backward kernel needs."""
+    scan_checkpoint_shape) receives the tile-start states the backward kernel needs.  ``z_gate`` (inference): z already
+    holds silu(z) (in_proj epilogue, linear_split3(act="silu_from")), the kernel multiplies by it as is."""
+    delta_softplus = int(bool(delta_softplus)) | (2 if z_gate else 0)
     _cuda(u, delta, A, Bm, Cm, D, z, delta_bias)
     B, L, Dm = u.shape
     N = A.shape[1]

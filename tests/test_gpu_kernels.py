@@ -659,3 +659,73 @@ def test_point_linear3(ops):
     for act, fn in (("none", lambda t: t), ("relu", torch.relu), ("gelu", torch.nn.functional.gelu)):
         y = ops.point_linear3(dev(x), dev(w), dev(b), act)
         assert torch.allclose(y.cpu(), fn(torch.nn.functional.linear(x, w, b)), rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- a-10 fp16 x 2 planes, epilogue activations
+@pytest.mark.parametrize("M,N,K", [(16384, 1536, 384), (4096, 1536, 384), (1000, 768, 384), (100, 64, 40), (7, 384, 128),
+                                   (300, 256, 72)])
+def test_gemm_f16x2(ops, M, N, K):
+    """Two fp16 planes per operand (hi + 2^-11 lo), three products: fp32-GEMM class accuracy against fp64, and agreement
+    with the six-product bf16 path; the planes reconstruct the operand to 2^-22."""
+    g = torch.Generator().manual_seed(M + N + 1)
+    x = torch.randn(M, K, generator=g) * 3.0
+    x[0, 0], x[-1, -1] = 2.9e4, -1.0e-6  # the ends of the admitted range
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    ref = x.double() @ w.double().t()
+    xs, ws = ops.split2h(dev(x)), ops.split2h(dev(w))
+    assert xs.dtype == torch.float16 and xs.shape[0] == 2
+    rec = xs[0].double() + xs[1].double() / 2048
+    assert ((rec[:, :K].cpu() - x.double()).abs() <= x.double().abs() * 2.0 ** -21 + 2.0 ** -35).all()
+    y = ops.linear_split3(xs, ws, K)
+    assert y.shape == (M, N)
+    assert rel_err(y.cpu().double(), ref) < 2e-6
+    y3 = ops.linear_split3(ops.split3(dev(x)), ops.split3(dev(w)), K)
+    assert rel_err(y.cpu().double(), y3.cpu().double()) < 2e-6
+
+
+def test_add_layernorm_split2h(ops):
+    g = torch.Generator().manual_seed(5)
+    B, L, C = 2, 77, 384
+    x, r = dev(torch.randn(B, L, C, generator=g)), dev(torch.randn(B, L, C, generator=g))
+    w, b = dev(torch.randn(C, generator=g)), dev(torch.randn(C, generator=g))
+    y, res = ops.add_layernorm(x, r, w, b)
+    ys, res2 = ops.add_layernorm(x, r, w, b, split="f16x2")
+    assert ys.planes.dtype == torch.float16 and ys.planes.shape == (2, B * L, C) and torch.equal(res, res2)
+    rec = (ys.planes[0].double() + ys.planes[1].double() / 2048).view(B, L, C)
+    assert ((rec - y.double()).abs() <= y.double().abs() * 2.0 ** -21 + 2.0 ** -35).all()
+    assert torch.equal(ys.planes, ops.split2h(y))  # the producer's planes are the standalone split's
+
+
+@pytest.mark.parametrize("fmt", ["bf16x3", "f16x2"])
+@pytest.mark.parametrize("B,L,D,C", [(4, 512, 768, 384), (2, 37, 64, 128), (40, 128, 192, 96)])
+def test_gemm_epilogue_activations_feed_the_scan(ops, fmt, B, L, D, C):
+    """in_proj / dt_proj epilogues that hand the scan silu(z) / softplus(delta + bias) (sim_gemm_planes act_mode 1 / 2):
+    same device arithmetic as the scan's own pre-pass, so the scan output is bit-identical either way."""
+    g = torch.Generator().manual_seed(B * L + D)
+    split = ops.split3 if fmt == "bf16x3" else ops.split2h
+    h = dev(torch.randn(B * L, C, generator=g))
+    w_in = dev(torch.randn(2 * D, C, generator=g) * C ** -0.5)
+    hs, ws = split(h), split(w_in)
+    xz0 = ops.linear_split3(hs, ws, C)
+    xz1 = ops.linear_split3(hs, ws, C, act="silu_from", act_col0=D)
+    assert torch.equal(xz0[:, :D], xz1[:, :D])
+    assert rel_err(xz1[:, D:].double(), torch.nn.functional.silu(xz0[:, D:].double())) < 1e-6
+    dtl = dev(torch.randn(B * L, 32, generator=g))
+    w_dt = dev(torch.randn(D, 32, generator=g) * 0.2)
+    bias = dev(torch.randn(D, generator=g) - 3.0)
+    ds, wds = split(dtl), split(w_dt)
+    d0 = ops.linear_split3(ds, wds, 32)
+    d1 = ops.linear_split3(ds, wds, 32, act="softplus_bias", bias=bias)
+    assert rel_err(d1.double(), torch.nn.functional.softplus(d0.double() + bias.double())) < 1e-6
+    u = dev(torch.randn(B, L, D, generator=g))
+    A = -dev(torch.rand(D, 16, generator=g) * 4 + 0.1)
+    Bm, Cm = dev(torch.randn(B, L, 16, generator=g)), dev(torch.randn(B, L, 16, generator=g))
+    Dv = dev(torch.randn(D, generator=g))
+    v = lambda t, a, b_: t.view(B, L, -1)[..., a:b_]
+    base = ops.selective_scan_tm(u, v(d0, 0, D), A, Bm, Cm, Dv, v(xz0, D, 2 * D), bias, True)
+    gated = ops.selective_scan_tm(u, v(d0, 0, D), A, Bm, Cm, Dv, v(xz1, D, 2 * D), bias, True, z_gate=True)
+    both = ops.selective_scan_tm(u, v(d1, 0, D), A, Bm, Cm, Dv, v(xz1, D, 2 * D), None, False, z_gate=True)
+    assert torch.equal(base, gated) and torch.equal(base, both)
+    if D % 64 == 0:
+        sp = ops.selective_scan_tm(u, v(d1, 0, D), A, Bm, Cm, Dv, v(xz1, D, 2 * D), None, False, z_gate=True, split=True)
+        assert torch.equal(sp.planes.float().sum(0).view(B, L, D), base)

@@ -213,3 +213,54 @@ def test_bench_inputs_match_oracle(lib, golden, name):
     with torch.no_grad():
         logits2 = m(pts.cuda())
     assert ((logits2.cpu() - ref).abs().max() / scale) < 2e-3
+
+
+def test_inproj_f16_planes_and_hoisted_activations(lib, monkeypatch):
+    """The two inference-only choices of the fp32 mixer - in_proj on two fp16 planes (LayerNorm output: bounded operand)
+    and silu(z) / softplus(delta + bias) applied by the producing GEMM's epilogue - against the path without them: the
+    hoists are bit-identical, the fp16 planes agree to fp32-GEMM accuracy; an out-of-range LayerNorm gain is refused."""
+    import si_mamba_b200 as sm
+    from si_mamba_b200 import autograd as ag, ops
+    m = make_model(sm.finetune_modelnet()).cuda()
+    pts = tokenizer.synthetic_clouds(3, 1024, 7, "surface").cuda()
+
+    def run(f16, hoist):
+        monkeypatch.setattr(ag, "_INPROJ_F16", f16)
+        monkeypatch.setattr(ag, "_HOIST_ACT", hoist)
+        ag.invalidate_param_cache()
+        with torch.no_grad():
+            return m(pts)
+
+    # bit-exactness is a property of the mixer stack (the tokenizer / Encoder in front of it may accumulate with atomics)
+    tok = torch.randn(3, 512, 384, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    pos = torch.randn(3, 512, 384, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+
+    def run_stack(f16, hoist):
+        monkeypatch.setattr(ag, "_INPROJ_F16", f16)
+        monkeypatch.setattr(ag, "_HOIST_ACT", hoist)
+        ag.invalidate_param_cache()
+        with torch.no_grad():
+            return m.blocks(tok, pos)
+
+    sbase = run_stack(False, "0")
+    assert torch.equal(run_stack(False, "0"), sbase)
+    assert torch.equal(run_stack(False, "z"), sbase) and torch.equal(run_stack(False, "zdt"), sbase)
+    sfast = run_stack(True, "z")
+    assert torch.equal(run_stack(True, "zdt"), sfast) and torch.equal(run_stack(True, "0"), sfast)
+    err = (sfast - sbase).abs().max() / sbase.abs().max()
+    assert err < 2e-5, err
+    base, fast = run(False, "0"), run(True, "z")
+    err = (fast - base).abs().max() / base.abs().max()
+    assert err < 2e-5, err
+    # the range check: which format the Block asks its LayerNorm for
+    blk = m.blocks.layers[1]
+    seen = []
+    real = ops.add_layernorm
+    monkeypatch.setattr(ops, "add_layernorm", lambda *a, **k: (seen.append(k.get("split")), real(*a, **k))[1])
+    h = torch.randn(2, 64, 384, device="cuda")
+    with torch.no_grad():
+        blk(h, h.clone())
+        blk.norm.weight.mul_(4000.0)  # sqrt(384) * 4000 > 3e4: no longer provably inside the fp16 range
+        blk(h, h.clone())
+        blk.norm.weight.div_(4000.0)
+    assert seen == ["f16x2", True], seen

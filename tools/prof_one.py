@@ -50,6 +50,23 @@ def main():
         outs = [torch.empty(M, N, device=dev) for _ in range(3)]
         for i in range(a.iters):
             ops.linear_split3(xs[i % 3], ws, K, out=outs[i % 3])
+    elif a.kernel == "gemm_f16":  # in_proj on two fp16 planes with the silu epilogue on the z half (the C1 inference path)
+        M, N, K = B * L, 1536, 384
+        xs = [ops.split2h(r(M, K)) for _ in range(3)]
+        ws = ops.split2h(r(N, K) * K ** -0.5)
+        outs = [torch.empty(M, N, device=dev) for _ in range(3)]
+        for i in range(a.iters):
+            ops.linear_split3(xs[i % 3], ws, K, out=outs[i % 3], act="silu_from", act_col0=N // 2)
+    elif a.kernel == "scan_gate":  # the scan as the C1 inference path calls it: z arrives as the gate silu(z)
+        sets = []
+        for _ in range(3):
+            xz, u, dl, xd = r(B, L, 2 * D).to(dt), r(B, L, D).to(dt), (0.5 * r(B, L, D)).to(dt), r(B, L, 56).to(dt)
+            sets.append((u, dl, xd[..., 24:40], xd[..., 40:], xz[..., D:], torch.empty(B, L, D, dtype=dt, device=dev)))
+        A = -torch.arange(1, 17, device=dev, dtype=torch.float32).repeat(D, 1)
+        Dv, bias = torch.ones(D, device=dev), torch.full((D,), -4.0, device=dev)
+        for i in range(a.iters):
+            s = sets[i % 3]
+            ops.selective_scan_tm(s[0], s[1], A, s[2], s[3], Dv, s[4], bias, True, out=s[5], variant=a.variant, z_gate=True)
     elif a.kernel == "scanfused":
         sets = []
         for _ in range(3):
