@@ -82,6 +82,75 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- CTA pairs (thread-block cluster of two): TMA multicast of the shared W tile, cross-CTA stage release
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one tensor copy whose box lands at the SAME shared-memory offset, and signals the mbarrier at the same offset, in every
+// CTA of cta_mask
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, "
+      "%4}], [%5], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of cta_mask once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+// ---- cta_group::2: one MMA spans the two SMs of a pair (M = 256; each CTA supplies its 128 rows of A, HALF of the W tile
+// and holds its 128 accumulator lanes).  PTX forms as in CUTLASS' sm100 2-SM atoms (cute/arch/{mma_sm100_umma,
+// copy_sm100_tma,tmem_allocator_sm100}.hpp, cutlass/arch/barrier.h).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> rank 0's copy
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {  // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// tensor copy into MY shared memory whose completion bytes are counted on rank 0's mbarrier (the MMA issuer's)
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
+      "[%5];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar) & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // 32 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -288,10 +357,10 @@ __global__ void __launch_bounds__(192, GemmCfg<BN, NSTAGE_, NP>::MINB) gemm_spli
 // epilogue warps (two per TMEM lane quadrant, half of the tile's columns each) first drain both accumulators into
 // registers (BN / 2 fp32 values per thread), release the accumulators to the MMA warp, and only then do the slow part
 // (staging + global stores) while the next tile's MMAs are already running.
-template <int BN, int NSTAGE_, int NP = 3>
+template <int BN, int NSTAGE_, int NP = 3, int MC = 0>
 struct GemmPCfg {
   static constexpr int A_TILE = kBM * kBK * 2;
-  static constexpr int B_TILE = BN * kBK * 2;
+  static constexpr int B_TILE = (MC == 2 ? BN / 2 : BN) * kBK * 2;  // MC == 2: this CTA holds half of the pair's W tile
   static constexpr int STAGE = NP * A_TILE + NP * B_TILE;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int NEPI = 8;                      // epilogue warps
@@ -300,15 +369,37 @@ struct GemmPCfg {
   static constexpr int STG = NEPI * 32 * STG_LD * 4;  // one 32 x 32 (padded) staging tile per epilogue warp
   static constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
   static constexpr int CW = BN / 2;                   // columns per epilogue warp
+  // accumulator sets in TMEM (each = leading + correction accumulator, 2 BN columns): two when they fit (BN <= 128), so the
+  // MMAs of tile i + 1 start while tile i is still being drained.  ncu on the single-set kernel (profiles/r02_gemm_ncu.md):
+  // the tensor pipe idles ~3 us per tile between the last MMA of a tile and the first of the next (commit -> epilogue
+  // wake-up -> six dependent tcgen05.ld -> release -> MMA warp wake-up), 29 % of the bf16 x 3 in_proj and 49 % of the
+  // fp16 x 2 one.
+  static constexpr int NACC = 4 * BN <= 512 ? 2 : 1;
   static_assert(CW % 32 == 0 && 2 * BN <= 512, "two column halves of whole 32-column chunks; both accumulators in TMEM");
   static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(A_TILE % 512 == 0 && B_TILE % 512 == 0 && STAGE % 512 == 0, "swizzle-64B tiles need 512-byte aligned bases");
 };
 
-template <int BN, int NSTAGE_, int NP>
-__global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
+// MC = 1: the CTAs run as PAIRS (cluster of two, launch attribute).  A pair owns two vertically adjacent 128-row tiles of
+// the same BN columns, so both need the same W tile: each CTA fetches half of its rows and the TMA unit multicasts that
+// half into both CTAs' shared memory - one L2 read of W per pair instead of two.  (ncu, profiles/r02_gemm_ncu.md: the kernel
+// is bound by operand delivery from L2 at ~9 TB/s, not by the tensor pipe, in both operand formats.)  A stage may be
+// refilled once BOTH CTAs' MMAs have read it (the peer's half lands in my buffer), so the MMA warp's commit arrives on
+// the `empty` barrier of both CTAs (count 2); the CTAs walk the same number of tiles and k-blocks.
+// MC = 2: the pair additionally shares ONE tensor-core instruction stream: rank 0 issues tcgen05.mma.cta_group::2 with
+// M = 256, each CTA loads only ITS half of the W rows (no multicast: the MMA reads both halves where they lie), so the
+// bytes delivered into each SM per k-block drop from A + W to A + W / 2.  (Measured: multicast alone, MC = 1, changes
+// nothing - the bound is bytes delivered to the SMs, not L2 reads.)  Barriers: both CTAs' tensor copies count on rank 0's
+// `full`; rank 0's commits arrive on both CTAs' `empty` / `acc_full`; both CTAs' epilogue warps arrive on rank 0's `acc_empty`.
+template <int BN, int NSTAGE_, int NP, int MC>
+__global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP, MC>::NT, 1)
     gemm_split3_persistent_kernel(const __grid_constant__ GemmTmaps tm, float* __restrict__ Y, long ldd, int M, int N, int K,
                                   int n_tiles, int total_tiles, const EpiAct act) {
-  using Cfg = GemmPCfg<BN, NSTAGE_, NP>;
+  using Cfg = GemmPCfg<BN, NSTAGE_, NP, MC>;
+  static_assert(!MC || (BN / 2) % 8 == 0, "half W tiles must be whole 8-row swizzle groups");
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int tile_first = MC ? blockIdx.x >> 1 : blockIdx.x;  // MC: `tile` counts pair tiles (two 128-row tiles)
+  const int tile_step = MC ? gridDim.x >> 1 : gridDim.x;
   using PP = PlaneProducts<NP>;
   constexpr int NSTAGE = Cfg::NSTAGE, CW = Cfg::CW;
   extern __shared__ unsigned char smem_raw[];
@@ -317,53 +408,79 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
   float* stg_base = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE + Cfg::STG);
   uint64_t* empty = full + NSTAGE;
+  constexpr int NACC = Cfg::NACC;
   uint64_t* acc_full = empty + NSTAGE;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (K + kBK - 1) / kBK;
-  constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+  constexpr uint32_t kTmemCols = 2 * BN * NACC <= 128 ? 128 : (2 * BN * NACC <= 256 ? 256 : 512);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm.x);
     tma_prefetch_desc(&tm.w);
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC == 1 ? 2 : 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, Cfg::NEPI);
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], MC == 2 ? 2 * Cfg::NEPI : Cfg::NEPI);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if constexpr (MC == 2) {
+    cluster_sync_all();  // both CTAs are resident before the paired allocation
+    if (warp == 1) tmem_alloc2(tmem_ptr, kTmemCols);
+  } else {
+    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_ptr;
+  const uint32_t tmem_base = *tmem_ptr;
+  auto tile_m0 = [&](int tile) { return (MC ? 2 * (tile / n_tiles) + crank : tile / n_tiles) * kBM; };
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int m0 = tile_m0(tile), n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % NSTAGE;
           if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
           unsigned char* st = smem + s * Cfg::STAGE;
+          if constexpr (MC == 2) {
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE);  // both CTAs' copies count on rank 0's barrier
+            tma_load_3d_pair(st, &tm.x, kb * kBK, m0, 0, &full[s]);
+            tma_load_3d_pair(st + NP * Cfg::A_TILE, &tm.w, kb * kBK, n0 + crank * (BN / 2), 0, &full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
           tma_load_3d(st, &tm.x, kb * kBK, m0, 0, &full[s]);
-          tma_load_3d(st + NP * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+          if constexpr (MC == 1) {
+            // my half of the W rows, plane by plane (the box is (kBK, BN / 2, 1)), into both CTAs
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+              tma_load_3d_mc(st + NP * Cfg::A_TILE + q * Cfg::B_TILE + crank * (BN / 2) * kBK * 2, &tm.w, kb * kBK,
+                             n0 + crank * (BN / 2), q, &full[s], (uint16_t)3);
+          } else {
+            tma_load_3d(st + NP * Cfg::A_TILE, &tm.w, kb * kBK, n0, 0, &full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_planes(kBM, BN, NP);
+    if (lane == 0 && (MC != 2 || crank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_planes(MC == 2 ? 2 * kBM : kBM, BN, NP);
       int it = 0, i = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-        if (i >= 1) {  // the epilogue warps have drained the previous tile's accumulators
-          mbar_wait(acc_empty, (i - 1) & 1);
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++i) {
+        const int ab = i % NACC;
+        const uint32_t tmem_d = tmem_base + ab * 2 * BN;
+        if (i >= NACC) {  // the epilogue warps have drained the tile that used this accumulator set last
+          mbar_wait(&acc_empty[ab], ((i / NACC) - 1) & 1);
           tc_fence_after();
         }
         for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -378,12 +495,18 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
             for (int k = 0; k < kBK / kUK; ++k) {
               const uint64_t da = umma_desc_sw64(a0 + PP::pa(q) * Cfg::A_TILE + k * kUK * 2);
               const uint64_t db = umma_desc_sw64(b0 + PP::pb(q) * Cfg::B_TILE + k * kUK * 2);
-              umma_bf16(tmem_d + (q == PP::N - 1 ? 0 : BN), da, db, idesc, q == PP::N - 1 ? (kb | k) != 0 : (kb | q | k) != 0);
+              if constexpr (MC == 2)
+                umma2_f16(tmem_d + (q == PP::N - 1 ? 0 : BN), da, db, idesc, q == PP::N - 1 ? (kb | k) != 0 : (kb | q | k) != 0);
+              else
+                umma_bf16(tmem_d + (q == PP::N - 1 ? 0 : BN), da, db, idesc, q == PP::N - 1 ? (kb | k) != 0 : (kb | q | k) != 0);
             }
           }
-          umma_commit(&empty[s]);
+          if constexpr (MC == 2) umma2_commit_mc(&empty[s], (uint16_t)3);
+          else if constexpr (MC == 1) umma_commit_mc(&empty[s], (uint16_t)3);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(acc_full);
+        if constexpr (MC == 2) umma2_commit_mc(&acc_full[ab], (uint16_t)3);
+        else umma_commit(&acc_full[ab]);
       }
     }
   } else {
@@ -391,9 +514,11 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
     float* stg = stg_base + ew * 32 * Cfg::STG_LD;
     int i = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
-      mbar_wait(acc_full, i & 1);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++i) {
+      const int m0 = tile_m0(tile), n0 = (tile % n_tiles) * BN;
+      const int ab = i % NACC;
+      const uint32_t tmem_d = tmem_base + ab * 2 * BN;
+      mbar_wait(&acc_full[ab], (i / NACC) & 1);
       tc_fence_after();
       float v[CW / 32][32];
 #pragma unroll
@@ -407,7 +532,10 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);  // the MMA warp may overwrite the accumulators: the rest overlaps its work
+      if (lane == 0) {  // the MMA warp may overwrite this set: the rest overlaps its work
+        if constexpr (MC == 2) mbar_arrive_rank0(&acc_empty[ab]);
+        else mbar_arrive(&acc_empty[ab]);
+      }
 #pragma unroll
       for (int c = 0; c < CW / 32; ++c) {
         const int nc = n0 + half * CW + c * 32;
@@ -434,9 +562,11 @@ __global__ void __launch_bounds__(GemmPCfg<BN, NSTAGE_, NP>::NT, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers / read its tiles
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, kTmemCols);
+    if constexpr (MC == 2) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -648,7 +778,8 @@ __global__ void __launch_bounds__(576, 1) gemm_f32a_split3_kernel(const __grid_c
 }
 
 // 3-D map over the three bf16 planes of a row-major (rows, K) operand: dims (K, rows, 3), 64-byte swizzle.
-int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows, int np = 3) {
+int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld, long plane, int box_rows, int np = 3,
+                     int box_planes = 0) {
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -656,7 +787,7 @@ int make_tmap_planes(CUtensorMap* m, const void* base, int K, int rows, long ld,
   }
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)np};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, (cuuint32_t)np};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, (cuuint32_t)(box_planes ? box_planes : np)};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = enc(m, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -694,11 +825,11 @@ int launch_gemm(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cu
   return check_launch("gemm_split3");
 }
 
-template <int BN, int NSTAGE, int NP = 3>
+template <int BN, int NSTAGE, int NP = 3, int MC = 0>
 int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N, int K, cudaStream_t stream,
                            EpiAct act = EpiAct{0, 0, nullptr}) {
-  using Cfg = GemmPCfg<BN, NSTAGE, NP>;
-  auto kern = gemm_split3_persistent_kernel<BN, NSTAGE, NP>;
+  using Cfg = GemmPCfg<BN, NSTAGE, NP, MC>;
+  auto kern = gemm_split3_persistent_kernel<BN, NSTAGE, NP, MC>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("gemm_split3 persistent attr");
   static int sm_count[64] = {};
@@ -706,10 +837,24 @@ int launch_gemm_persistent(const GemmTmaps& tm, float* Y, long ldd, int M, int N
   cudaGetDevice(&dev);
   if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + kBM - 1) / kBM;
-  const int total = m_tiles * n_tiles;
-  const int grid = total < sm_count[dev & 63] ? total : sm_count[dev & 63];
-  kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total, act);
-  return check_launch("gemm_split3 persistent");
+  if constexpr (MC) {
+    const int total = ((m_tiles + 1) / 2) * n_tiles;  // pair tiles
+    int grid = 2 * total < sm_count[dev & 63] ? 2 * total : (sm_count[dev & 63] & ~1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(Cfg::NT), cfg.dynamicSmemBytes = Cfg::SMEM, cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tm, Y, ldd, M, N, K, n_tiles, total, act) != cudaSuccess)
+      return check_launch("gemm_split3 persistent (CTA pairs)");
+    return check_launch("gemm_split3 persistent (CTA pairs)");
+  } else {
+    const int total = m_tiles * n_tiles;
+    const int grid = total < sm_count[dev & 63] ? total : sm_count[dev & 63];
+    kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(tm, Y, ldd, M, N, K, n_tiles, total, act);
+    return check_launch("gemm_split3 persistent");
+  }
 }
 
 // x = x0 + x1 + x2 with every residual formed exactly in fp32 (the differences are representable)
@@ -855,31 +1000,42 @@ int gemm_planes(int np, const void* Xs, long ldx, long xplane, const void* Ws, l
   if (K <= 2 * kBK && N > 64 && shallow_mode == 1) bn = 192;
   GemmTmaps tm;
   int rc;
+  static const int persist = [] { const char* e = getenv("SIM_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
+  // CTA pairs with the W tile multicast (persistent 192-wide kernel, enough pair tiles to fill the SMs); 0 = ablation
+  // CTA pairs (opt-in, SIM_GEMM_PAIRS): 1 = W tile multicast into both CTAs, 2 = one MMA stream per pair (cta_group::2, M = 256,
+  // each CTA loads half of W).  Both are bit-identical to the default and both measured NEUTRAL at the in_proj / out_proj
+  // shapes (profiles/r02_gemm_ncu.md: 55.2 / 56.7 vs 54.7 us, 83.1 / 86.7 vs 84.6 us): the main loop is bound by the bytes
+  // that enter each SM (~42 B/clk/SM, the TMA / L2 -> SM ingest rate), which multicast does not change and which the pair's
+  // operand exchange re-spends; so the default stays the plain one-CTA-per-SM kernel.
+  static const int pairs_on = [] { const char* e = getenv("SIM_GEMM_PAIRS"); return e ? atoi(e) : 0; }();
+  if (np == 2 && bn == 96) bn = 128;
+  const bool persist192 = bn == 192 && persist && (long)m_tiles * ((N + 191) / 192) >= 148;
+  const int pairs = persist192 && K > 2 * kBK ? pairs_on : 0;
+  if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM, np))) return rc;
+  if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, pairs ? bn / 2 : bn, np, pairs == 1 ? 1 : 0))) return rc;
   if (np == 2) {
-    if (bn == 96) bn = 128;
-    if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM, 2))) return rc;
-    if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn, 2))) return rc;
     switch (bn) {
       case 64: return launch_gemm<64, 6, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
       case 128: return launch_gemm<128, 5, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
       case 192:
-        if ((long)m_tiles * ((N + 191) / 192) >= 148) return launch_gemm_persistent<192, 4, 2>(tm, Y, ldd, M, N, K, stream, act);
+        if (pairs == 2) return launch_gemm_persistent<192, 6, 2, 2>(tm, Y, ldd, M, N, K, stream, act);
+        if (pairs == 1) return launch_gemm_persistent<192, 4, 2, 1>(tm, Y, ldd, M, N, K, stream, act);
+        if (persist192) return launch_gemm_persistent<192, 4, 2>(tm, Y, ldd, M, N, K, stream, act);
         return launch_gemm<192, 4, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
       default: return launch_gemm<256, 4, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
     }
   }
-  if ((rc = make_tmap_planes(&tm.x, Xs, K, M, ldx, xplane, kBM))) return rc;
-  if ((rc = make_tmap_planes(&tm.w, Ws, K, N, ldw, wplane, bn))) return rc;
   switch (bn) {
     case 64: return launch_gemm<64, 5>(tm, Y, ldd, M, N, K, stream, po, po_cols, po_ld, po_plane, act);
-    case 128: return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act)
-                                   : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
+    case 128:
+      return (force == 1282 || shallow) ? launch_gemm<128, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act)
+                                        : launch_gemm<128, 4>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
     case 96: return launch_gemm<96, 2>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
-    case 192: {
-      static const int persist = [] { const char* e = getenv("SIM_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
-      if (persist && (long)m_tiles * ((N + 191) / 192) >= 148) return launch_gemm_persistent<192, 3>(tm, Y, ldd, M, N, K, stream, act);
+    case 192:
+      if (pairs == 2) return launch_gemm_persistent<192, 4, 3, 2>(tm, Y, ldd, M, N, K, stream, act);
+      if (pairs == 1) return launch_gemm_persistent<192, 3, 3, 1>(tm, Y, ldd, M, N, K, stream, act);
+      if (persist192) return launch_gemm_persistent<192, 3>(tm, Y, ldd, M, N, K, stream, act);
       return launch_gemm<192, 3>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
-    }
     default: return launch_gemm<256, 3>(tm, Y, ldd, M, N, K, stream, nullptr, 0, 0, 0, act);
   }
 }

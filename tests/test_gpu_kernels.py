@@ -729,3 +729,36 @@ def test_gemm_epilogue_activations_feed_the_scan(ops, fmt, B, L, D, C):
     if D % 64 == 0:
         sp = ops.selective_scan_tm(u, v(d1, 0, D), A, Bm, Cm, Dv, v(xz1, D, 2 * D), None, False, z_gate=True, split=True)
         assert torch.equal(sp.planes.float().sum(0).view(B, L, D), base)
+
+
+_PAIR_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from si_mamba_b200 import ops
+g = torch.Generator().manual_seed(11)
+x = torch.randn(2600, 384, generator=g).cuda()      # 21 row tiles: the last pair has an empty second tile
+w = (torch.randn(1536, 384, generator=g) * 0.05).cuda()
+out = {}
+for name, split in (("bf16x3", ops.split3), ("f16x2", ops.split2h)):
+    out[name] = ops.linear_split3(split(x), split(w), 384, act="silu_from", act_col0=768).cpu()
+torch.save(out, sys.argv[2])
+"""
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_gemm_cta_pair_variants_bit_identical(lib, tmp_path, mode):
+    """SIM_GEMM_PAIRS=1 (cluster of two, W tile multicast) and =2 (tcgen05.mma.cta_group::2, M = 256 across the pair) are
+    opt-in schedules of the persistent plane GEMM: same products in the same order, so bit-identical to the default."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for m in ("0", mode):
+        f = tmp_path / f"pairs_{m}.pt"
+        env = dict(os.environ, SIM_GEMM_PAIRS=m)
+        r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT, root, str(f)], env=env, capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[m] = torch.load(f)
+    for name in ("bf16x3", "f16x2"):
+        assert torch.equal(outs["0"][name], outs[mode][name]), name

@@ -38,6 +38,14 @@ def main():
             t = time_fn(fns)
             print(json.dumps(dict(kernel="in_proj", fmt=fmt, act=act, us=round(t * 1e6, 2),
                                   tflops_fp32_equiv=round(2 * M * C * 2 * D / t / 1e12, 1))), flush=True)
+    # out_proj: scan output (unbounded: three bf16 planes) . W_out^T, K = 768, N = 384
+    ys = [ops.split3(r(M, D)) for _ in range(nset)]
+    w_out = ops.split3(r(C, D) * D ** -0.5)
+    oouts = [torch.empty(M, C, device="cuda") for _ in range(nset)]
+    t = time_fn([(lambda x=x, o=o: ops.linear_split3(x, w_out, D, out=o)) for x, o in zip(ys, oouts)])
+    print(json.dumps(dict(kernel="out_proj", fmt="bf16x3", us=round(t * 1e6, 2),
+                          tflops_fp32_equiv=round(2 * M * C * D / t / 1e12, 1))), flush=True)
+    del ys, oouts
     # dt_proj: K = 32 (24 zero-padded), N = 768
     dl = [ops.split3(r(M, 32)) for _ in range(nset)]
     wdt = ops.split3(r(D, 32) * 0.2)
