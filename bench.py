@@ -318,8 +318,12 @@ class Feeder:
 
 def scan_roofline(args, dev, mix, B, L, Dm, backward=False):
     """Dominant own kernel on the layer's real shapes, inputs rotated so they miss L2, CUDA events around a captured graph
-    of back-to-back launches on the launching stream (an eager loop would time the host's tensor-map encodes)."""
-    from si_mamba_b200 import ops
+    of back-to-back launches on the launching stream (an eager loop would time the host's tensor-map encodes).  The
+    forward is timed the way the timed model calls it - fp32 inference hands it z as the gate silu(z), written by the
+    in_proj GEMM's epilogue (si_mamba_b200/autograd.py, SIM_HOIST_ACT) - and, for reference, under the full mamba-ssm
+    contract (softplus and silu evaluated in the kernel): `roofline.general_contract`."""
+    from si_mamba_b200 import autograd as sim_autograd, ops
+    z_gate = (not backward) and args.precision != "bf16" and sim_autograd._HOIST_ACT in ("z", "zdt")
     adt = torch.bfloat16 if args.precision == "bf16" else torch.float32
     es = 2 if adt == torch.bfloat16 else 4
     per_set = (8 if backward else 4) * B * L * Dm * es
@@ -339,8 +343,9 @@ def scan_roofline(args, dev, mix, B, L, Dm, backward=False):
     A = -torch.exp(mix.A_log.detach().float())
     Dp, bias = mix.D.detach(), mix.dt_proj.bias.detach()
 
-    def fwd_call(s):
-        ops.selective_scan_tm(s["u"], s["dl"], A, s["B"], s["C"], Dp, s["z"], bias, True, out=s["out"], checkpoints=s.get("ckpt"))
+    def fwd_call(s, gate=None):
+        ops.selective_scan_tm(s["u"], s["dl"], A, s["B"], s["C"], Dp, s["z"], bias, True, out=s["out"], checkpoints=s.get("ckpt"),
+                              z_gate=z_gate if gate is None else gate)
 
     def bwd_call(s):
         ops.selective_scan_bwd_tm(s["u"], s["dl"], A, s["B"], s["C"], Dp, s["z"], bias, s["dout"], s["ckpt"], True)
@@ -351,24 +356,29 @@ def scan_roofline(args, dev, mix, B, L, Dm, backward=False):
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for s in sets:
-            fwd_call(s)
+            fwd_call(s, gate=False)
             if backward:
                 bwd_call(s)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        for i in range(iters):
-            call(sets[i % nsets])
-    graph.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+
+    def timed(fn):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                fn(sets[i % nsets])
         graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / (iters * reps) * 1e-3
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (iters * reps) * 1e-3
+
+    sec = timed(call)
+    sec_general = timed(lambda s: fwd_call(s, gate=False)) if z_gate else None
     E, S = B * L * Dm, B * L * 16
     if backward:  # reads u, delta, z, dout + writes du, ddelta, dz (7E) + B, C reads (2S) + fp32 dB, dC (2S*4) -- DESIGN.md 4.2
         alg = 7 * E * es + 2 * S * es + 2 * S * 4
@@ -376,7 +386,7 @@ def scan_roofline(args, dev, mix, B, L, Dm, backward=False):
     else:
         alg = 4 * E * es + 2 * S * es
     peak, peak_src = peaks()
-    key = f"{'bwd_' if backward else ''}{args.precision}_B{B}_L{L}"
+    key = f"{'bwd_' if backward else ''}{args.precision}_B{B}_L{L}{'_gate' if z_gate else ''}"
     traffic, tsrc = None, None
     tf = ROOT / "profiles" / "scan_traffic.json"
     if tf.exists():
@@ -391,9 +401,19 @@ def scan_roofline(args, dev, mix, B, L, Dm, backward=False):
            "shape": {"B": B, "L": L, "D": Dm, "N": 16, "dtype": str(adt).split(".")[-1]},
            "timing": "CUDA events around a CUDA graph of 20 back-to-back launches on rotating inputs (> L2), 3 replays"}
     if not backward:
-        out["ceiling"] = {"bound": "mufu", "frac": 0.58 if es == 4 else 0.29,
-                          "why": "a general A needs one MUFU.EX2 per state update + 4 per channel-step: 20 MUFU lane-ops per "
-                                 "channel-step at 16 /clk/SM = 54 us at this shape (DESIGN.md 4.1)"}
+        # MUFU lane-ops per channel-step: 16 (one exp per state update of a general A) + 2 (softplus) + 2 (silu, unless the
+        # gate arrives precomputed), at 16 /clk/SM and 1.965 GHz
+        mufu = 18 if z_gate else 20
+        t_mufu = mufu * E / (148 * 16 * 1.965e9)
+        out["called_as"] = ("z = silu(z) precomputed by the in_proj GEMM epilogue (fp32 inference path of the timed model)"
+                            if z_gate else "mamba-ssm contract: softplus(delta + bias) and silu(z) evaluated in the kernel")
+        out["ceiling"] = {"bound": "mufu", "frac": (alg / t_mufu / 1e9) / peak,
+                          "why": f"a general A needs one MUFU.EX2 per state update: {mufu} MUFU lane-ops per channel-step at "
+                                 f"16 /clk/SM = {t_mufu * 1e6:.0f} us at this shape, before the 0.86-wave imbalance of 384 CTAs "
+                                 "on 148 x 3 slots (DESIGN.md 4.1)"}
+        if sec_general is not None:
+            out["general_contract"] = {"us_per_launch": sec_general * 1e6, "achieved": alg / sec_general / 1e9,
+                                       "frac": alg / sec_general / 1e9 / peak}
     return out
 
 
