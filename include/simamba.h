@@ -276,6 +276,17 @@ int sim_gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, in
 int sim_gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldy, int out_bf16,
                   int M, int N, int K, int splits, const float* bias, int relu, sim_stream_t stream);
 
+/* a-2  sim_gemm_tf32 (K-major operands) with the per-patch glue of Encoder.forward in its epilogue; rows = points, every 32
+ * consecutive rows = one patch (group_size 32 of every shipped config; M % 32 == 0):
+ *   Y[M,N] (f32, may be NULL) = relu?(A . B^T + bias[N] + gbias[row / 32][N])   -- `cat([feature_global.expand, feature])`
+ *                               followed by the second_conv's first Conv1d + BN + ReLU (models/point_mamba.py:67-69), the
+ *                               global half of that conv computed once per patch and passed in as gbias (row stride ld_gbias);
+ *   gmax[M / 32, N] (f32, may be NULL) = max of Y over each patch's rows                -- `torch.max(feature, dim=2)` (:66, :72).
+ * bias / gbias may be NULL; at least one of gbias / gmax must be given. */
+int sim_gemm_tf32_group(const float* A, long lda, const float* B, long ldb, float* Y, long ldy, int M, int N, int K,
+                        const float* bias, const float* gbias, long ld_gbias, int relu, float* gmax, long ld_gmax,
+                        sim_stream_t stream);
+
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
  * elements, row stride ldo); the weights are split once per model, activations by their producer.

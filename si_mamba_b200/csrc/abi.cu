@@ -118,6 +118,13 @@ int sim_gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, 
                         static_cast<cudaStream_t>(stream));
 }
 
+int sim_gemm_tf32_group(const float* A, long lda, const float* B, long ldb, float* Y, long ldy, int M, int N, int K,
+                        const float* bias, const float* gbias, long ld_gbias, int relu, float* gmax, long ld_gmax,
+                        sim_stream_t stream) {
+  return sim::gemm_tf32_group(A, lda, B, ldb, Y, ldy, M, N, K, bias, gbias, ld_gbias, relu, gmax, ld_gmax,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream) {
   return sim::pairwise_dist_mean(center, B, G, partial, sigma, static_cast<cudaStream_t>(stream));
 }

@@ -130,11 +130,20 @@ __host__ __device__ constexpr uint32_t idesc_tc(int M, int N, bool a_mn, bool b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// optional epilogue: + bias[column], ReLU
+// optional epilogue: + bias[column], ReLU; and, for the per-patch PointNet of Encoder.forward (models/point_mamba.py:59-73,
+// rows = points, 32 consecutive rows = one patch = the 32 TMEM lanes of one epilogue warp): + gbias[row / 32][column] (the
+// patch's pooled global feature pushed through its half of the next conv: the `cat([global.expand, local])` of :67-68 without
+// the cat) and gmax[row / 32][column] = max over the patch's rows (the `torch.max(feature, dim=2)` of :66 / :72), written
+// instead of or next to Y.  Persistent kernel only.
 struct Epi {
   const float* bias;
   int relu;
+  const float* gbias = nullptr;
+  long ld_gbias = 0;
+  float* gmax = nullptr;
+  long ld_gmax = 0;
 };
+constexpr int kGroupRows = 32;
 __device__ __forceinline__ float4 apply_epi(float4 o, const Epi& e, int gn) {
   if (e.bias) {
     const float4 b = *reinterpret_cast<const float4*>(e.bias + gn);
@@ -411,16 +420,49 @@ __global__ void __launch_bounds__(PCfg<BN, NSTAGE_>::NT, 1)
         if (n0 + cb >= N) break;
         float v[32];
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + buf * BN + cb, v);
+        const bool grouped = epi.gbias != nullptr || epi.gmax != nullptr;
+        if (grouped) {
+          // this warp's 32 rows are one patch: bias / patch bias / ReLU go on the registers (one broadcast row of each),
+          // so the staged tile already holds the final values for both the row stores and the column maxima
+          const long grow = (m0 + quad * 32) / kGroupRows;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int gn = n0 + cb + 4 * q;
+            float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < N) {
+              if (epi.bias) add = *reinterpret_cast<const float4*>(epi.bias + gn);
+              if (epi.gbias && m0 + quad * 32 < M) {
+                const float4 g = *reinterpret_cast<const float4*>(epi.gbias + grow * epi.ld_gbias + gn);
+                add.x += g.x, add.y += g.y, add.z += g.z, add.w += g.w;
+              }
+            }
+            v[4 * q] += add.x, v[4 * q + 1] += add.y, v[4 * q + 2] += add.z, v[4 * q + 3] += add.w;
+            if (epi.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[4 * q + e] = fmaxf(v[4 * q + e], 0.f);
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(stg + lane * C::STG_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
+        if (epi.gmax) {
+          // lane l takes column l of the staged 32 x 32 tile (consecutive lanes -> consecutive banks): max over the patch
+          float mx = stg[lane];
+#pragma unroll
+          for (int r = 1; r < 32; ++r) mx = fmaxf(mx, stg[r * C::STG_LD + lane]);
+          const int gn = n0 + cb + lane;
+          if (m0 + quad * 32 < M && gn < N) epi.gmax[((long)(m0 + quad * 32) / kGroupRows) * epi.ld_gmax + gn] = mx;
+        }
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
+          if (Yv == nullptr) break;
           const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
           const int gm = m0 + quad * 32 + row, gn = n0 + cb + col;
           if (gm < M && gn < N) {
-            const float4 o = apply_epi(*reinterpret_cast<const float4*>(stg + row * C::STG_LD + col), epi, gn);
+            const float4 staged = *reinterpret_cast<const float4*>(stg + row * C::STG_LD + col);
+            const float4 o = grouped ? staged : apply_epi(staged, epi, gn);
             if (out_bf16) {
               const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
               uint2 pk;
@@ -514,7 +556,7 @@ int launch_persistent(const Problem& q, cudaStream_t stream) {
 template <bool A_MN, bool B_MN, bool TF32>
 int dispatch(const Problem& q, int bn, cudaStream_t stream) {
   static const int persist = [] { const char* e = getenv("SIM_GEMM_BF16_PERSIST"); return e ? atoi(e) : 1; }();
-  if (q.splits == 1 && persist) {
+  if (q.splits == 1 && (persist || q.epi.gbias || q.epi.gmax)) {  // the per-patch epilogue lives in the persistent kernel
     switch (bn) {
       case 64: return launch_persistent<64, 6, A_MN, B_MN, TF32>(q, stream);
       case 128: return launch_persistent<128, 5, A_MN, B_MN, TF32>(q, stream);
@@ -531,9 +573,14 @@ int dispatch(const Problem& q, int bn, cudaStream_t stream) {
 
 template <bool TF32>
 int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
-             int N, int K, int splits, const float* bias, int relu, cudaStream_t stream) {
+             int N, int K, int splits, const float* bias, int relu, cudaStream_t stream, const float* gbias = nullptr,
+             long ld_gbias = 0, float* gmax = nullptr, long ld_gmax = 0) {
   constexpr int ES = El<TF32>::ES, BK = El<TF32>::BK;
-  SIM_REQUIRE(A && B && Y && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_tc: empty problem / null tensor");
+  const bool grouped = gbias != nullptr || gmax != nullptr;
+  SIM_REQUIRE(A && B && (Y || gmax) && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_tc: empty problem / null tensor");
+  SIM_REQUIRE(!grouped || (M % kGroupRows == 0 && splits == 1 && !out_bf16 && (!gbias || (aligned16(gbias) && ld_gbias % 4 == 0)) &&
+                           (!gmax || ld_gmax >= N)),
+              SIM_ERR_INVALID, "gemm_tc: the per-patch epilogue needs M %% 32 == 0, an fp32 result, no split-K, 16-byte aligned patch bias rows");
   SIM_REQUIRE(!TF32 || (!a_mn && !b_mn), SIM_ERR_INVALID, "gemm_tf32: only K-major operands ((M,K) and (N,K) row-major) are built");
   SIM_REQUIRE(aligned16(A) && aligned16(B) && (lda * ES) % 16 == 0 && (ldb * ES) % 16 == 0, SIM_ERR_ALIGN,
               "gemm_tc: TMA needs 16-byte aligned operand bases and row strides (lda=%ld ldb=%ld)", lda, ldb);
@@ -565,6 +612,7 @@ int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_m
   Problem q;
   q.Y = Y, q.ldd = ldd, q.M = M, q.N = N, q.K = K, q.out_bf16 = out_bf16, q.splits = splits;
   q.epi.bias = bias, q.epi.relu = relu;
+  q.epi.gbias = gbias, q.epi.ld_gbias = ld_gbias, q.epi.gmax = gmax, q.epi.ld_gmax = ld_gmax;
   int rc;
   if (a_mn) rc = make_tmap_2d(&q.tm.a, A, M, K, lda, BK, TF32); else rc = make_tmap_2d(&q.tm.a, A, K, M, lda, kBM, TF32);
   if (rc) return rc;
@@ -596,6 +644,13 @@ int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_
 int gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
               int N, int K, int splits, const float* bias, int relu, cudaStream_t stream) {
   return gemm_any<true>(A, lda, a_mn, B, ldb, b_mn, Y, ldd, out_bf16, M, N, K, splits, bias, relu, stream);
+}
+
+// Y (fp32, may be NULL) = relu?(A . B^T + bias[N] + gbias[row / 32][N]);  gmax[row / 32][N] = max over each 32-row patch
+int gemm_tf32_group(const float* A, long lda, const float* B, long ldb, float* Y, long ldd, int M, int N, int K, const float* bias,
+                    const float* gbias, long ld_gbias, int relu, float* gmax, long ld_gmax, cudaStream_t stream) {
+  SIM_REQUIRE(gbias || gmax, SIM_ERR_INVALID, "gemm_tf32_group: neither a patch bias nor a patch max was asked for");
+  return gemm_any<true>(A, lda, 0, B, ldb, 0, Y, Y ? ldd : 4, 0, M, N, K, 1, bias, relu, stream, gbias, ld_gbias, gmax, ld_gmax);
 }
 
 }  // namespace sim

@@ -85,14 +85,19 @@ __device__ __forceinline__ void sts4<__nv_bfloat16>(__nv_bfloat16* dst, float4 v
 // them.  With the 8-step tiles: 1.5 exps per state-step, no history traffic.
 constexpr int SUB = 4;  // steps per sub-tile
 
-template <typename T, int CH_, int LPC_, bool SAVE_A_ = false, int NS_ = 2, int MINB_ = 1>
+// CPT = channels per thread.  With CPT = 2 a thread owns two channels (CH / 2 apart) x 16 / LPC states (LPC = 4: the same eight state
+// chains per thread as LPC = 2, CPT = 1): the B / C row slices it loads serve both channels (2 instead of 4 LDS.128 per step and
+// phase), and the dB / dC partials of its two channels are added in registers BEFORE the warp butterfly, which then reduces
+// 2 S = 8 values over 8 lane groups (7 shuffles) instead of 16 values over 16 (15 shuffles).
+template <typename T, int CH_, int LPC_, bool SAVE_A_ = false, int NS_ = 2, int MINB_ = 1, int CPT_ = 1>
 struct BwdCfg {
+  static constexpr int CPT = CPT_;
   static constexpr bool SAVE_A = SAVE_A_;  // keep exp(dt A) of a recomputed sub-tile in registers for its adjoint steps
   static constexpr int MINB = MINB_;       // resident CTAs per SM the register allocation aims at
   static constexpr int CH = CH_;
   static constexpr int LPC = LPC_;       // lanes per channel
   static constexpr int S = kN / LPC_;    // states per thread
-  static constexpr int NT = LPC_ * CH_;  // threads per CTA
+  static constexpr int NT = LPC_ * CH_ / CPT_;  // threads per CTA
   static constexpr int NW = NT / 32;
   // raw TMA stages.  The pre-pass consumes a stage completely, so ONE stage already lets the next tile's copies fly during
   // the whole recurrence phase; the second stage only costs shared memory (fp32: 3 -> 4 CTAs per SM, bf16: 4 -> 5)
@@ -105,16 +110,18 @@ struct BwdCfg {
   static constexpr int WORK = (6 + 3 * LPC_) * TT * CH_ * 4     // (dt, u, dy, dt*u) packed, sg, dzc; y, s1, s2 per lane of a channel
                               + 2 * TT * kN * 4                 // B, C fp32
                               + NW * TT * 2 * kN * 4;           // per-warp dB | dC tile sums
-  static constexpr int SCK = (TT / SUB - 1) * (S / 4) * NT * 16;  // sub-tile start states, float4 planes
+  static constexpr int SCK = (TT / SUB - 1) * (CPT_ * S / 4) * NT * 16;  // sub-tile start states, float4 planes
   static constexpr int SMEM = NS * RAW_STAGE + OUT + WORK + SCK + NS * 8 + 64;
   static_assert(RAW_MAIN % 128 == 0 && RAW_BC % 128 == 0 && RAW_CK % 128 == 0, "TMA tiles must stay 128-B aligned");
   static_assert(TT % SUB == 0 && NT % CH_ == 0, "whole sub-tiles; a thread's elementwise channel is fixed");
+  static_assert(S % 4 == 0 && CH_ % CPT_ == 0, "float4 state groups; whole channel groups");
 };
 
 template <typename Cfg, typename T>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(const __grid_constant__ BwdTmaps tm,
                                                                      const ScanBwdParams p) {
-  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW, LPC = Cfg::LPC, SQ = Cfg::S / 4;
+  constexpr int CH = Cfg::CH, NT = Cfg::NT, NS = Cfg::NS, S = Cfg::S, NW = Cfg::NW, LPC = Cfg::LPC, SQ = Cfg::S / 4,
+                CPT = Cfg::CPT;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* raw = smem;
   T* __restrict__ o_du = reinterpret_cast<T*>(smem + NS * Cfg::RAW_STAGE);
@@ -130,14 +137,15 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
   float* __restrict__ w_C = w_B + TT * kN;
   float* __restrict__ a_dBC = w_C + TT * kN;                                  // [warp][t][dB(16) | dC(16)]
   float4* __restrict__ sck = reinterpret_cast<float4*>(a_dBC + NW * TT * 2 * kN);  // [sub-1][half][thread]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sck + (TT / SUB - 1) * SQ * NT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sck + (TT / SUB - 1) * CPT * SQ * NT);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunk = p.D / CH;
   const int b = blockIdx.x / nchunk;
   const int c0 = (blockIdx.x % nchunk) * CH;
   const int sub = tid % LPC;  // which slice of the 16 states
-  const int c = tid / LPC;    // channel within the CTA
+  const int c = tid / LPC;  // first of this thread's CPT channels within the CTA: c, c + CH / CPT, ... (the stride keeps
+  constexpr int CSTR = CH / CPT;  // every per-(step, channel) shared-memory access of a warp on distinct banks)
   const int ntiles = (p.L + TT - 1) / TT;
   const bool has_z = p.z != nullptr;
 
@@ -165,14 +173,16 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
     for (int k = 0; k < NS && k < ntiles; ++k) issue_tile(k);
   }
 
-  float A[S], A2[S], dA[S], dh[S];
+  float A[CPT][S], A2[CPT][S], dA[CPT][S], dh[CPT][S];
 #pragma unroll
-  for (int n = 0; n < S; ++n) {
-    A[n] = p.A[(long)(c0 + c) * kN + sub * S + n];
-    A2[n] = A[n] * kLog2e;
-    dA[n] = 0.f;
-    dh[n] = 0.f;
-  }
+  for (int j = 0; j < CPT; ++j)
+#pragma unroll
+    for (int n = 0; n < S; ++n) {
+      A[j][n] = p.A[(long)(c0 + c + j * CSTR) * kN + sub * S + n];
+      A2[j][n] = A[j][n] * kLog2e;
+      dA[j][n] = 0.f;
+      dh[j][n] = 0.f;
+    }
   const int ce = tid % CH;  // channel of this thread's elements in the elementwise passes (NT % CH == 0)
   const float De = p.Dv ? p.Dv[c0 + ce] : 0.f;
   const float bias_e = p.dbias ? p.dbias[c0 + ce] : 0.f;
@@ -183,8 +193,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
   float* my_acc = a_dBC + warp * TT * 2 * kN + (vfin < S ? sub * S + vfin : kN + sub * S + vfin - S);
 
   // one forward step of this thread's 8 states: hn = a * hp + dt*u*B; returns the thread's share of <h, C>
-  auto fwd_step = [&](int r, const float (&hp)[S], float (&hn)[S], float* aout = nullptr) -> float {
-    const float4 w = w4[r * CH + c];
+  auto fwd_step = [&](int j_, int r, const float (&hp)[S], float (&hn)[S], float* aout = nullptr) -> float {
+    const float4 w = w4[r * CH + c + j_ * CSTR];
     const float dtv = w.x, dtu = w.w;
     float2 y2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
 #pragma unroll
       for (int i = 0; i < 4; i += 2) {
         const int n = 4 * q + i;
-        const float2 x = __fmul2_rn(make_float2(dtv, dtv), make_float2(A2[n], A2[n + 1]));
+        const float2 x = __fmul2_rn(make_float2(dtv, dtv), make_float2(A2[j_][n], A2[j_][n + 1]));
         const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
         const float2 bu = __fmul2_rn(make_float2(dtu, dtu), make_float2(Bv[i], Bv[i + 1]));
         const float2 h2 = __ffma2_rn(a, make_float2(hp[n], hp[n + 1]), bu);
@@ -254,27 +264,36 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
       w_C[e] = to_f32<T>(sC[e]);
     }
     // state at the start of this tile (from the training forward; arrived with the operand tiles)
-    float h0[S];
+    float h0[CPT][S];
 #pragma unroll
-    for (int q = 0; q < SQ; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(sck0 + c * kN + sub * S + 4 * q);
-      h0[4 * q] = v.x, h0[4 * q + 1] = v.y, h0[4 * q + 2] = v.z, h0[4 * q + 3] = v.w;
-    }
+    for (int j = 0; j < CPT; ++j)
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(sck0 + (c + j * CSTR) * kN + sub * S + 4 * q);
+        h0[j][4 * q] = v.x, h0[j][4 * q + 1] = v.y, h0[j][4 * q + 2] = v.z, h0[j][4 * q + 3] = v.w;
+      }
     if (tid == 0) bulk_wait_read0();  // previous tile's stores have finished reading the output tiles
     __syncthreads();
     if (tid == 0 && k + NS < ntiles) issue_tile(k + NS);  // raw stage s is free again
 
     // ---- (1) forward sweep over steps 0 .. TT-SUB-1: leaves the start state of sub-tiles 1 .. 3 in shared memory
     {
-      float h[S];
+      float h[CPT][S];
 #pragma unroll
-      for (int n = 0; n < S; ++n) h[n] = h0[n];
+      for (int j = 0; j < CPT; ++j)
+#pragma unroll
+        for (int n = 0; n < S; ++n) h[j][n] = h0[j][n];
 #pragma unroll 1
       for (int q = 0; q < TT / SUB - 1; ++q) {
 #pragma unroll
-        for (int i = 0; i < SUB; ++i) fwd_step(SUB * q + i, h, h);
+        for (int i = 0; i < SUB; ++i)
 #pragma unroll
-        for (int j = 0; j < SQ; ++j) sck[(q * SQ + j) * NT + tid] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          for (int j = 0; j < CPT; ++j) fwd_step(j, SUB * q + i, h[j], h[j]);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+#pragma unroll
+          for (int g = 0; g < SQ; ++g)
+            sck[((q * CPT + j) * SQ + g) * NT + tid] = make_float4(h[j][4 * g], h[j][4 * g + 1], h[j][4 * g + 2], h[j][4 * g + 3]);
       }
     }
 
@@ -282,67 +301,85 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
 #pragma unroll 1
     for (int sb = TT / SUB - 1; sb >= 0; --sb) {
       const int rb = SUB * sb;
-      float hs[S], hq[SUB][S];
-      [[maybe_unused]] float aq[Cfg::SAVE_A ? SUB : 1][S];  // exp(dt A) of the sub-tile's steps
-      if (sb == 0) {
+      float hs[CPT][S], hq[CPT][SUB][S];
+      [[maybe_unused]] float aq[CPT][Cfg::SAVE_A ? SUB : 1][S];  // exp(dt A) of the sub-tile's steps
 #pragma unroll
-        for (int n = 0; n < S; ++n) hs[n] = h0[n];
-      } else {
+      for (int j = 0; j < CPT; ++j) {
+        if (sb == 0) {
 #pragma unroll
-        for (int j = 0; j < SQ; ++j) {
-          const float4 pj = sck[((sb - 1) * SQ + j) * NT + tid];
-          hs[4 * j] = pj.x, hs[4 * j + 1] = pj.y, hs[4 * j + 2] = pj.z, hs[4 * j + 3] = pj.w;
+          for (int n = 0; n < S; ++n) hs[j][n] = h0[j][n];
+        } else {
+#pragma unroll
+          for (int g = 0; g < SQ; ++g) {
+            const float4 pj = sck[(((sb - 1) * CPT + j) * SQ + g) * NT + tid];
+            hs[j][4 * g] = pj.x, hs[j][4 * g + 1] = pj.y, hs[j][4 * g + 2] = pj.z, hs[j][4 * g + 3] = pj.w;
+          }
         }
       }
 #pragma unroll
       for (int i = 0; i < SUB; ++i) {
         const int r = rb + i;
-        float* ao = Cfg::SAVE_A ? aq[Cfg::SAVE_A ? i : 0] : nullptr;
-        float y = (i == 0) ? fwd_step(r, hs, hq[0], ao) : fwd_step(r, hq[i > 0 ? i - 1 : 0], hq[i], ao);
-        w_y[(r * CH + c) * LPC + sub] = y;  // partial <h, C>; D u is added in the epilogue
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          float* ao = Cfg::SAVE_A ? aq[j][Cfg::SAVE_A ? i : 0] : nullptr;
+          float y = (i == 0) ? fwd_step(j, r, hs[j], hq[j][0], ao) : fwd_step(j, r, hq[j][i > 0 ? i - 1 : 0], hq[j][i], ao);
+          w_y[(r * CH + c + j * CSTR) * LPC + sub] = y;  // partial <h, C>; D u is added in the epilogue
+        }
       }
 #pragma unroll
       for (int i = SUB - 1; i >= 0; --i) {
         const int r = rb + i;
-        const float4 w = w4[r * CH + c];
-        const float dtv = w.x, dy = w.z, dtu = w.w;
-        // packed f32x2 over state pairs.  s1 = sum_n dh_n B_n feeds both ddt (x u) and du (x dt); s2 = sum_n tmp_n A_n
-        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-        float red[2 * S];  // [0,S): dB partials, [S,2S): dC partials of this (channel, state slice)
-        const float2 dy2 = make_float2(dy, dy), dt2 = make_float2(dtv, dtv), dtu2 = make_float2(dtu, dtu);
+        float red[2 * S];  // [0,S): dB partials, [S,2S): dC partials of this state slice, summed over the thread's channels
 #pragma unroll
-        for (int q = 0; q < S / 4; ++q) {
-          const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + sub * S + 4 * q);
-          const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + sub * S + 4 * q);
-          const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
+        for (int j = 0; j < CPT; ++j) {
+          const float4 w = w4[r * CH + c + j * CSTR];
+          const float dtv = w.x, dy = w.z, dtu = w.w;
+          // packed f32x2 over state pairs.  s1 = sum_n dh_n B_n feeds both ddt (x u) and du (x dt); s2 = sum_n tmp_n A_n
+          float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+          const float2 dy2 = make_float2(dy, dy), dt2 = make_float2(dtv, dtv), dtu2 = make_float2(dtu, dtu);
 #pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            const int n = 4 * q + j;
-            const float2 hprev = (i == 0) ? make_float2(hs[n], hs[n + 1]) : make_float2(hq[i > 0 ? i - 1 : 0][n], hq[i > 0 ? i - 1 : 0][n + 1]);
-            const float2 dhn = __ffma2_rn(dy2, make_float2(Cv[j], Cv[j + 1]), make_float2(dh[n], dh[n + 1]));  // dL/dh_t
-            float2 a;
-            if constexpr (Cfg::SAVE_A) {
-              a = make_float2(aq[Cfg::SAVE_A ? i : 0][n], aq[Cfg::SAVE_A ? i : 0][n + 1]);
-            } else {
-              const float2 x = __fmul2_rn(dt2, make_float2(A2[n], A2[n + 1]));
-              a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          for (int q = 0; q < S / 4; ++q) {
+            const float4 Bq = *reinterpret_cast<const float4*>(w_B + r * kN + sub * S + 4 * q);
+            const float4 Cq = *reinterpret_cast<const float4*>(w_C + r * kN + sub * S + 4 * q);
+            const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj += 2) {
+              const int n = 4 * q + jj;
+              const float2 hprev = (i == 0) ? make_float2(hs[j][n], hs[j][n + 1])
+                                            : make_float2(hq[j][i > 0 ? i - 1 : 0][n], hq[j][i > 0 ? i - 1 : 0][n + 1]);
+              const float2 dhn = __ffma2_rn(dy2, make_float2(Cv[jj], Cv[jj + 1]), make_float2(dh[j][n], dh[j][n + 1]));  // dL/dh_t
+              float2 a;
+              if constexpr (Cfg::SAVE_A) {
+                a = make_float2(aq[j][Cfg::SAVE_A ? i : 0][n], aq[j][Cfg::SAVE_A ? i : 0][n + 1]);
+              } else {
+                const float2 x = __fmul2_rn(dt2, make_float2(A2[j][n], A2[j][n + 1]));
+                a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+              }
+              const float2 hq2 = make_float2(hq[j][i][n], hq[j][i][n + 1]);
+              if (j == 0) {
+                const float2 rc = __fmul2_rn(dy2, hq2);
+                const float2 rb2 = __fmul2_rn(dhn, dtu2);
+                red[S + n] = rc.x, red[S + n + 1] = rc.y;
+                red[n] = rb2.x, red[n + 1] = rb2.y;
+              } else {  // the second channel's partials join the first's before the butterfly
+                const float2 rc = __ffma2_rn(dy2, hq2, make_float2(red[S + n], red[S + n + 1]));
+                const float2 rb2 = __ffma2_rn(dhn, dtu2, make_float2(red[n], red[n + 1]));
+                red[S + n] = rc.x, red[S + n + 1] = rc.y;
+                red[n] = rb2.x, red[n + 1] = rb2.y;
+              }
+              const float2 dhp = __fmul2_rn(a, dhn);                    // dL/dh_{t-1} through the decay
+              const float2 tmp = __fmul2_rn(dhp, hprev);                // dL/da * a
+              s1 = __ffma2_rn(dhn, make_float2(Bv[jj], Bv[jj + 1]), s1);
+              s2 = __ffma2_rn(tmp, make_float2(A[j][n], A[j][n + 1]), s2);
+              const float2 dAn = __ffma2_rn(tmp, dt2, make_float2(dA[j][n], dA[j][n + 1]));
+              dA[j][n] = dAn.x, dA[j][n + 1] = dAn.y;
+              dh[j][n] = dhp.x, dh[j][n + 1] = dhp.y;
             }
-            const float2 rc = __fmul2_rn(dy2, make_float2(hq[i][n], hq[i][n + 1]));
-            const float2 rb2 = __fmul2_rn(dhn, dtu2);
-            red[S + n] = rc.x, red[S + n + 1] = rc.y;
-            red[n] = rb2.x, red[n + 1] = rb2.y;
-            const float2 dhp = __fmul2_rn(a, dhn);                    // dL/dh_{t-1} through the decay
-            const float2 tmp = __fmul2_rn(dhp, hprev);                // dL/da * a
-            s1 = __ffma2_rn(dhn, make_float2(Bv[j], Bv[j + 1]), s1);
-            s2 = __ffma2_rn(tmp, make_float2(A[n], A[n + 1]), s2);
-            const float2 dAn = __ffma2_rn(tmp, dt2, make_float2(dA[n], dA[n + 1]));
-            dA[n] = dAn.x, dA[n + 1] = dAn.y;
-            dh[n] = dhp.x, dh[n + 1] = dhp.y;
           }
+          w_s1[(r * CH + c + j * CSTR) * LPC + sub] = s1.x + s1.y;
+          w_s2[(r * CH + c + j * CSTR) * LPC + sub] = s2.x + s2.y;
         }
-        w_s1[(r * CH + c) * LPC + sub] = s1.x + s1.y;
-        w_s2[(r * CH + c) * LPC + sub] = s2.x + s2.y;
-        // reduce the 2 S partials over the warp's 32 / LPC channels: transposed butterfly over the channel lane bits
+        // reduce the 2 S partials over the warp's 32 / LPC lane groups: transposed butterfly over the group lane bits
 #pragma unroll
         for (int ov = S, ol = 16; ov >= 1; ov >>= 1, ol >>= 1) {
           const bool up = (lane & ol) != 0;
@@ -397,14 +434,16 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) selective_scan_bwd_kernel(
   }
   if (tid == 0) bulk_wait0();
 #pragma unroll
-  for (int n = 0; n < S; ++n) atomicAdd(p.dA + (long)(c0 + c) * kN + sub * S + n, dA[n]);
+  for (int j = 0; j < CPT; ++j)
+#pragma unroll
+    for (int n = 0; n < S; ++n) atomicAdd(p.dA + (long)(c0 + c + j * CSTR) * kN + sub * S + n, dA[j][n]);
   if (p.dD) atomicAdd(p.dD + c0 + ce, dD);
   if (p.ddbias) atomicAdd(p.ddbias + c0 + ce, dbias);
 }
 
-template <typename T, int CH, int LPC, bool SAVE_A = false, int NS = 2, int MINB = 1>
+template <typename T, int CH, int LPC, bool SAVE_A = false, int NS = 2, int MINB = 1, int CPT = 1>
 int launch_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
-  using Cfg = BwdCfg<T, CH, LPC, SAVE_A, NS, MINB>;
+  using Cfg = BwdCfg<T, CH, LPC, SAVE_A, NS, MINB, CPT>;
   auto kern = selective_scan_bwd_kernel<Cfg, T>;
   static SmemAttrCache attr;
   if (ensure_dyn_smem(kern, Cfg::SMEM, attr) != cudaSuccess) return check_launch("selective_scan_bwd attr");
@@ -453,6 +492,8 @@ int selective_scan_bwd(const ScanBwdParams& p, int dtype, cudaStream_t stream) {
   static const int cfg = [] { const char* e = getenv("SIM_SCAN_BWD_CFG"); return e ? atoi(e) : 22; }();
   if (cfg == 42 || p.D % 64 != 0)
     return dtype == 0 ? launch_bwd<float, 32, 4, true, 1>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 32, 4, true, 2>(p, dtype, stream);
+  if (cfg == 24)  // 64-channel CTAs, 4 lanes per channel pair (2 channels x 4 states per thread), 128 threads
+    return dtype == 0 ? launch_bwd<float, 64, 4, true, 1, 3, 2>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 64, 4, true, 1, 3, 2>(p, dtype, stream);
   if (cfg == 2200)
     return dtype == 0 ? launch_bwd<float, 64, 2, false, 1, 4>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 64, 2, false, 1, 4>(p, dtype, stream);
   return dtype == 0 ? launch_bwd<float, 64, 2, true, 1, 3>(p, dtype, stream) : launch_bwd<__nv_bfloat16, 64, 2, true, 1, 3>(p, dtype, stream);

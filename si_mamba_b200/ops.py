@@ -743,6 +743,33 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     return out
 
 
+def gemm_tf32_group(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                    gbias: Optional[torch.Tensor] = None, relu: bool = False, want_y: bool = True, want_gmax: bool = False):
+    """gemm_tf32 with the per-patch glue of Encoder.forward in its epilogue (sim_gemm_tf32_group); rows of ``a`` are points,
+    every 32 consecutive rows one patch.  y = relu?(a @ b.T + bias + gbias[row // 32]) (returned if ``want_y``), gmax =
+    y.view(-1, 32, N).max(1) (returned if ``want_gmax``): the `torch.max(feature, dim=2)` / `cat([global.expand, local])`
+    passes of models/point_mamba.py:66-72 without a separate kernel or, for the last conv, the (points, C) tensor itself.
+    -> (y or None, gmax or None)."""
+    _cuda(a, b, bias, gbias)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    assert gbias is not None or want_gmax
+
+    def operand(t):
+        return t if (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0) else t.contiguous()
+    a, b = operand(a), operand(b)
+    (M, K), (N, Kb) = a.shape, b.shape
+    assert K == Kb and M % 32 == 0
+    if gbias is not None:
+        gbias = operand(gbias.float())
+        assert gbias.shape == (M // 32, N)
+    y = torch.empty(M, N, dtype=torch.float32, device=a.device) if want_y else None
+    gmax = torch.empty(M // 32, N, dtype=torch.float32, device=a.device) if want_gmax else None
+    _lib.call("sim_gemm_tf32_group", _p(a), a.stride(0), _p(b), b.stride(0), _p(y), 0 if y is None else y.stride(0), M, N, K,
+              _p(_f32c(bias)), _p(gbias), 0 if gbias is None else gbias.stride(0), int(relu), _p(gmax),
+              0 if gmax is None else gmax.stride(0), _stream())
+    return y, gmax
+
+
 def point_linear3(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: str = "none") -> torch.Tensor:
     """y = act(x @ w.T + b) for 3-D points: x (rows, 3), w (C, 3) -> (rows, C) fp32; act in none | relu | gelu (erf)."""
     _cuda(x, w, b)

@@ -127,19 +127,30 @@ class Encoder(nn.Module):
         on the hand-written tcgen05 kernel: as TF32 with the bias in its epilogue (sim_gemm_tf32) when
         torch.backends.cudnn.allow_tf32 is on - these GEMMs ARE the reference's convolutions, so they follow cuDNN's
         switch, True by default - and fp32-accurate on three bf16 planes (sim_gemm_bf16x3) when it is off."""
-        bs, g, n, _ = point_groups.shape
-        P = bs * g * n
+        bs, g_, n, _ = point_groups.shape
+        P = bs * g_ * n
         x = point_groups.reshape(P, 3)
         w1, b1 = self._fold_bn(self.first_conv[0], self.first_conv[1])
         h = ops.point_linear3(x, w1, b1, "relu")                                                # (P, 128)
-        f = _own_linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)         # (P, 256)
         w3, b3 = self._fold_bn(self.second_conv[0], self.second_conv[1])
+        if torch.backends.cudnn.allow_tf32 and n == 32:
+            # TF32 policy (the default) and 32-point patches: the per-patch passes ride in the GEMM epilogues
+            # (sim_gemm_tf32_group) - the pooled global feature leaves the first GEMM with f, its half of the next conv comes
+            # back as a per-patch bias, and the last conv writes only the patch maxima (never the (points, C) tensor)
+            c2, c4 = self.first_conv[3], self.second_conv[3]
+            f, fg = ops.gemm_tf32_group(h, c2.weight[:, :, 0].detach(), bias=c2.bias.detach(), want_y=True, want_gmax=True)
+            c_loc = f.shape[-1]
+            g = ops.gemm_tf32(fg, w3[:, :c_loc], bias=b3)                                       # (BG, 512), once per patch
+            h2, _ = ops.gemm_tf32_group(f, w3[:, c_loc:], gbias=g, relu=True, want_y=True)      # (P, 512)
+            _, tok = ops.gemm_tf32_group(h2, c4.weight[:, :, 0].detach(), bias=c4.bias.detach(), want_y=False, want_gmax=True)
+            return tok.view(bs, g_, self.encoder_channel)
+        f = _own_linear(h, self.first_conv[3].weight[:, :, 0], self.first_conv[3].bias)         # (P, 256)
         c_loc = f.shape[-1]
         # row passes between the GEMMs on the sim_group_* kernels (one read + one write each)
         fg = ops.group_max(f, n)                                                                # (BG, 256)
         h2 = ops.group_bias_relu_(_own_linear(f, w3[:, c_loc:], None), _own_linear(fg, w3[:, :c_loc], b3), n)
         o = _own_linear(h2, self.second_conv[3].weight[:, :, 0], self.second_conv[3].bias)      # (P, C)
-        return ops.group_max(o, n).view(bs, g, self.encoder_channel)
+        return ops.group_max(o, n).view(bs, g_, self.encoder_channel)
 
     def _forward_rows(self, point_groups):
         """Differentiable form of forward() on the (B*G*M, C) point matrix: the 1x1 convolutions as row-major linears

@@ -762,3 +762,25 @@ def test_gemm_cta_pair_variants_bit_identical(lib, tmp_path, mode):
         outs[m] = torch.load(f)
     for name in ("bf16x3", "f16x2"):
         assert torch.equal(outs["0"][name], outs[mode][name]), name
+
+
+@pytest.mark.parametrize("P,N,K", [(65536, 256, 128), (4096, 512, 256), (2048, 384, 512), (96, 64, 40)])
+def test_gemm_tf32_group_epilogue(ops, P, N, K):
+    """Per-patch epilogue of the TF32 GEMM (patch bias + ReLU, patch max) against the separate kernels it replaces
+    (sim_gemm_tf32 + sim_group_bias_relu + sim_group_max): same accumulation, so bit-identical."""
+    g = torch.Generator().manual_seed(P + N)
+    a = dev(torch.randn(P, K, generator=g))
+    w = dev(torch.randn(N, K, generator=g) * K ** -0.5)
+    bias = dev(torch.randn(N, generator=g))
+    gb = dev(torch.randn(P // 32, N, generator=g))
+    y_ref = ops.gemm_tf32(a, w, bias=bias)
+    y, mx = ops.gemm_tf32_group(a, w, bias=bias, want_y=True, want_gmax=True)
+    assert torch.equal(y, y_ref) and torch.equal(mx, ops.group_max(y_ref, 32))
+    none, mx2 = ops.gemm_tf32_group(a, w, bias=bias, want_y=False, want_gmax=True)
+    assert none is None and torch.equal(mx2, mx)
+    h_ref = ops.group_bias_relu_(ops.gemm_tf32(a, w), gb, 32)
+    h, hm = ops.gemm_tf32_group(a, w, gbias=gb, relu=True, want_y=True, want_gmax=True)
+    assert torch.equal(h, h_ref) and torch.equal(hm, h_ref.view(P // 32, 32, N).amax(1))
+    # and against plain fp32 arithmetic at TF32 accuracy
+    ref = torch.relu(a.double() @ w.double().t() + gb.double().repeat_interleave(32, 0))
+    assert rel_err(h.double(), ref) < 2e-3
