@@ -190,12 +190,23 @@ class Group(nn.Module):
         self.num_group = num_group
         self.group_size = group_size
 
-    def forward(self, xyz):
-        """xyz (B, N, 3) -> (neighborhood (B,G,M,3) centred, center (B,G,3), neighborhood_org (B,G,M,3))."""
+    def centers(self, xyz):
+        """The FPS half of forward(): xyz (B, N, 3) -> center (B, G, 3).  Callers that overlap work which only needs the
+        centres (the spectral kernel) with the kNN grouping call centers() and patches() separately."""
         center, _ = ops.fps(xyz, self.num_group)
+        return center
+
+    def patches(self, xyz, center):
+        """The kNN half of forward(): -> (neighborhood centred, neighborhood_org)."""
         idx, neighborhood, neighborhood_org = ops.knn_group(xyz, center, self.group_size)
         assert idx.size(1) == self.num_group
         assert idx.size(2) == self.group_size
+        return neighborhood, neighborhood_org
+
+    def forward(self, xyz):
+        """xyz (B, N, 3) -> (neighborhood (B,G,M,3) centred, center (B,G,3), neighborhood_org (B,G,M,3))."""
+        center = self.centers(xyz)
+        neighborhood, neighborhood_org = self.patches(xyz, center)
         return neighborhood, center, neighborhood_org
 
 
@@ -450,16 +461,20 @@ class PointMamba(nn.Module):
         if use_wavelets:
             raise NotImplementedError("use_wavelets is broken at the reference HEAD (point_mamba.py:879) and out of scope")
         batch_size = pts.size(0)
-        neighborhood, center, neighborhood_org = self.group_divider(pts)
         spec = None
-        if self.method == "SAST" and pts.is_cuda:
-            # the spectral kernel only needs the centres: run it on a side stream next to the Encoder GEMMs
-            # (it occupies B of the 148 SMs for ~0.3 ms); both branches are captured by a CUDA graph as a fork/join
+        if self.method == "SAST" and pts.is_cuda and isinstance(self.group_divider, Group):
+            # the spectral kernel only needs the centres: fork it onto a side stream right after FPS, next to the kNN grouping,
+            # the Encoder GEMMs and pos_embed (it occupies B of the 148 SMs for ~0.3 ms, longer than all of those together);
+            # both branches are captured by a CUDA graph as a fork / join
+            center = self.group_divider.centers(pts)
             cur = torch.cuda.current_stream()
             side = _side_stream(pts.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 spec = self.spectral_order(center)
+            neighborhood, neighborhood_org = self.group_divider.patches(pts, center)
+        else:
+            neighborhood, center, neighborhood_org = self.group_divider(pts)
         group_input_tokens = self.encoder(neighborhood)
         pos = self._pos_embed(center)
         if spec is not None:
