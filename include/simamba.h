@@ -287,6 +287,12 @@ int sim_gemm_tf32_group(const float* A, long lda, const float* B, long ldb, floa
                         const float* bias, const float* gbias, long ld_gbias, int relu, float* gmax, long ld_gmax,
                         sim_stream_t stream);
 
+/* a-10  sim_gemm_bf16 (K-major operands, no split-K) whose output columns >= silu_col0 leave as silu(v), computed on the fp32
+ * accumulator before the rounding to bf16: in_proj of the bf16 (autocast) inference mixer hands the scan the gate silu(z)
+ * (pair with bit 1 of sim_selective_scan_fwd's delta_softplus), as sim_gemm_planes act_mode 1 does for fp32. */
+int sim_gemm_bf16_silu(const void* A, long lda, const void* B, long ldb, void* Y, long ldy, int out_bf16, int M, int N, int K,
+                       int silu_col0, sim_stream_t stream);
+
 /* a-10  the same fp32-accurate projection from PRE-SPLIT operands (hand-written TMA + tcgen05 + TMEM kernel,
  * csrc/gemm_split3.cu).  sim_split3_bf16 writes x = x0 + x1 + x2 as three bf16 planes (plane q at out + q * plane
  * elements, row stride ldo); the weights are split once per model, activations by their producer.

@@ -47,6 +47,7 @@ SIGNATURES = {
     "sim_point_linear3": (_i, [_p, _p, _p, _p, _l, _i, _i, _p]),
     "sim_gemm_tf32": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
     "sim_gemm_tf32_group": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _p, _l, _i, _p, _l, _p]),
+    "sim_gemm_bf16_silu": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _i, _p]),
     "sim_argsort_rows": (_i, [_p, _l, _l, _i, _i, _p, _p, _p]),
     "sim_order_gather_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sim_order_gather_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

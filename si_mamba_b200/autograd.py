@@ -230,6 +230,14 @@ def mamba_inner_tm(hidden, in_proj_w, conv_w, conv_b, x_proj_w, dt_proj_w, dt_pr
         wp = _CACHE.get(in_proj_w, "x2h", ops.split2h) if f16 else _CACHE.get(in_proj_w, "x3", ops.split3)
         xz = ops.linear_f32_x3(hidden, wp, in_proj_w.shape[1], act="silu_from" if hoist_z else None, act_col0=d_inner)
         x, z = xz[..., :d_inner], xz[..., d_inner:]
+    elif own_bf16 and not need_grad and _HOIST_ACT in ("z", "zdt") and not _FUSE_DT:
+        # bf16 inference: the same hoist - in_proj's epilogue turns the z half into the gate (silu on the fp32 accumulator,
+        # then the bf16 rounding), the scan multiplies by it as is
+        hb = hidden.to(act)
+        h2 = hb.reshape(-1, hb.shape[-1]) if hb.is_contiguous() else ops._as_rows(hb)
+        xz = ops.gemm_bf16(h2, w_in, silu_col0=d_inner).view(*hb.shape[:-1], 2 * d_inner)
+        x, z = xz[..., :d_inner], xz[..., d_inner:]
+        hoist_z = True
     else:
         xz = linear(hidden if isinstance(hidden, ops.Split3) else hidden.to(act), w_in)  # (B, L, 2*d_inner)
         if need_grad:

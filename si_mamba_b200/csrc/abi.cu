@@ -125,6 +125,11 @@ int sim_gemm_tf32_group(const float* A, long lda, const float* B, long ldb, floa
                               static_cast<cudaStream_t>(stream));
 }
 
+int sim_gemm_bf16_silu(const void* A, long lda, const void* B, long ldb, void* Y, long ldy, int out_bf16, int M, int N, int K,
+                       int silu_col0, sim_stream_t stream) {
+  return sim::gemm_bf16_silu(A, lda, B, ldb, Y, ldy, out_bf16, M, N, K, silu_col0, static_cast<cudaStream_t>(stream));
+}
+
 int sim_pairwise_dist_mean(const float* center, int B, int G, double* partial, float* sigma, sim_stream_t stream) {
   return sim::pairwise_dist_mean(center, B, G, partial, sigma, static_cast<cudaStream_t>(stream));
 }

@@ -142,6 +142,7 @@ struct Epi {
   long ld_gbias = 0;
   float* gmax = nullptr;
   long ld_gmax = 0;
+  int silu_col0 = -1;  // >= 0: columns from here on leave as silu(v) (in_proj hands the scan the gate, see gemm_split3.cu EpiAct)
 };
 constexpr int kGroupRows = 32;
 __device__ __forceinline__ float4 apply_epi(float4 o, const Epi& e, int gn) {
@@ -150,6 +151,7 @@ __device__ __forceinline__ float4 apply_epi(float4 o, const Epi& e, int gn) {
     o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
   }
   if (e.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+  if (e.silu_col0 >= 0 && gn >= e.silu_col0) o = make_float4(silu_f(o.x), silu_f(o.y), silu_f(o.z), silu_f(o.w));
   return o;
 }
 
@@ -574,7 +576,7 @@ int dispatch(const Problem& q, int bn, cudaStream_t stream) {
 template <bool TF32>
 int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
              int N, int K, int splits, const float* bias, int relu, cudaStream_t stream, const float* gbias = nullptr,
-             long ld_gbias = 0, float* gmax = nullptr, long ld_gmax = 0) {
+             long ld_gbias = 0, float* gmax = nullptr, long ld_gmax = 0, int silu_col0 = -1) {
   constexpr int ES = El<TF32>::ES, BK = El<TF32>::BK;
   const bool grouped = gbias != nullptr || gmax != nullptr;
   SIM_REQUIRE(A && B && (Y || gmax) && M > 0 && N > 0 && K > 0, SIM_ERR_INVALID, "gemm_tc: empty problem / null tensor");
@@ -613,6 +615,9 @@ int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_m
   q.Y = Y, q.ldd = ldd, q.M = M, q.N = N, q.K = K, q.out_bf16 = out_bf16, q.splits = splits;
   q.epi.bias = bias, q.epi.relu = relu;
   q.epi.gbias = gbias, q.epi.ld_gbias = ld_gbias, q.epi.gmax = gmax, q.epi.ld_gmax = ld_gmax;
+  SIM_REQUIRE(silu_col0 < 0 || (silu_col0 % 4 == 0 && splits == 1 && !grouped), SIM_ERR_INVALID,
+              "gemm_tc: the silu epilogue starts at a multiple of 4 columns and excludes split-K / the per-patch epilogue");
+  q.epi.silu_col0 = silu_col0;
   int rc;
   if (a_mn) rc = make_tmap_2d(&q.tm.a, A, M, K, lda, BK, TF32); else rc = make_tmap_2d(&q.tm.a, A, K, M, lda, kBM, TF32);
   if (rc) return rc;
@@ -639,6 +644,12 @@ int gemm_any(const void* A, long lda, int a_mn, const void* B, long ldb, int b_m
 int gemm_bf16(const void* A, long lda, int a_mn, const void* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,
               int N, int K, int splits, cudaStream_t stream) {
   return gemm_any<false>(A, lda, a_mn, B, ldb, b_mn, Y, ldd, out_bf16, M, N, K, splits, nullptr, 0, stream);
+}
+
+// gemm_bf16 (K-major operands) whose columns >= silu_col0 leave as silu(v): in_proj of the bf16 inference mixer
+int gemm_bf16_silu(const void* A, long lda, const void* B, long ldb, void* Y, long ldd, int out_bf16, int M, int N, int K,
+                   int silu_col0, cudaStream_t stream) {
+  return gemm_any<false>(A, lda, 0, B, ldb, 0, Y, ldd, out_bf16, M, N, K, 1, nullptr, 0, stream, nullptr, 0, nullptr, 0, silu_col0);
 }
 
 int gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, void* Y, long ldd, int out_bf16, int M,

@@ -76,6 +76,8 @@ int gemm_tf32(const float* A, long lda, int a_mn, const float* B, long ldb, int 
               int N, int K, int splits, const float* bias, int relu, cudaStream_t stream);
 int gemm_tf32_group(const float* A, long lda, const float* B, long ldb, float* Y, long ldd, int M, int N, int K, const float* bias,
                     const float* gbias, long ld_gbias, int relu, float* gmax, long ld_gmax, cudaStream_t stream);
+int gemm_bf16_silu(const void* A, long lda, const void* B, long ldb, void* Y, long ldd, int out_bf16, int M, int N, int K,
+                   int silu_col0, cudaStream_t stream);
 int causal_conv1d_bwd(const void*, long, const float*, const float*, const void*, long, void*, long, float*, float*,
                       int, int, int, int, int, int, cudaStream_t);
 

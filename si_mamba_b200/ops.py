@@ -704,7 +704,8 @@ def _gemm_operand(t: torch.Tensor) -> torch.Tensor:
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False,
-              out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None, splits: int = 1) -> torch.Tensor:
+              out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None, splits: int = 1,
+              silu_col0: Optional[int] = None) -> torch.Tensor:
     """Y = op(a) @ op(b).T on the tcgen05 bf16 kernel (sim_gemm_bf16).  a: (M,K), or (K,M) when ``a_mn``; b: (N,K), or (K,N)
     when ``b_mn`` - row-major views with a uniform row stride are read in place.  ``splits`` = 0: automatic split-K into an
     fp32 result (weight gradients)."""
@@ -718,6 +719,11 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     if out is None:
         out = (torch.zeros if splits != 1 else torch.empty)(M, N, dtype=out_dtype, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    if silu_col0 is not None:  # inference in_proj: columns >= silu_col0 (the z half) leave as silu(z)
+        assert not a_mn and not b_mn and splits == 1
+        _lib.call("sim_gemm_bf16_silu", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0),
+                  int(out.dtype == torch.bfloat16), M, N, K, int(silu_col0), _stream())
+        return out
     _lib.call("sim_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out), out.stride(0),
               int(out.dtype == torch.bfloat16), M, N, K, int(splits), _stream())
     return out

@@ -784,3 +784,16 @@ def test_gemm_tf32_group_epilogue(ops, P, N, K):
     # and against plain fp32 arithmetic at TF32 accuracy
     ref = torch.relu(a.double() @ w.double().t() + gb.double().repeat_interleave(32, 0))
     assert rel_err(h.double(), ref) < 2e-3
+
+
+def test_gemm_bf16_silu_epilogue(ops):
+    """bf16 in_proj whose z half leaves as silu(z) (sim_gemm_bf16_silu): silu on the fp32 accumulator, then the bf16 rounding."""
+    g = torch.Generator().manual_seed(21)
+    M, N, K = 4096, 1536, 384
+    x = dev(torch.randn(M, K, generator=g)).bfloat16()
+    w = dev(torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    y0 = ops.gemm_bf16(x, w)
+    y1 = ops.gemm_bf16(x, w, silu_col0=N // 2)
+    assert torch.equal(y0[:, :N // 2], y1[:, :N // 2])
+    ref = torch.nn.functional.silu(x.double() @ w.double().t())[:, N // 2:]
+    assert rel_err(y1[:, N // 2:].double(), ref) < 8e-3  # one bf16 rounding of the result
