@@ -370,10 +370,9 @@ struct GemmPCfg {
   static constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
   static constexpr int CW = BN / 2;                   // columns per epilogue warp
   // accumulator sets in TMEM (each = leading + correction accumulator, 2 BN columns): two when they fit (BN <= 128), so the
-  // MMAs of tile i + 1 start while tile i is still being drained.  ncu on the single-set kernel (profiles/r02_gemm_ncu.md):
-  // the tensor pipe idles ~3 us per tile between the last MMA of a tile and the first of the next (commit -> epilogue
-  // wake-up -> six dependent tcgen05.ld -> release -> MMA warp wake-up), 29 % of the bf16 x 3 in_proj and 49 % of the
-  // fp16 x 2 one.
+  // MMAs of tile i + 1 can start while tile i is still being drained.  Measured with 128-wide tiles (profiles/r02_gemm_ncu.md):
+  // slower than 192-wide tiles with one set, by the extra operand bytes per flop - the kernel is ingest-bound, not
+  // turn-around-bound - so no 128-wide persistent instance is dispatched and NACC is 1 in every built kernel.
   static constexpr int NACC = 4 * BN <= 512 ? 2 : 1;
   static_assert(CW % 32 == 0 && 2 * BN <= 512, "two column halves of whole 32-column chunks; both accumulators in TMEM");
   static_assert(SMEM <= 232448, "shared memory budget");
