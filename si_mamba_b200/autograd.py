@@ -1,6 +1,8 @@
 """Wiring of the mixer body: ``mamba_inner_tm`` is the token-major equivalent of mamba-ssm's ``mamba_inner_fn``
-(in_proj -> causal conv1d + SiLU -> x_proj -> dt_proj -> selective scan -> out_proj) with the GEMMs on cuBLAS
-(tensor cores) and conv / scan on the hand-written kernels, through autograd nodes when a graph is needed.
+(in_proj -> causal conv1d + SiLU -> x_proj -> dt_proj -> selective scan -> out_proj), every stage on the hand-written
+kernels - the projections on the tcgen05 GEMMs (fp32: split planes, csrc/gemm_split3.cu; bf16 autocast: csrc/gemm_bf16.cu),
+conv and scan on their TMA kernels - through autograd nodes when a graph is needed.  ``SIM_FP32_GEMM=cublas`` /
+``SIM_BF16_GEMM=cublas`` keep F.linear as ablation switches.
 """
 
 from __future__ import annotations
