@@ -155,3 +155,18 @@ def test_bench_generator_matches_test_generator():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     assert torch.equal(bench.synthetic_clouds(3, 256, 4321), tokenizer.synthetic_clouds(3, 256, 4321, "surface"))
+
+
+def test_docs_name_only_declared_entry_points():
+    """INTEGRATION.md / DESIGN.md / README.md map reference call sites to C-ABI entry points: every `sim_*` name they
+    quote must be declared in include/simamba.h (prefixes such as `sim_mae_compact_*` are checked as prefixes)."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    declared = set(re.findall(r"\b(sim_[a-z0-9_]+)\s*\(", (root / "include" / "simamba.h").read_text()))
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        for name in set(re.findall(r"`(sim_[a-z0-9_]+)", (root / doc).read_text())):
+            if name.endswith("_"):
+                assert any(d.startswith(name) for d in declared), (doc, name)
+            else:
+                assert name in declared or any(d.startswith(name + "_") for d in declared), (doc, name)
