@@ -227,3 +227,35 @@ def test_mae_index_maps_torch_consistency():
     for b in range(B):
         vis_rows = rs[b][rs[b] >= 0]
         assert torch.equal(vis_rows, torch.arange(vis_rows.numel()))  # visible rows appear in encoder order
+
+
+def test_f16x2_plane_format_error_model():
+    """The operand format of in_proj on the fp32 inference path (csrc/gemm_split3.cu, NP = 2): x = x0 + 2^-11 x1' with
+    x0 = fp16(x), x1' = fp16(2^11 (x - x0)), three products x0.w0 + 2^-11 (x0.w1' + x1'.w0).  Emulated here with exact (fp64)
+    accumulation: the representation error is ~1e-7 of the result norm, below an fp32 GEMM's own accumulation error, and
+    it needs |x| < 65504 - which is why the host only selects it for LayerNorm outputs (autograd.inproj_f16_ok)."""
+    g = torch.Generator().manual_seed(0)
+    M, K, N = 256, 384, 192
+    x = torch.randn(M, K, generator=g) * 3.0
+    x[0, 0] = 2.9e4                     # top of the admitted range
+    x[1, :8] = 1e-6                     # far below the fp16 normal range: absolute error stays negligible
+    w = torch.randn(N, K, generator=g) * 0.05
+    ref = x.double() @ w.double().t()
+
+    def split(t):
+        t0 = t.half().float()
+        return t0.double(), ((t - t0) * 2048.0).half().double()
+
+    x0, x1 = split(x)
+    w0, w1 = split(w)
+    assert torch.isfinite(x0).all() and torch.isfinite(x1).all()
+    y = x0 @ w0.t() + (x0 @ w1.t() + x1 @ w0.t()) / 2048.0
+    err = ((y - ref).norm() / ref.norm()).item()
+    fp32_err = (((x @ w.t()).double() - ref).norm() / ref.norm()).item()
+    assert err < 2e-7 and err < fp32_err, (err, fp32_err)
+    # planes reconstruct the operand to 2^-22 relative (plus 2^-36 absolute in the subnormal tail)
+    rec = x0 + x1 / 2048.0
+    assert ((rec - x.double()).abs() <= x.double().abs() * 2.0 ** -21 + 2.0 ** -35).all()
+    # outside the range the format breaks (inf) - the bf16 x 3 planes keep the fp32 exponent and do not
+    big = torch.tensor([7.0e4])
+    assert torch.isinf(big.half()).all() and torch.isfinite(big.bfloat16().float()).all()
